@@ -1,0 +1,45 @@
+"""Shared test utilities: fixture loading and oracle construction."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import advchain_oracle as orc
+from tests.golden.cases import CASES, stage_cfgs
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    arrays = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    return meta, arrays
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| -- the normwise metric of SURVEY.md section 8c."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    den = b.abs().max().item()
+    return (a - b).abs().max().item() / (den if den > 0 else 1.0)
+
+
+def make_model(case, arrays, device="cpu"):
+    conv = torch.nn.Conv2d if case["d"] == 2 else torch.nn.Conv3d
+    m = conv(case["size"][1], case["K"], 3, 1, 1)
+    with torch.no_grad():
+        m.weight.copy_(arrays["model_w"])
+        m.bias.copy_(arrays["model_b"])
+    return m.eval().to(device)
+
+
+def oracle_solver(case, size=None):
+    size = size or case["size"]
+    cfgs = stage_cfgs(case["d"], size, vector=case.get("vector"))
+    pad = case.get("padding", "zeros")
+    stages = []
+    for n in case["chain"]:
+        kw = {"padding": pad} if n in ("morph", "affine") else {}
+        stages.append(orc.make_stage(n, cfgs[n], **kw))
+    return orc.Solver(stages, if_norm_image=True)
