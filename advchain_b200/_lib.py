@@ -1,0 +1,139 @@
+"""ctypes binding of libadvchain_b200.so (the C ABI declared in include/advk.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the
+product path raises.  PyTorch is used only for device memory, streams and autograd plumbing;
+every device computation of the hot path goes through the `advk_*` entry points.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadvchain_b200.so")
+ABI_VERSION = 1
+
+PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
+INTERP_LINEAR, INTERP_NEAREST = 0, 1
+UPD_L2_ASCENT, UPD_SIGN_ASCENT, UPD_L2_POWER, UPD_SIGN_POWER = 0, 1, 2, 3
+
+
+class Geom(C.Structure):
+    _fields_ = [("d", C.c_int), ("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+class AffineCfg(C.Structure):
+    _fields_ = [("d", C.c_int), ("rot", C.c_float * 3), ("scale", C.c_float * 3),
+                ("shift", C.c_float * 3)]
+
+
+class MorphCfg(C.Structure):
+    _fields_ = [("lr", C.c_int * 3), ("ktaps", C.c_int), ("gauss", C.c_float * 15)]
+
+
+class BiasCfg(C.Structure):
+    _fields_ = [("n_cp", C.c_int * 3), ("low", C.c_int * 3), ("A", C.c_void_p * 3),
+                ("up_scale", C.c_float * 3), ("upsample", C.c_int), ("use_log", C.c_int),
+                ("magnitude", C.c_float)]
+
+
+_P = C.c_void_p
+_F = C.c_float
+_I = C.c_int
+_Z = C.c_size_t
+_G = C.POINTER(Geom)
+
+# name -> (restype, argtypes); mirrors include/advk.h one to one
+SIGNATURES = {
+    "advk_abi_version": (_I, []),
+    "advk_last_error": (C.c_char_p, []),
+    "advk_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_Z)]),
+    "advk_affine_theta_fwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P]),
+    "advk_affine_theta_bwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P, _P]),
+    "advk_warp_affine_fwd": (_I, [_G, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "advk_warp_affine_bwd": (_I, [_G, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "advk_warp_field_fwd": (_I, [_G, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "advk_warp_field_bwd": (_I, [_G, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "advk_morph_unorm2": (_I, [_G, C.POINTER(MorphCfg), _P, _F, _P, _P, _P]),
+    "advk_morph_field_fwd": (_I, [_G, C.POINTER(MorphCfg), _P, _F, _I, _P, _P, _P, _P]),
+    "advk_morph_lr_scratch_floats": (_Z, [_G, C.POINTER(MorphCfg)]),
+    "advk_morph_field_bwd": (_I, [_G, C.POINTER(MorphCfg), _F, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "advk_bias_lowfield_fwd": (_I, [C.POINTER(BiasCfg), _I, _P, _F, _P, _P]),
+    "advk_bias_lowfield_bwd": (_I, [C.POINTER(BiasCfg), _I, _P, _F, _P, _P]),
+    "advk_intensity_fwd": (_I, [_G, _I, _I, _P, _P, _F, _P, C.POINTER(BiasCfg), _I, _F, _P, _P, _P]),
+    "advk_intensity_bwd": (_I, [_G, _I, _I, _P, _P, _P, _F, _P, C.POINTER(BiasCfg), _I, _F, _P, _P,
+                                _P, _P]),
+    "advk_bias_scratch_floats": (_Z, [_G, C.POINTER(BiasCfg)]),
+    "advk_bias_upsample_adjoint": (_I, [_G, C.POINTER(BiasCfg), _P, _P, _P, _P]),
+    "advk_pgd_update": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P]),
+    "advk_clamp": (_I, [_P, _F, _F, _P, _Z, _P]),
+    "advk_clamp_bwd": (_I, [_P, _P, _F, _F, _P, _Z, _P]),
+    "advk_nonzero_mask": (_I, [_P, _Z, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises if it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "advchain_b200: %s not found. Build it with `python -m advchain_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.advk_abi_version() != ABI_VERSION:
+        raise RuntimeError("advchain_b200: ABI mismatch (library %d, binding %d)"
+                           % (lib.advk_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Calls an int-returning launch function; raises RuntimeError with the library's message."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.advk_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("advchain_b200 runs on CUDA tensors only (got %s); there is no CPU "
+                           "fallback" % t.device)
+    if t.dtype not in (torch.float32, torch.float64) or not t.is_contiguous():
+        raise RuntimeError("advchain_b200: expected a contiguous fp32 tensor, got %s contiguous=%s"
+                           % (t.dtype, t.is_contiguous()))
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def geom(size):
+    """size: [N, C, (D,) H, W] -> Geom (C is not part of it)."""
+    sp = list(size[2:])
+    if len(sp) == 2:
+        return Geom(2, int(size[0]), 1, int(sp[0]), int(sp[1]))
+    if len(sp) == 3:
+        return Geom(3, int(size[0]), int(sp[0]), int(sp[1]), int(sp[2]))
+    raise ValueError("only 2-D / 3-D data is supported, got size %s" % (list(size),))
+
+
+def device_info():
+    lib = load()
+    sm, ma, mi, l2 = _I(), _I(), _I(), _Z()
+    rc = lib.advk_device_info(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2))
+    if rc != 0:
+        raise RuntimeError(lib.advk_last_error().decode())
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)

@@ -1,0 +1,301 @@
+"""torch.autograd.Function wrappers around the advk_* C ABI (include/advk.h).
+
+PyTorch supplies tensors (device memory), the current stream and the autograd tape; all device
+arithmetic is in libadvchain_b200.so.  Fields are carried as fp32 tensors of shape
+[N, *spatial, 2] (2-D) or [N, *spatial, 4] (3-D, last lane unused) -- the interleaved layout
+the kernels gather from with one vector load per stencil corner.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _lib
+from .._lib import call, ptr, stream
+
+_PAD = {"zeros": _lib.PAD_ZEROS, "border": _lib.PAD_BORDER, "reflection": _lib.PAD_REFLECTION}
+_INTERP = {"bilinear": _lib.INTERP_LINEAR, "trilinear": _lib.INTERP_LINEAR,
+           "linear": _lib.INTERP_LINEAR, "nearest": _lib.INTERP_NEAREST}
+
+
+def parse_interp(interp):
+    if interp not in _INTERP:
+        raise NotImplementedError("interpolation mode %r is not supported by the CUDA path "
+                                  "(bilinear/trilinear/nearest are)" % (interp,))
+    return _INTERP[interp]
+
+
+def parse_padding(padding_mode, data):
+    """-> (pad_mode, per-sample pad-value tensor or None).
+    'lowest' / numeric padding = sample (x - v) with zero padding, add v back
+    (adv_affine.py:299-311, adv_morph.py:542-554).  Deviation from the reference (quirk Q13):
+    'lowest' uses the per-sample minimum for any batch size; the reference's broadcast only
+    works for N == 1."""
+    if isinstance(padding_mode, str):
+        if padding_mode == "lowest":
+            pv = data.detach().reshape(data.shape[0], -1).min(dim=1).values.float().contiguous()
+            return _lib.PAD_ZEROS, pv
+        if padding_mode not in _PAD:
+            raise ValueError("unknown padding mode %r" % (padding_mode,))
+        return _PAD[padding_mode], None
+    if isinstance(padding_mode, (int, float)) and not isinstance(padding_mode, bool):
+        pv = torch.full((data.shape[0],), float(padding_mode), dtype=torch.float32, device=data.device)
+        return _lib.PAD_ZEROS, pv
+    raise ValueError("unknown padding mode %r" % (padding_mode,))
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def field_lanes(d):
+    return 2 if d == 2 else 4
+
+
+# --------------------------------------------------------------------------------------- affine
+
+
+class AffineTheta(Function):
+    """param (N x 5|9) -> theta, theta_inv (N x d x (d+1)). adv_affine.py:210-273, 316-324."""
+
+    @staticmethod
+    def forward(ctx, param, cfg, pscale):
+        param = _f32c(param)
+        n, d = param.shape[0], cfg.d
+        theta = torch.empty(n, d, d + 1, dtype=torch.float32, device=param.device)
+        theta_inv = torch.empty_like(theta)
+        call("advk_affine_theta_fwd", C.byref(cfg), ptr(param), pscale, n, ptr(theta), ptr(theta_inv),
+             stream())
+        ctx.save_for_backward(param)
+        ctx.cfg, ctx.pscale = cfg, pscale
+        return theta, theta_inv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_theta, g_theta_inv):
+        (param,) = ctx.saved_tensors
+        g_param = torch.empty_like(param)
+        call("advk_affine_theta_bwd", C.byref(ctx.cfg), ptr(param), ctx.pscale, param.shape[0],
+             ptr(_f32c(g_theta)), ptr(_f32c(g_theta_inv)), ptr(g_param), stream())
+        return g_param, None, None
+
+
+# --------------------------------------------------------------------------------------- warps
+
+
+class WarpAffine(Function):
+    """F.affine_grid + F.grid_sample with the grid generated on the fly. adv_affine.py:297-313."""
+
+    @staticmethod
+    def forward(ctx, src, theta, pad, interp, padv):
+        src, theta = _f32c(src), _f32c(theta)
+        g = _lib.geom(src.shape)
+        out = torch.empty_like(src)
+        call("advk_warp_affine_fwd", C.byref(g), src.shape[1], ptr(src), ptr(theta), pad, interp,
+             ptr(padv), ptr(out), stream())
+        ctx.save_for_backward(src, theta, padv)
+        ctx.meta = (g, pad, interp)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_out):
+        src, theta, padv = ctx.saved_tensors
+        g, pad, interp = ctx.meta
+        g_src = torch.zeros_like(src) if ctx.needs_input_grad[0] else None
+        g_theta = torch.zeros_like(theta) if ctx.needs_input_grad[1] else None
+        if g_src is not None or g_theta is not None:
+            call("advk_warp_affine_bwd", C.byref(g), src.shape[1], ptr(_f32c(g_out)), ptr(src),
+                 ptr(theta), pad, interp, ptr(padv), ptr(g_src), ptr(g_theta), stream())
+        return g_src, g_theta, None, None, None
+
+
+class WarpField(Function):
+    """F.grid_sample with a dense interleaved field. adv_morph.py:546-557."""
+
+    @staticmethod
+    def forward(ctx, src, field, pad, interp, padv):
+        src = _f32c(src)
+        g = _lib.geom(src.shape)
+        out = torch.empty_like(src)
+        call("advk_warp_field_fwd", C.byref(g), src.shape[1], ptr(src), ptr(field), pad, interp,
+             ptr(padv), ptr(out), stream())
+        ctx.save_for_backward(src, field, padv)
+        ctx.meta = (g, pad, interp)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_out):
+        src, field, padv = ctx.saved_tensors
+        g, pad, interp = ctx.meta
+        g_src = torch.zeros_like(src) if ctx.needs_input_grad[0] else None
+        g_field = torch.empty_like(field) if ctx.needs_input_grad[1] else None
+        if g_src is not None or g_field is not None:
+            call("advk_warp_field_bwd", C.byref(g), src.shape[1], ptr(_f32c(g_out)), ptr(src),
+                 ptr(field), pad, interp, ptr(padv), ptr(g_src), ptr(g_field), stream())
+        return g_src, g_field, None, None, None
+
+
+# --------------------------------------------------------------------------------------- morph
+
+
+def morph_unorm2(v, size, cfg, scale):
+    """||upsample(G * (scale v))||_F^2 over the batch -- a device scalar (adv_morph.py:159-162)."""
+    v = _f32c(v)
+    g = _lib.geom(size)
+    u_lr = torch.empty_like(v)
+    out = torch.empty(1, dtype=torch.float32, device=v.device)
+    call("advk_morph_unorm2", C.byref(g), C.byref(cfg), ptr(v), float(scale), ptr(u_lr), ptr(out),
+         stream())
+    return out
+
+
+class MorphField(Function):
+    """velocity -> (unclamped) deformation field; DemonsCompose, adv_morph.py:454-491."""
+
+    @staticmethod
+    def forward(ctx, v, size, cfg, scale, nb_steps):
+        v = _f32c(v)
+        g = _lib.geom(size)
+        lanes = field_lanes(g.d)
+        spatial = tuple(size[2:])
+        nvox = g.N * g.D * g.H * g.W
+        u_lr = torch.empty_like(v)
+        levels = torch.empty((nb_steps + 1) * nvox * lanes, dtype=torch.float32, device=v.device)
+        field = torch.empty((g.N,) + spatial + (lanes,), dtype=torch.float32, device=v.device)
+        call("advk_morph_field_fwd", C.byref(g), C.byref(cfg), ptr(v), float(scale), nb_steps,
+             ptr(u_lr), ptr(levels), ptr(field), stream())
+        ctx.save_for_backward(levels, field)
+        ctx.meta = (g, cfg, float(scale), nb_steps, v.shape)
+        return field
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_field):
+        levels, field = ctx.saved_tensors
+        g, cfg, scale, nb, vshape = ctx.meta
+        g_field = _f32c(g_field)
+        scratch = torch.empty(3 * field.numel(), dtype=torch.float32, device=field.device)
+        nlr = _lib.load().advk_morph_lr_scratch_floats(C.byref(g), C.byref(cfg))
+        lr_scratch = torch.empty(nlr, dtype=torch.float32, device=field.device)
+        g_v = torch.empty(vshape, dtype=torch.float32, device=field.device)
+        call("advk_morph_field_bwd", C.byref(g), C.byref(cfg), scale, nb, ptr(levels), ptr(field),
+             ptr(g_field), ptr(scratch), ptr(lr_scratch), ptr(g_v), stream())
+        return g_v, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------- intensity
+
+ORDER_NOISE, ORDER_BIAS, ORDER_NOISE_BIAS, ORDER_BIAS_NOISE = 0, 1, 2, 3
+
+
+class Intensity(Function):
+    """AdvNoise / AdvBias stage(s): adv_noise.py:79-90, adv_bias.py:152-188, 279-356.
+    `plan` is a BiasPlan (geometry + device matrices) or None for noise only."""
+
+    @staticmethod
+    def forward(ctx, x, delta, cp, order, noise_scale, plan, cp_scale, ignore):
+        x = _f32c(x)
+        g = _lib.geom(x.shape)
+        low = None
+        cfg_ref = None
+        if order != ORDER_NOISE:
+            cp = _f32c(cp)
+            cfg_ref = C.byref(plan.cfg(x.device))
+            low = torch.empty((g.N,) + tuple(plan.low_size), dtype=torch.float32, device=x.device)
+            call("advk_bias_lowfield_fwd", cfg_ref, g.N, ptr(cp), float(cp_scale), ptr(low), stream())
+        if order != ORDER_BIAS:
+            delta = _f32c(delta)
+        out = torch.empty_like(x)
+        use_ig = 0 if ignore is None else 1
+        call("advk_intensity_fwd", C.byref(g), x.shape[1], order, ptr(x),
+             ptr(delta) if order != ORDER_BIAS else None, float(noise_scale), ptr(low), cfg_ref,
+             use_ig, float(ignore or 0.0), ptr(out), None, stream())
+        ctx.save_for_backward(x, delta if order != ORDER_BIAS else None, low)
+        ctx.meta = (g, order, float(noise_scale), plan, float(cp_scale), use_ig, float(ignore or 0.0),
+                    None if cp is None else cp.shape)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_out):
+        x, delta, low = ctx.saved_tensors
+        g, order, ns, plan, cp_scale, use_ig, ig, cp_shape = ctx.meta
+        need_x, need_d, need_cp = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_d = need_d and order != ORDER_BIAS
+        need_cp = need_cp and order != ORDER_NOISE
+        g_x = torch.empty_like(x) if need_x else None
+        g_delta = torch.empty_like(x) if need_d else None
+        nvox = g.N * g.D * g.H * g.W
+        g_up = torch.empty(nvox, dtype=torch.float32, device=x.device) if need_cp else None
+        cfg_ref = C.byref(plan.cfg(x.device)) if order != ORDER_NOISE else None
+        call("advk_intensity_bwd", C.byref(g), x.shape[1], order, ptr(_f32c(g_out)), ptr(x), ptr(delta),
+             ns, ptr(low), cfg_ref, use_ig, ig, ptr(g_x), ptr(g_delta), ptr(g_up), stream())
+        g_cp = None
+        if need_cp:
+            lib = _lib.load()
+            ns_ = lib.advk_bias_scratch_floats(C.byref(g), cfg_ref)
+            scratch = torch.empty(max(int(ns_), 1), dtype=torch.float32, device=x.device)
+            g_low = torch.empty_like(low)
+            call("advk_bias_upsample_adjoint", C.byref(g), cfg_ref, ptr(g_up), ptr(scratch), ptr(g_low),
+                 stream())
+            g_cp = torch.empty(cp_shape, dtype=torch.float32, device=x.device)
+            call("advk_bias_lowfield_bwd", cfg_ref, g.N, ptr(g_low), cp_scale, ptr(g_cp), stream())
+        return g_x, g_delta, g_cp, None, None, None, None, None
+
+
+def bias_field_only(cp, plan, size, cp_scale=1.0):
+    """The clipped bias field N x 1 x spatial (the reference's `bias_field` attribute)."""
+    cp = _f32c(cp.detach())
+    g = _lib.geom(size)
+    dev = cp.device
+    cfg_ref = C.byref(plan.cfg(dev))
+    low = torch.empty((g.N,) + tuple(plan.low_size), dtype=torch.float32, device=dev)
+    call("advk_bias_lowfield_fwd", cfg_ref, g.N, ptr(cp), float(cp_scale), ptr(low), stream())
+    ones = torch.ones((g.N, 1) + tuple(size[2:]), dtype=torch.float32, device=dev)
+    out = torch.empty_like(ones)
+    call("advk_intensity_fwd", C.byref(g), 1, ORDER_BIAS, ptr(ones), None, 0.0, ptr(low), cfg_ref, 0, 0.0,
+         ptr(out), None, stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------- glue
+
+
+class Clamp(Function):
+    """torch.clamp(x, lo, hi) of solver.forward (adv_compose_solver.py:167-175)."""
+
+    @staticmethod
+    def forward(ctx, x, lo, hi):
+        x = _f32c(x)
+        out = torch.empty_like(x)
+        call("advk_clamp", ptr(x), float(lo), float(hi), ptr(out), x.numel(), stream())
+        ctx.save_for_backward(x)
+        ctx.lohi = (float(lo), float(hi))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_out):
+        (x,) = ctx.saved_tensors
+        g_x = torch.empty_like(x)
+        call("advk_clamp_bwd", ptr(_f32c(g_out)), ptr(x), ctx.lohi[0], ctx.lohi[1], ptr(g_x), x.numel(),
+             stream())
+        return g_x, None, None
+
+
+def nonzero_mask_(t):
+    """t = (t != 0) in place (adv_compose_solver.py:325)."""
+    call("advk_nonzero_mask", ptr(t), t.numel(), stream())
+    return t
+
+
+def pgd_update_(param, grad, step, mode):
+    """In-place PGD update of a parameter tensor; see ADVK_UPD_* in include/advk.h."""
+    n = param.shape[0]
+    per = param.numel() // n
+    ss = torch.empty(n, dtype=torch.float64, device=param.device)
+    call("advk_pgd_update", ptr(param), ptr(_f32c(grad)), float(step), mode, n, per, ptr(ss), stream())
+    return param

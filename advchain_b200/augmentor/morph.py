@@ -1,0 +1,232 @@
+"""AdvMorph -- adversarial diffeomorphic-style deformation. Drop-in for
+advchain.augmentor.adv_morph.AdvMorph (adv_morph.py:204-567).
+
+The deformation-field build (DemonsCompose) runs in advk_morph_field_fwd/bwd; image / prediction
+warps in advk_warp_field_fwd/bwd.  The field for +eps*v and the one for -eps*v are each built
+ONCE per parameter value and cached (the reference rebuilds both twice per PGD step: forward,
+warp-back, and the two passes of the valid-region mask, adv_compose_solver.py:314-324).
+"""
+import logging
+import math
+import weakref
+
+import numpy as np
+import torch
+
+from .. import _lib
+from . import _ops
+from .base import AdvTransformBase
+
+logger = logging.getLogger(__name__)
+
+
+def gaussian_taps(sigma=1.0, kernel_size=5):
+    """1-D factor of the reference's sum-normalised Gaussian (adv_morph.py:391-421): the d-dim
+    kernel exp(-|r|^2/(2 sigma^2))/sum is exactly the outer product of e_i / sum(e)."""
+    if kernel_size <= 2 * int(4 * sigma + 0.5) + 1:
+        kernel_size = 2 * int(4 * sigma + 0.5) + 1
+    r = np.arange(kernel_size, dtype=np.float64) - (kernel_size - 1) / 2.0
+    e = np.exp(-(r ** 2) / (2.0 * sigma ** 2))
+    return (e / e.sum()).astype(np.float32)
+
+
+def get_base_grid(batch_size, image_height, image_width, image_depth=None, device=torch.device('cuda')):
+    """Identity sampling grid, channel-first, channel 0 = x = last axis (adv_morph.py:14-55).
+    Kept for API compatibility; the kernels generate base coordinates on the fly."""
+    sizes = [image_height, image_width] + ([] if image_depth is None else [image_depth])
+    mesh = torch.meshgrid([torch.linspace(-1, 1, s, device=device) for s in sizes], indexing='ij')
+    grid = torch.stack(mesh[::-1], 0).unsqueeze(0)
+    return grid.repeat(batch_size, *([1] * (len(sizes) + 1)))
+
+
+class AdvMorph(AdvTransformBase):
+    def __init__(self, spatial_dims=2,
+                 config_dict={'epsilon': 1.5, 'data_size': [10, 1, 8, 8], 'vector_size': [4, 4],
+                              'forward_interp': 'bilinear', 'backward_interp': 'bilinear'},
+                 power_iteration=False, device=torch.device("cuda"), image_padding_mode="zeros",
+                 use_gpu=True, debug=False):
+        super(AdvMorph, self).__init__(spatial_dims=spatial_dims, config_dict=config_dict,
+                                       use_gpu=use_gpu, debug=debug, device=device)
+        self.align_corners = True
+        self.sigma = 1
+        self.gaussian_ks = 5
+        self.smooth_iter = 1
+        self.num_steps = 8
+        # quirk Q3: the constructor overrides the configured interpolators until init_parameters()
+        self.forward_interp = 'bilinear'
+        self.backward_interp = 'bilinear'
+        self.integration_type = 'ss'
+        self.param = None
+        self.power_iteration = power_iteration
+        self.image_padding_mode = image_padding_mode
+        self._cache = {}
+        self._steps_cache = None
+        self._cfg = None
+
+    def init_config(self, config_dict):
+        self.epsilon = config_dict['epsilon']
+        self.xi = 0.5
+        self.data_size = config_dict['data_size']
+        self.vector_size = config_dict['vector_size']
+        if 'forward_interp' in config_dict:
+            self.forward_interp = config_dict['forward_interp']
+        if 'backward_interp' in config_dict:
+            self.backward_interp = config_dict['backward_interp']
+
+    # ------------------------------------------------------------------ parameters
+    def init_velocity(self, batch_size, height, width, depth=None, use_zero=False):
+        """U(-1,1) velocity, unit-L2 per sample (adv_morph.py:349-375)."""
+        shape = [batch_size, self.spatial_dims, height, width] + ([] if self.spatial_dims == 2 else [depth])
+        if use_zero:
+            velocity = torch.zeros(*shape, device=self.device)
+        else:
+            velocity = torch.rand(*shape, device=self.device) * 2 - 1
+        return self.unit_normalize(velocity)
+
+    def init_parameters(self):
+        self.init_config(self.config_dict)
+        vs = self.vector_size
+        if self.spatial_dims == 2:
+            vector = self.init_velocity(self.data_size[0], vs[0], vs[1])
+        elif self.spatial_dims == 3:
+            vector = self.init_velocity(self.data_size[0], vs[0], vs[1], vs[2])
+        else:
+            raise NotImplementedError('only 2D and 3D are supported')
+        self.param = vector
+        self._cache.clear()
+        return vector
+
+    @property
+    def base_grid(self):
+        sp = self.data_size[2:]
+        return get_base_grid(self.data_size[0], sp[0], sp[1], sp[2] if len(sp) == 3 else None, self.device)
+
+    def train(self):
+        self.is_training = True
+        if self.param is None:
+            self.init_parameters()
+        p = self.param.detach()
+        if self.power_iteration:
+            p = self.unit_normalize(p)
+        self.param = self._as_leaf(p)
+
+    def optimize_parameters(self, step_size=None):
+        if step_size is None:
+            step_size = self.step_size
+        return self._l2_step(step_size)
+
+    def rescale_parameters(self, param=None):
+        if param is None:
+            param = self.param
+        self.param = self.unit_normalize(param)
+        return self.param
+
+    # ------------------------------------------------------------------ field build
+    def _morph_cfg(self):
+        if self._cfg is None:
+            c = _lib.MorphCfg()
+            lr = [1] * (3 - self.spatial_dims) + [int(s) for s in self.param.shape[2:]]
+            taps = gaussian_taps(self.sigma, self.gaussian_ks)
+            for i in range(3):
+                c.lr[i] = lr[i]
+            c.ktaps = len(taps)
+            for i, t in enumerate(taps):
+                c.gauss[i] = float(t)
+            self._cfg = (c, tuple(self.param.shape[2:]))
+        if self._cfg[1] != tuple(self.param.shape[2:]):
+            self._cfg = None
+            return self._morph_cfg()
+        return self._cfg[0]
+
+    def _scale(self):
+        return self.xi if (self.power_iteration and self.is_training) else self.epsilon
+
+    def _valid(self, entry):
+        # an entry built with an autograd graph also serves no_grad consumers (the mask path);
+        # an entry built without one cannot serve a differentiable consumer.
+        ref, version, scale, has_graph = entry[:4]
+        p = self.param
+        need_graph = torch.is_grad_enabled() and p.requires_grad
+        return (ref() is p and version == p._version and scale == self._scale()
+                and (has_graph or not need_graph))
+
+    def _nb_steps(self):
+        """2-D: always 8. 3-D: smallest n >= 8 with ||u / 2^n||_F <= 0.5 over the whole batch
+        (adv_morph.py:159-162) -- one device reduction + one scalar read per parameter value."""
+        if self.spatial_dims == 2:
+            return self.num_steps
+        e = self._steps_cache
+        if e is not None and e[0]() is self.param and e[1] == self.param._version and e[2] == self._scale():
+            return e[3]
+        n2 = _ops.morph_unorm2(self.param.detach(), self.data_size, self._morph_cfg(), self._scale())
+        norm = math.sqrt(float(n2.item()))
+        n = self.num_steps
+        while norm / (2.0 ** n) > 0.5:
+            n += 1
+        self._steps_cache = (weakref.ref(self.param), self.param._version, self._scale(), n)
+        return n
+
+    def _field(self, sign):
+        """Cached (unclamped) deformation field for duv = sign * scale * param, [N, *spatial, 2|4]."""
+        e = self._cache.get(sign)
+        if e is not None and self._valid(e):
+            return e[4]
+        p = self.param
+        field = _ops.MorphField.apply(p, self.data_size, self._morph_cfg(), sign * self._scale(),
+                                      self._nb_steps())
+        self._cache[sign] = (weakref.ref(p), p._version, self._scale(),
+                             torch.is_grad_enabled() and p.requires_grad, field)
+        return field
+
+    def get_deformation_displacement_field(self, duv=None):
+        """API compatibility (adv_morph.py:339-347): returns (dxy N x d x spatial, disp N x spatial x d)
+        for duv = +scale*param; `duv` overrides are not supported on the device path."""
+        if duv is not None:
+            raise NotImplementedError("pass parameters through set_parameters(); explicit duv is not supported")
+        d = self.spatial_dims
+        f = torch.clamp(self._field(+1).detach()[..., :d], -1, 1)
+        dxy = f.permute(0, d + 1, *range(1, d + 1)).contiguous()
+        disp = f - self.base_grid.permute(0, *range(2, d + 2), 1)
+        return dxy, disp
+
+    @property
+    def displacement(self):
+        return self.get_deformation_displacement_field()[1]
+
+    # ------------------------------------------------------------------ warps
+    def transform(self, data, field, interp=None, padding_mode=None):
+        if padding_mode is None:
+            padding_mode = self.image_padding_mode
+        if interp is None:
+            interp = self.forward_interp
+        pad, padv = _ops.parse_padding(padding_mode, data)
+        return _ops.WarpField.apply(data, field, pad, _ops.parse_interp(interp), padv)
+
+    def forward(self, data, interp=None, padding_mode=None):
+        """adv_morph.py:285-311."""
+        if self.param is None:
+            self.init_parameters()
+        if interp is None:
+            interp = self.forward_interp
+        out = self.transform(data, self._field(+1), interp=interp, padding_mode=padding_mode)
+        src = data
+        self.diff = lambda: out.detach() - src
+        return out
+
+    def backward(self, data, interp=None, padding_mode=None):
+        """Warp with the field built from -eps*v (adv_morph.py:313-331) -- not a numerical inverse."""
+        if interp is None:
+            interp = self.backward_interp
+        return self.transform(data, self._field(-1), interp=interp, padding_mode=padding_mode)
+
+    def predict_forward(self, data, interp=None, padding_mode=None):
+        return self.forward(data, interp=interp, padding_mode=padding_mode)
+
+    def predict_backward(self, data, interp=None, padding_mode=None):
+        return self.backward(data, interp=interp, padding_mode=padding_mode)
+
+    def get_name(self):
+        return 'morph'
+
+    def is_geometric(self):
+        return 1

@@ -1,0 +1,165 @@
+// advk_common.cuh -- shared device helpers: geometry, base coordinates, grid_sample index
+// math (ATen semantics, align_corners=True), linear-upsample index math (align_corners=False),
+// warp/block reductions, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/advk.h"
+
+namespace advk {
+
+typedef long long i64;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define ADVK_REQUIRE(cond, msg)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      advk::set_error("%s: %s", __func__, msg); \
+      return ADVK_ERR_ARG;                      \
+    }                                           \
+  } while (0)
+
+struct Dims {
+  int N, D, H, W;
+  i64 S;  // D*H*W
+};
+
+inline bool make_dims(const advk_geom* g, Dims& o) {
+  if (!g || (g->d != 2 && g->d != 3) || g->N < 1 || g->D < 1 || g->H < 1 || g->W < 1) return false;
+  if (g->d == 2 && g->D != 1) return false;
+  o.N = g->N; o.D = g->D; o.H = g->H; o.W = g->W;
+  o.S = (i64)g->D * g->H * g->W;
+  return true;
+}
+
+template <int DIM> struct FieldT;
+template <> struct FieldT<2> { typedef float2 type; };
+template <> struct FieldT<3> { typedef float4 type; };
+
+// ---------------------------------------------------------------------------------------
+// Base coordinate = torch.linspace(-1, 1, size)[i]  (RangeFactories: step=(end-start)/(steps-1),
+// first half counted up from start, second half counted down from end).
+// `single` is the value for size==1: linspace gives -1 (morph base grid, adv_morph.py:27),
+// affine_grid's linspace_from_neg_one gives 0.
+__device__ __forceinline__ float base_coord(int i, int size, float single = -1.f) {
+  if (size <= 1) return single;
+  float step = 2.0f / (float)(size - 1);
+  return (i < size / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(size - 1 - i));
+}
+
+// ---------------------------------------------------------------------------------------
+// grid_sample source index, align_corners=True (GridSampler.cuh:23-31, 52-80, 85-136, 138-168).
+// Returns the (possibly clipped / reflected) pixel coordinate and d(index)/d(coord) in `mult`.
+__device__ __forceinline__ float gs_reflect(float in, int twice_low, int twice_high, float& m) {
+  if (twice_low == twice_high) { m = 0.f; return 0.f; }
+  float mn = (float)twice_low / 2.f;
+  float span = (float)(twice_high - twice_low) / 2.f;
+  in = in - mn;
+  float s = 1.f;
+  if (in < 0.f) { s = -1.f; in = -in; }
+  float extra = fmodf(in, span);
+  int flips = (int)floorf(in / span);
+  if (flips % 2 == 0) { m = s; return extra + mn; }
+  m = -s;
+  return span - extra + mn;
+}
+
+__device__ __forceinline__ float gs_index(float coord, int size, int pad, float& mult) {
+  float x = ((coord + 1.f) / 2.f) * (float)(size - 1);
+  mult = (float)(size - 1) / 2.f;
+  if (pad == ADVK_PAD_REFLECTION) {
+    float m;
+    x = gs_reflect(x, 0, 2 * (size - 1), m);
+    mult *= m;
+  }
+  if (pad != ADVK_PAD_ZEROS) {
+    if (x <= 0.f) { x = 0.f; mult = 0.f; }
+    else {
+      float mx = (float)(size - 1);
+      if (x >= mx) { x = mx; mult = 0.f; }
+    }
+  }
+  // safe_downgrade_to_int_range: anything non-finite or huge is "far outside"
+  if (!(x <= 2147483646.f && x >= -2147483648.f)) x = -100.f;
+  return x;
+}
+
+// One axis of a linear / nearest sampling stencil.
+struct Axis {
+  int i0;          // first corner index
+  float w0, w1;    // weights of corner i0 and i0+1
+  bool v0, v1;     // in-bounds flags
+  float mult;      // d(pixel index)/d(normalised coord) incl. padding clip multiplier
+};
+
+__device__ __forceinline__ Axis make_axis(float coord, int size, int pad, int interp) {
+  Axis a;
+  float x = gs_index(coord, size, pad, a.mult);
+  if (interp == ADVK_INTERP_NEAREST) {
+    float r = nearbyintf(x);
+    a.i0 = (int)r;
+    a.w0 = 1.f; a.w1 = 0.f;
+    a.v0 = (a.i0 >= 0 && a.i0 < size); a.v1 = false;
+    a.mult = 0.f;
+    return a;
+  }
+  float f = floorf(x);
+  a.i0 = (int)f;
+  a.w0 = (f + 1.f) - x;
+  a.w1 = x - f;
+  a.v0 = (a.i0 >= 0 && a.i0 < size);
+  a.v1 = (a.i0 + 1 >= 0 && a.i0 + 1 < size);
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// F.interpolate(mode=linear, align_corners=False) source index (UpSample.cuh:96-131).
+struct UpAxis { int i0, i1; float l0, l1; };
+__device__ __forceinline__ UpAxis up_axis(int dst, int in_size, float scale) {
+  UpAxis u;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  u.i0 = (int)src;
+  if (u.i0 > in_size - 1) u.i0 = in_size - 1;
+  u.i1 = u.i0 + ((u.i0 < in_size - 1) ? 1 : 0);
+  u.l1 = src - (float)u.i0;
+  u.l0 = 1.f - u.l1;
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0. `sm` needs NV*32 floats.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* sm) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float s = warp_sum(v[k]);
+    if (lane == 0) sm[k * 32 + wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float s = (lane < nw) ? sm[k * 32 + lane] : 0.f;
+      v[k] = warp_sum(s);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+inline unsigned blocks_for(i64 n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace advk

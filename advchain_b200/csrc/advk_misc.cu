@@ -1,0 +1,141 @@
+// advk_misc.cu -- error plumbing, device query, the fused PGD parameter update (per-sample L2
+// norm + axpy / sign step, adv_transformation_base.py:129-156 and the optimize_parameters
+// bodies), and the solver's pointwise glue (intensity clamp, valid-region mask binarisation).
+#include <stdarg.h>
+#include "advk_common.cuh"
+
+namespace advk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %d: %s", what, (int)e, cudaGetErrorString(e));
+    return ADVK_ERR_CUDA;
+  }
+  return ADVK_OK;
+}
+
+// sum of squares per sample, accumulated in double across blocks
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, size_t per, double* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const float* src = g + (size_t)n * per;
+  float v[1] = {0.f};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+    float t = src[i];
+    v[0] += t * t;
+  }
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(out + n, (double)v[0]);
+}
+
+__global__ void __launch_bounds__(256)
+update_kernel(float* param, const float* grad, float step, int mode, size_t per,
+              const double* __restrict__ ss) {
+  const int n = blockIdx.y;
+  float inv = 0.f;
+  if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) inv = 1.f / ((float)sqrt(ss[n]) + 1e-20f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+    size_t q = (size_t)n * per + i;
+    float gval = grad[q];
+    float sg = (gval > 0.f) ? 1.f : ((gval < 0.f) ? -1.f : 0.f);
+    float r;
+    switch (mode) {
+      case ADVK_UPD_L2_ASCENT: r = param[q] + step * (gval * inv); break;
+      case ADVK_UPD_SIGN_ASCENT: r = param[q] + step * sg; break;
+      case ADVK_UPD_L2_POWER: r = gval * inv; break;
+      default: r = sg; break;
+    }
+    param[q] = r;
+  }
+}
+
+__global__ void clamp_kernel(const float* __restrict__ x, float lo, float hi, float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = fminf(fmaxf(x[i], lo), hi);
+}
+__global__ void clamp_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, float lo, float hi,
+                                 float* __restrict__ gx, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    gx[i] = (v >= lo && v <= hi) ? go[i] : 0.f;
+  }
+}
+__global__ void nonzero_kernel(float* __restrict__ x, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = (x[i] != 0.f) ? 1.f : 0.f;
+}
+
+static unsigned ew_blocks(size_t n) {
+  size_t b = (n + 255) / 256;
+  return (unsigned)(b > 148 * 16 ? 148 * 16 : (b ? b : 1));
+}
+
+}  // namespace advk
+
+using namespace advk;
+
+extern "C" int advk_abi_version(void) { return ADVK_ABI_VERSION; }
+extern "C" const char* advk_last_error(void) { return g_err; }
+
+extern "C" int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    set_error("advk_device_info: no CUDA device");
+    (void)cudaGetLastError();
+    return ADVK_ERR_CUDA;
+  }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+  return ADVK_OK;
+}
+
+extern "C" int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
+                               size_t per_sample, double* sumsq, void* stream) {
+  ADVK_REQUIRE(param && grad && N >= 1 && per_sample >= 1, "null pointer / bad size");
+  ADVK_REQUIRE(mode >= 0 && mode <= 3, "bad mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t b = (per_sample + 255) / 256;
+  unsigned bx = (unsigned)(b > 1024 ? 1024 : b);
+  dim3 grid(bx, N);
+  if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) {
+    ADVK_REQUIRE(sumsq != nullptr, "sumsq scratch is NULL");
+    cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
+    sumsq_kernel<<<grid, 256, 0, st>>>(grad, per_sample, sumsq);
+  }
+  update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq);
+  return check_launch("pgd_update");
+}
+
+extern "C" int advk_clamp(const float* x, float lo, float hi, float* out, size_t n, void* stream) {
+  ADVK_REQUIRE(x && out, "null pointer");
+  if (n == 0) return ADVK_OK;
+  clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, lo, hi, out, n);
+  return check_launch("clamp");
+}
+extern "C" int advk_clamp_bwd(const float* g_out, const float* x, float lo, float hi, float* g_x, size_t n,
+                              void* stream) {
+  ADVK_REQUIRE(x && g_out && g_x, "null pointer");
+  if (n == 0) return ADVK_OK;
+  clamp_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(g_out, x, lo, hi, g_x, n);
+  return check_launch("clamp_bwd");
+}
+extern "C" int advk_nonzero_mask(float* x, size_t n, void* stream) {
+  ADVK_REQUIRE(x != nullptr, "null pointer");
+  if (n == 0) return ADVK_OK;
+  nonzero_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n);
+  return check_launch("nonzero_mask");
+}

@@ -1,0 +1,619 @@
+// advk_morph.cu -- AdvMorph deformation-field build (DemonsCompose, adv_morph.py:454-491) and its
+// hand-derived backward (the reference relies on autograd; derivation in SURVEY.md section 9).
+//
+// Forward, per sign s (scale = s*epsilon):
+//   u_lr  = G (*) (scale * v)                         low-res depthwise Gaussian, zero pad
+//   phi_0 = base + upsample(u_lr) / 2^n               linear, align_corners=False
+//   phi_k = phi_{k-1} o phi_{k-1}, k = 1..n            grid_sample(border, align_corners=True)
+//   r     = compose_with_base(phi_n - phi_0 + base) - base        (quirk Q1: minus phi_0)
+//   field = G (*) r + base                             full-res separable Gaussian, zero pad
+// (the final clamp to [-1,1] is applied by the consumers on load).
+//
+// Fields are interleaved float2 / float4 per voxel so that every stencil corner is ONE vector
+// load and every backward scatter ONE vector reduction (REDG.E.ADD.F32x2/x4).
+#include "advk_common.cuh"
+
+namespace advk {
+
+constexpr int KT = 9;   // Gaussian taps (sigma = 1 -> 2*int(4*sigma+0.5)+1, adv_morph.py:394-400)
+constexpr int KR = 4;
+
+struct MorphCfg {
+  int Dl, Hl, Wl;
+  float w[KT];
+  float sD, sH, sW;   // ATen upsample scales in/out
+};
+
+static bool make_cfg(const advk_morph_cfg* c, const Dims& g, int d, MorphCfg& o) {
+  if (!c || c->ktaps != KT) return false;
+  o.Dl = c->lr[0]; o.Hl = c->lr[1]; o.Wl = c->lr[2];
+  if (o.Dl < 1 || o.Hl < 1 || o.Wl < 1 || (d == 2 && o.Dl != 1)) return false;
+  for (int i = 0; i < KT; ++i) o.w[i] = c->gauss[i];
+  o.sD = (float)o.Dl / (float)g.D; o.sH = (float)o.Hl / (float)g.H; o.sW = (float)o.Wl / (float)g.W;
+  return true;
+}
+
+template <int DIM> struct V;
+template <> struct V<2> {
+  typedef float2 T;
+  static __device__ __forceinline__ T make(float x, float y, float) { return make_float2(x, y); }
+  static __device__ __forceinline__ float z(const T&) { return 0.f; }
+};
+template <> struct V<3> {
+  typedef float4 T;
+  static __device__ __forceinline__ T make(float x, float y, float z) { return make_float4(x, y, z, 0.f); }
+  static __device__ __forceinline__ float z(const T& v) { return v.z; }
+};
+
+// ---------------------------------------------------------------------------------------
+// Low-res depthwise Gaussian (direct 9^d taps; the lattice is tiny: 16x16 / 8x8x8).
+// in/out planar [NC][Dl][Hl][Wl]; out = G (*) (scale*in).  Self-adjoint -> also used backward.
+template <int DIM>
+__global__ void lowres_smooth_kernel(MorphCfg c, int NC, const float* __restrict__ in, float scale,
+                                     float* __restrict__ out) {
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (i64)NC * lr) return;
+  int x = (int)(idx % c.Wl);
+  int y = (int)((idx / c.Wl) % c.Hl);
+  int z = (int)((idx / ((i64)c.Wl * c.Hl)) % c.Dl);
+  i64 nc = idx / lr;
+  const float* src = in + nc * lr;
+  float acc = 0.f;
+  for (int kz = 0; kz < (DIM == 3 ? KT : 1); ++kz) {
+    int zz = (DIM == 3) ? z + kz - KR : 0;
+    if (zz < 0 || zz >= c.Dl) continue;
+    float wz = (DIM == 3) ? c.w[kz] : 1.f;
+    for (int ky = 0; ky < KT; ++ky) {
+      int yy = y + ky - KR;
+      if (yy < 0 || yy >= c.Hl) continue;
+      float wzy = wz * c.w[ky];
+      for (int kx = 0; kx < KT; ++kx) {
+        int xx = x + kx - KR;
+        if (xx < 0 || xx >= c.Wl) continue;
+        acc += (wzy * c.w[kx]) * (scale * src[((i64)zz * c.Hl + yy) * c.Wl + xx]);
+      }
+    }
+  }
+  out[idx] = acc;
+}
+
+// upsampled velocity at one voxel; u_lr planar [N][DIM][lr]
+template <int DIM>
+__device__ __forceinline__ void upsample_u(const MorphCfg& c, const Dims& g, const float* __restrict__ u_lr,
+                                           int n, int z, int y, int x, float (&u)[3]) {
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  UpAxis ux = up_axis(x, c.Wl, c.sW), uy = up_axis(y, c.Hl, c.sH);
+  UpAxis uz;
+  if (DIM == 3) uz = up_axis(z, c.Dl, c.sD);
+  else { uz.i0 = uz.i1 = 0; uz.l0 = 1.f; uz.l1 = 0.f; }
+#pragma unroll
+  for (int ch = 0; ch < DIM; ++ch) {
+    const float* s = u_lr + ((i64)n * DIM + ch) * lr;
+    float acc = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+      int zi = dz ? uz.i1 : uz.i0;
+      float lz = dz ? uz.l1 : uz.l0;
+      const float* r0 = s + ((i64)zi * c.Hl + uy.i0) * c.Wl;
+      const float* r1 = s + ((i64)zi * c.Hl + uy.i1) * c.Wl;
+      float a = uy.l0 * (ux.l0 * __ldg(r0 + ux.i0) + ux.l1 * __ldg(r0 + ux.i1)) +
+                uy.l1 * (ux.l0 * __ldg(r1 + ux.i0) + ux.l1 * __ldg(r1 + ux.i1));
+      acc += lz * a;
+    }
+    u[ch] = acc;
+  }
+  if (DIM == 2) u[2] = 0.f;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+init_phi0_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n,
+                 typename V<DIM>::T* __restrict__ phi0) {
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.S) return;
+  const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
+  float u[3];
+  upsample_u<DIM>(c, g, u_lr, n, z, y, x, u);
+  phi0[(i64)n * g.S + p] = V<DIM>::make(base_coord(x, g.W) + u[0] * inv2n,
+                                         base_coord(y, g.H) + u[1] * inv2n,
+                                         (DIM == 3 ? base_coord(z, g.D) + u[2] * inv2n : 0.f));
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+unorm2_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  float v[1] = {0.f};
+  if (p < g.S) {
+    const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
+    float u[3];
+    upsample_u<DIM>(c, g, u_lr, n, z, y, x, u);
+    v[0] = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+  }
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(out, v[0]);
+}
+
+// ---------------------------------------------------------------------------------------
+// One squaring step: out(p) = sample(in, at in(p)), border padding, align_corners=True.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
+  typedef typename V<DIM>::T T;
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.S) return;
+  const T* src = in + (i64)n * g.S;
+  const T f = src[p];
+  Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis az;
+  if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
+  const i64 HW = (i64)g.H * g.W;
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll
+  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+    bool vz = dz ? az.v1 : az.v0;
+    float wz = dz ? az.w1 : az.w0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      bool vy = dy ? ay.v1 : ay.v0;
+      float wy = dy ? ay.w1 : ay.w0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        bool vx = dx ? ax.v1 : ax.v0;
+        float wx = dx ? ax.w1 : ax.w0;
+        if (vx && vy && vz) {
+          i64 q = (i64)(az.i0 + dz) * HW + (i64)(ay.i0 + dy) * g.W + (ax.i0 + dx);
+          T s = __ldg(src + q);
+          float w = wx * wy * wz;
+          ox += s.x * w; oy += s.y * w;
+          if (DIM == 3) oz += V<DIM>::z(s) * w;
+        }
+      }
+    }
+  }
+  out[(i64)n * g.S + p] = V<DIM>::make(ox, oy, oz);
+}
+
+// Backward of one squaring step: given g_out = dL/dphi_k and phi_{k-1}, accumulate
+// dL/dphi_{k-1} = scatter-adjoint of the gather + spatial Jacobian.  g_in must be zeroed.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
+                   const typename V<DIM>::T* __restrict__ g_out, typename V<DIM>::T* __restrict__ g_in) {
+  typedef typename V<DIM>::T T;
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.S) return;
+  const T* src = phi_prev + (i64)n * g.S;
+  T* dst = g_in + (i64)n * g.S;
+  const T f = src[p];
+  const T go = g_out[(i64)n * g.S + p];
+  Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis az;
+  if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
+  const i64 HW = (i64)g.H * g.W;
+  float jx = 0.f, jy = 0.f, jz = 0.f;
+#pragma unroll
+  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+    bool vz = dz ? az.v1 : az.v0;
+    float wz = dz ? az.w1 : az.w0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      bool vy = dy ? ay.v1 : ay.v0;
+      float wy = dy ? ay.w1 : ay.w0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        bool vx = dx ? ax.v1 : ax.v0;
+        float wx = dx ? ax.w1 : ax.w0;
+        if (vx && vy && vz) {
+          i64 q = (i64)(az.i0 + dz) * HW + (i64)(ay.i0 + dy) * g.W + (ax.i0 + dx);
+          float w = wx * wy * wz;
+          atomicAdd(dst + q, V<DIM>::make(go.x * w, go.y * w, V<DIM>::z(go) * w));
+          T s = __ldg(src + q);
+          float dot = s.x * go.x + s.y * go.y + V<DIM>::z(s) * V<DIM>::z(go);
+          jx += (dx ? dot : -dot) * (wy * wz);
+          jy += (dy ? dot : -dot) * (wx * wz);
+          if (DIM == 3) jz += (dz ? dot : -dot) * (wx * wy);
+        }
+      }
+    }
+  }
+  atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+}
+
+// ---------------------------------------------------------------------------------------
+// Full-res separable Gaussian with fused pre/post maps.
+//   MODE 0 (forward):  in  = compose_with_base(phi_n - phi_0 + base) - base
+//                      out = smooth + base                            -> field_out
+//   MODE 1 (backward): in  = g_field * [ -1 <= field <= 1 ]
+//                      out = smooth * [ 0 < pix(phi_n - phi_0 + base) < size-1 ]   -> g_off
+// A, B are the two fields the input map reads at halo positions (phi_n, phi_0 | g_field, field);
+// C, D are read at the centre by the backward output map (phi_n, phi_0).
+template <int DIM>
+struct SmoothArgs {
+  const typename V<DIM>::T* A;
+  const typename V<DIM>::T* B;
+  const typename V<DIM>::T* C;
+  const typename V<DIM>::T* D;
+  typename V<DIM>::T* out;
+  float w[KT];
+};
+
+// grid_sample(base, c, border) along one axis: linear interpolation of the linspace.
+__device__ __forceinline__ float compose_axis(float c, int size, float& mult) {
+  float i = gs_index(c, size, ADVK_PAD_BORDER, mult);
+  float f = floorf(i);
+  int i0 = (int)f;
+  float v = base_coord(i0, size) * ((f + 1.f) - i);
+  if (i0 + 1 < size) v += base_coord(i0 + 1, size) * (i - f);
+  return v;
+}
+
+template <int DIM, int MODE>
+__device__ __forceinline__ void smooth_in(const SmoothArgs<DIM>& a, const Dims& g, i64 idx, int z,
+                                          int y, int x, float (&r)[3]) {
+  typedef typename V<DIM>::T T;
+  T p = a.A[idx], q = a.B[idx];
+  if (MODE == 0) {
+    float m;
+    float bx = base_coord(x, g.W), by = base_coord(y, g.H);
+    r[0] = compose_axis((p.x - q.x) + bx, g.W, m) - bx;
+    r[1] = compose_axis((p.y - q.y) + by, g.H, m) - by;
+    if (DIM == 3) {
+      float bz = base_coord(z, g.D);
+      r[2] = compose_axis((V<DIM>::z(p) - V<DIM>::z(q)) + bz, g.D, m) - bz;
+    } else r[2] = 0.f;
+  } else {
+    r[0] = (q.x >= -1.f && q.x <= 1.f) ? p.x : 0.f;
+    r[1] = (q.y >= -1.f && q.y <= 1.f) ? p.y : 0.f;
+    r[2] = (DIM == 3 && V<DIM>::z(q) >= -1.f && V<DIM>::z(q) <= 1.f) ? V<DIM>::z(p) : 0.f;
+  }
+}
+
+template <int DIM, int MODE>
+__device__ __forceinline__ void smooth_out(const SmoothArgs<DIM>& a, const Dims& g, i64 idx, int z,
+                                           int y, int x, const float (&s)[3]) {
+  typedef typename V<DIM>::T T;
+  if (MODE == 0) {
+    a.out[idx] = V<DIM>::make(s[0] + base_coord(x, g.W), s[1] + base_coord(y, g.H),
+                              DIM == 3 ? s[2] + base_coord(z, g.D) : 0.f);
+  } else {
+    T p = a.C[idx], q = a.D[idx];
+    float mx, my, mz = 0.f;
+    gs_index((p.x - q.x) + base_coord(x, g.W), g.W, ADVK_PAD_BORDER, mx);
+    gs_index((p.y - q.y) + base_coord(y, g.H), g.H, ADVK_PAD_BORDER, my);
+    if (DIM == 3) gs_index((V<DIM>::z(p) - V<DIM>::z(q)) + base_coord(z, g.D), g.D, ADVK_PAD_BORDER, mz);
+    a.out[idx] = V<DIM>::make(mx != 0.f ? s[0] : 0.f, my != 0.f ? s[1] : 0.f, mz != 0.f ? s[2] : 0.f);
+  }
+}
+
+constexpr int S2_TX = 32, S2_TY = 16, S2_THREADS = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(S2_THREADS)
+smooth2d_kernel(Dims g, SmoothArgs<2> a) {
+  __shared__ float s_in[2][S2_TY + 2 * KR][S2_TX + 2 * KR];
+  __shared__ float s_tmp[2][S2_TY + 2 * KR][S2_TX];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * S2_TX, y0 = blockIdx.y * S2_TY;
+  constexpr int IW = S2_TX + 2 * KR, IH = S2_TY + 2 * KR;
+  for (int i = threadIdx.x; i < IW * IH; i += S2_THREADS) {
+    int ly = i / IW, lx = i % IW;
+    int gy = y0 + ly - KR, gx = x0 + lx - KR;
+    float r[3] = {0.f, 0.f, 0.f};
+    if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+      smooth_in<2, MODE>(a, g, (i64)n * g.S + (i64)gy * g.W + gx, 0, gy, gx, r);
+    s_in[0][ly][lx] = r[0]; s_in[1][ly][lx] = r[1];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S2_TX * IH; i += S2_THREADS) {
+    int ly = i / S2_TX, lx = i % S2_TX;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { a0 += a.w[k] * s_in[0][ly][lx + k]; a1 += a.w[k] * s_in[1][ly][lx + k]; }
+    s_tmp[0][ly][lx] = a0; s_tmp[1][ly][lx] = a1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S2_TX * S2_TY; i += S2_THREADS) {
+    int ly = i / S2_TX, lx = i % S2_TX;
+    int gy = y0 + ly, gx = x0 + lx;
+    if (gy >= g.H || gx >= g.W) continue;
+    float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { s[0] += a.w[k] * s_tmp[0][ly + k][lx]; s[1] += a.w[k] * s_tmp[1][ly + k][lx]; }
+    smooth_out<2, MODE>(a, g, (i64)n * g.S + (i64)gy * g.W + gx, 0, gy, gx, s);
+  }
+}
+
+// 3-D: (x,y) tile per CTA, marching along z with a 9-plane register ring per thread.
+constexpr int S3_TX = 32, S3_TY = 16, S3_THREADS = S3_TX * S3_TY;
+
+template <int MODE>
+__global__ void __launch_bounds__(S3_THREADS)
+smooth3d_kernel(Dims g, SmoothArgs<3> a, int zchunk, int nzc) {
+  constexpr int IW = S3_TX + 2 * KR, IH = S3_TY + 2 * KR;
+  __shared__ float s_in[3][IH][IW];
+  __shared__ float s_tmp[3][IH][S3_TX];
+  const int n = blockIdx.z / nzc;
+  const int zc = blockIdx.z % nzc;
+  const int x0 = blockIdx.x * S3_TX, y0 = blockIdx.y * S3_TY;
+  const int zb = zc * zchunk;
+  const int ze = min(g.D, zb + zchunk);
+  const int tx = threadIdx.x % S3_TX, ty = threadIdx.x / S3_TX;
+  const i64 HW = (i64)g.H * g.W;
+  float ring[3][KT];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < KT; ++k) ring[c][k] = 0.f;
+  for (int pz = zb - KR; pz < ze + KR; ++pz) {
+    float v[3] = {0.f, 0.f, 0.f};
+    if (pz >= 0 && pz < g.D) {   // block-uniform
+      for (int i = threadIdx.x; i < IW * IH; i += S3_THREADS) {
+        int ly = i / IW, lx = i % IW;
+        int gy = y0 + ly - KR, gx = x0 + lx - KR;
+        float r[3] = {0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+          smooth_in<3, MODE>(a, g, (i64)n * g.S + (i64)pz * HW + (i64)gy * g.W + gx, pz, gy, gx, r);
+        s_in[0][ly][lx] = r[0]; s_in[1][ly][lx] = r[1]; s_in[2][ly][lx] = r[2];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < S3_TX * IH; i += S3_THREADS) {
+        int ly = i / S3_TX, lx = i % S3_TX;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          float w = a.w[k];
+          a0 += w * s_in[0][ly][lx + k]; a1 += w * s_in[1][ly][lx + k]; a2 += w * s_in[2][ly][lx + k];
+        }
+        s_tmp[0][ly][lx] = a0; s_tmp[1][ly][lx] = a1; s_tmp[2][ly][lx] = a2;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float w = a.w[k];
+        v[0] += w * s_tmp[0][ty + k][tx]; v[1] += w * s_tmp[1][ty + k][tx]; v[2] += w * s_tmp[2][ty + k][tx];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < KT - 1; ++k) ring[c][k] = ring[c][k + 1];
+      ring[c][KT - 1] = v[c];
+    }
+    const int zo = pz - KR;
+    const int gy = y0 + ty, gx = x0 + tx;
+    if (zo >= zb && zo < ze && gy < g.H && gx < g.W) {
+      float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float w = a.w[k];
+        s[0] += w * ring[0][k]; s[1] += w * ring[1][k]; s[2] += w * ring[2][k];
+      }
+      smooth_out<3, MODE>(a, g, (i64)n * g.S + (i64)zo * HW + (i64)gy * g.W + gx, zo, gy, gx, s);
+    }
+  }
+}
+
+template <int DIM, int MODE>
+static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const void* B, const void* C,
+                          const void* D, void* out, cudaStream_t st) {
+  typedef typename V<DIM>::T T;
+  SmoothArgs<DIM> a;
+  a.A = (const T*)A; a.B = (const T*)B; a.C = (const T*)C; a.D = (const T*)D; a.out = (T*)out;
+  for (int i = 0; i < KT; ++i) a.w[i] = c.w[i];
+  if (DIM == 2) {
+    dim3 grid((g.W + S2_TX - 1) / S2_TX, (g.H + S2_TY - 1) / S2_TY, g.N);
+    smooth2d_kernel<MODE><<<grid, S2_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<2>*>(&a));
+  } else {
+    int zchunk = 16;
+    int nzc = (g.D + zchunk - 1) / zchunk;
+    dim3 grid((g.W + S3_TX - 1) / S3_TX, (g.H + S3_TY - 1) / S3_TY, g.N * nzc);
+    smooth3d_kernel<MODE><<<grid, S3_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<3>*>(&a), zchunk, nzc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Adjoint of the align_corners=False linear upsample along ONE axis, gather form (deterministic).
+// in  viewed as [outer][n_in ][inner] elements of T, out as [outer][n_out][inner];
+// out[o][j][i] = sum_p w(p -> j) * val(o,p,i),  val = (a - b) * vs  (b nullable).
+template <typename T> __device__ __forceinline__ T t_zero();
+template <> __device__ __forceinline__ float t_zero<float>() { return 0.f; }
+template <> __device__ __forceinline__ float2 t_zero<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float4 t_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void t_fma(float& acc, float w, float a, float b, bool hb) { acc += w * (hb ? a - b : a); }
+__device__ __forceinline__ void t_fma(float2& acc, float w, float2 a, float2 b, bool hb) {
+  acc.x += w * (hb ? a.x - b.x : a.x); acc.y += w * (hb ? a.y - b.y : a.y);
+}
+__device__ __forceinline__ void t_fma(float4& acc, float w, float4 a, float4 b, bool hb) {
+  acc.x += w * (hb ? a.x - b.x : a.x); acc.y += w * (hb ? a.y - b.y : a.y); acc.z += w * (hb ? a.z - b.z : a.z);
+}
+__device__ __forceinline__ float t_scale(float a, float s) { return a * s; }
+__device__ __forceinline__ float2 t_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float4 t_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, 0.f); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out,
+                    i64 outer, int n_in, int n_out, i64 inner, float scale) {
+  i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= outer * n_out * inner) return;
+  i64 i = idx % inner;
+  int j = (int)((idx / inner) % n_out);
+  i64 o = idx / (inner * n_out);
+  // voxels p whose source coordinate scale*(p+0.5)-0.5 lies in (j-1, j+1), widened by one
+  int plo = (int)floorf(((float)j - 0.5f) / scale - 0.5f) - 1;
+  int phi = (int)ceilf(((float)j + 1.5f) / scale - 0.5f) + 1;
+  if (plo < 0) plo = 0;
+  if (phi > n_in - 1) phi = n_in - 1;
+  if (j == 0) plo = 0;                 // src is clamped at 0 from below
+  T acc = t_zero<T>();
+  const bool hb = (b != nullptr);
+  for (int p = plo; p <= phi; ++p) {
+    UpAxis u = up_axis(p, n_out, scale);
+    float w = (u.i0 == j ? u.l0 : 0.f) + (u.i1 == j ? u.l1 : 0.f);
+    if (w != 0.f) {
+      i64 q = (o * n_in + p) * inner + i;
+      t_fma(acc, w, a[q], hb ? b[q] : a[q], hb);
+    }
+  }
+  out[idx] = t_scale(acc, vs);
+}
+
+template <typename T>
+static void launch_adjoint_axis(const T* a, const T* b, float vs, T* out, i64 outer, int n_in, int n_out,
+                                i64 inner, float scale, cudaStream_t st) {
+  i64 tot = outer * n_out * inner;
+  adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, b, vs, out, outer, n_in, n_out, inner, scale);
+}
+
+template <int DIM>
+__global__ void aos_to_planar_kernel(const typename V<DIM>::T* __restrict__ in, float* __restrict__ out,
+                                     int N, i64 lr) {
+  i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (i64)N * lr) return;
+  i64 n = idx / lr, q = idx % lr;
+  typename V<DIM>::T v = in[idx];
+  out[(n * DIM + 0) * lr + q] = v.x;
+  out[(n * DIM + 1) * lr + q] = v.y;
+  if (DIM == 3) out[(n * DIM + 2) * lr + q] = V<DIM>::z(v);
+}
+
+// ---------------------------------------------------------------------------------------
+template <int DIM>
+static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float scale, int nb, float* u_lr,
+                     void* levels, void* field_out, cudaStream_t st) {
+  typedef typename V<DIM>::T T;
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  int NC = g.N * DIM;
+  lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
+  T* L = (T*)levels;
+  i64 F = (i64)g.N * g.S;
+  dim3 grid(blocks_for(g.S, 256), g.N);
+  float inv2n = 1.0f / (float)(1u << nb);
+  init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, L);
+  for (int k = 1; k <= nb; ++k) ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F);
+  launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, st);
+  return check_launch("morph_field_fwd");
+}
+
+template <int DIM>
+static size_t lr_scratch_floats(const Dims& g, const MorphCfg& c) {
+  size_t e = sizeof(typename V<DIM>::T) / sizeof(float);
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  i64 p1 = (DIM == 3) ? (i64)g.N * c.Dl * g.H * g.W : 0;
+  i64 p2 = (i64)g.N * c.Dl * c.Hl * g.W;
+  i64 p3 = (i64)g.N * lr;
+  return (size_t)(e * (p1 + p2 + p3) + (i64)g.N * DIM * lr);
+}
+
+template <int DIM>
+static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, const void* levels,
+                     const void* field_out, const void* g_field, void* scratch, float* lr_scratch,
+                     float* g_v, cudaStream_t st) {
+  typedef typename V<DIM>::T T;
+  const T* L = (const T*)levels;
+  i64 F = (i64)g.N * g.S;
+  T* g_off = (T*)scratch;
+  T* ping = g_off + F;
+  T* pong = ping + F;
+  // (9)+(8)+(7): clamp mask, Gaussian (self-adjoint), compose-with-base border mask -> g_off = dL/d(off)
+  launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, st);
+  // dL/dphi_n = g_off ; walk the squaring steps back
+  dim3 grid(blocks_for(g.S, 256), g.N);
+  const T* cur = g_off;
+  T* bufs[2] = {ping, pong};
+  for (int k = nb; k >= 1; --k) {
+    T* nxt = bufs[(nb - k) & 1];
+    cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
+    ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, cur, nxt);
+    cur = nxt;
+  }
+  // dL/dphi_0 = cur - g_off (quirk Q1);  dL/du = that / 2^n;  then the upsample adjoint per axis
+  float inv2n = 1.0f / (float)(1u << nb);
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  T* s1 = (T*)lr_scratch;
+  const T* a = cur;
+  const T* b = g_off;
+  float vs = inv2n;
+  if (DIM == 3) {
+    launch_adjoint_axis<T>(a, b, vs, s1, g.N, g.D, c.Dl, (i64)g.H * g.W, c.sD, st);
+    a = s1; b = nullptr; vs = 1.f;
+    s1 += (i64)g.N * c.Dl * g.H * g.W;
+  }
+  launch_adjoint_axis<T>(a, b, vs, s1, (i64)g.N * c.Dl, g.H, c.Hl, g.W, c.sH, st);
+  T* s2 = s1 + (i64)g.N * c.Dl * c.Hl * g.W;
+  launch_adjoint_axis<T>(s1, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
+  float* planar = (float*)(s2 + (i64)g.N * lr);
+  aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr);
+  int NC = g.N * DIM;
+  lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, planar, scale, g_v);
+  return check_launch("morph_field_bwd");
+}
+
+}  // namespace advk
+
+using namespace advk;
+
+extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg, const float* v,
+                                 float scale, float* u_lr, float* out_norm2, void* stream) {
+  Dims g; MorphCfg c;
+  ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
+  ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
+  ADVK_REQUIRE(v && u_lr && out_norm2, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  int NC = g.N * gg->d;
+  cudaMemsetAsync(out_norm2, 0, sizeof(float), st);
+  dim3 grid(blocks_for(g.S, 256), g.N);
+  if (gg->d == 2) {
+    lowres_smooth_kernel<2><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
+    unorm2_kernel<2><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2);
+  } else {
+    lowres_smooth_kernel<3><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
+    unorm2_kernel<3><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2);
+  }
+  return check_launch("morph_unorm2");
+}
+
+extern "C" int advk_morph_field_fwd(const advk_geom* gg, const advk_morph_cfg* cfg, const float* v,
+                                    float scale, int nb_steps, float* u_lr, void* levels,
+                                    void* field_out, void* stream) {
+  Dims g; MorphCfg c;
+  ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
+  ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
+  ADVK_REQUIRE(v && u_lr && levels && field_out, "null pointer");
+  ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  return gg->d == 2 ? field_fwd<2>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st)
+                    : field_fwd<3>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st);
+}
+
+extern "C" size_t advk_morph_lr_scratch_floats(const advk_geom* gg, const advk_morph_cfg* cfg) {
+  Dims g; MorphCfg c;
+  if (!make_dims(gg, g) || !make_cfg(cfg, g, gg->d, c)) return 0;
+  return gg->d == 2 ? lr_scratch_floats<2>(g, c) : lr_scratch_floats<3>(g, c);
+}
+
+extern "C" int advk_morph_field_bwd(const advk_geom* gg, const advk_morph_cfg* cfg, float scale,
+                                    int nb_steps, const void* levels, const void* field_out,
+                                    const void* g_field, void* scratch, float* lr_scratch,
+                                    float* g_v, void* stream) {
+  Dims g; MorphCfg c;
+  ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
+  ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
+  ADVK_REQUIRE(levels && field_out && g_field && scratch && lr_scratch && g_v, "null pointer");
+  ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  return gg->d == 2 ? field_bwd<2>(g, c, scale, nb_steps, levels, field_out, g_field, scratch, lr_scratch, g_v, st)
+                    : field_bwd<3>(g, c, scale, nb_steps, levels, field_out, g_field, scratch, lr_scratch, g_v, st);
+}

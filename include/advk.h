@@ -1,0 +1,193 @@
+/* advk.h -- C ABI of libadvchain_b200.so (hand-written sm_100a CUDA kernels for the advchain
+ * chained adversarial-augmentation hot path).
+ *
+ * The reference (cherise215/advchain) has NO FFI / plugin boundary: its device work is issued
+ * as PyTorch ATen calls from Python (`F.grid_sample`, `F.affine_grid`, `F.interpolate`,
+ * `F.conv_transposeNd`, depthwise `nn.ConvNd`, `.inverse()`).  Each entry
+ * point below therefore cites the reference *call site(s)* whose ATen work it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked "host"; fp32 everywhere
+ *   - every launch function returns 0 on success, <0 on error (advk_last_error() has the text);
+ *     it never allocates, never synchronises, and enqueues on `stream` (a cudaStream_t)
+ *   - tensors are contiguous, batch-major, torch layout  N x C x [D x] H x W
+ *   - x <-> W (last axis), y <-> H, z <-> D, exactly like torch's grid_sample / the
+ *     reference's base grid (adv_morph.py:14-55)
+ *   - "field" = dense sampling grid in normalised [-1,1] coordinates stored INTERLEAVED per voxel:
+ *     float2 (x,y) for d==2, float4 (x,y,z,0) for d==3; N*S elements (S = D*H*W)
+ *   - gradient outputs documented as "accumulated" must be zero-initialised by the caller
+ */
+#ifndef ADVK_H
+#define ADVK_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVK_ABI_VERSION 1
+
+enum { ADVK_OK = 0, ADVK_ERR_ARG = -1, ADVK_ERR_UNSUPPORTED = -2, ADVK_ERR_CUDA = -3 };
+enum { ADVK_PAD_ZEROS = 0, ADVK_PAD_BORDER = 1, ADVK_PAD_REFLECTION = 2 };
+enum { ADVK_INTERP_LINEAR = 0, ADVK_INTERP_NEAREST = 1 };
+
+/* PGD update modes (advk_pgd_update) */
+enum {
+  ADVK_UPD_L2_ASCENT = 0,  /* p += step * g/(||g||_2+1e-20)   adv_noise.py:51-64, adv_bias.py:139-148, adv_morph.py:501-516 */
+  ADVK_UPD_SIGN_ASCENT = 1,/* p += step * sign(g)             adv_affine.py:182-198 */
+  ADVK_UPD_L2_POWER = 2,   /* p  = g/(||g||_2+1e-20)          power iteration branches of the above */
+  ADVK_UPD_SIGN_POWER = 3  /* p  = sign(g) */
+};
+
+typedef struct advk_geom {
+  int d;        /* spatial dims: 2 or 3 */
+  int N;        /* batch */
+  int D, H, W;  /* torch spatial order; D must be 1 when d == 2 */
+} advk_geom;
+
+/* adv_affine.py:73-105 config; 2-D uses rot[0] only. */
+typedef struct advk_affine_cfg {
+  int d;
+  float rot[3];   /* rot (2-D) | rot_x, rot_y, rot_z */
+  float scale[3]; /* scale_x, scale_y, scale_z */
+  float shift[3]; /* shift_x, shift_y, shift_z */
+} advk_affine_cfg;
+
+/* adv_morph.py:247-258, 391-421: low-res velocity lattice + the 1-D factor of the separable,
+ * sum-normalised Gaussian (9 taps for sigma=1). */
+typedef struct advk_morph_cfg {
+  int lr[3];       /* low-res lattice in torch order (Dl,Hl,Wl); Dl = 1 for d == 2 */
+  int ktaps;       /* odd, <= 15 */
+  float gauss[15]; /* taps[0..ktaps-1], sum 1 */
+} advk_morph_cfg;
+
+/* adv_bias.py:202-335 geometry. `A[ax]` are dense (low[ax] x n_cp[ax]) row-major matrices
+ * (device pointers) that fold conv_transpose(kernel, stride, padding) + crop along one axis:
+ * low = A_D (x) A_H (x) A_W applied to the control points. */
+typedef struct advk_bias_cfg {
+  int n_cp[3];        /* control-point lattice, torch order (D,H,W); 1 for the unused axis */
+  int low[3];         /* low-res field size, torch order */
+  const float* A[3];  /* device pointers */
+  float up_scale[3];  /* ATen source-index scale per axis for the linear upsample (align_corners=False) */
+  int upsample;       /* 0: low-res field is already full-res */
+  int use_log;        /* bias = exp(field) (1) or 1 + field (0)          adv_bias.py:331-334 */
+  float magnitude;    /* clip to [1-m, 1+m]                               adv_bias.py:337-356 */
+} advk_bias_cfg;
+
+int advk_abi_version(void);
+const char* advk_last_error(void);                 /* thread-local, valid until the next call */
+int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes); /* host ptrs */
+
+/* ---- AdvAffine: parameters -> matrices -------------------------------------------------
+ * replaces gen_batch_affine_matrix (adv_affine.py:210-273: Hardtanh, cos/sin, stack, matmul)
+ * and get_inverse_matrix (adv_affine.py:316-324: batched .inverse()).
+ * param: N x (5|9); theta / theta_inv: N x d x (d+1). `pscale` multiplies param first
+ * (xi in power-iteration training, adv_affine.py:136-138; else 1). */
+int advk_affine_theta_fwd(const advk_affine_cfg* cfg, const float* param, float pscale, int N,
+                          float* theta, float* theta_inv, void* stream);
+/* g_theta_inv may be NULL. g_param is written (not accumulated). */
+int advk_affine_theta_bwd(const advk_affine_cfg* cfg, const float* param, float pscale, int N,
+                          const float* g_theta, const float* g_theta_inv, float* g_param,
+                          void* stream);
+
+/* ---- warps ------------------------------------------------------------------------------
+ * advk_warp_affine_*: F.affine_grid + F.grid_sample (adv_affine.py:297-313) with the grid
+ *   generated on the fly.
+ * advk_warp_field_*:  F.grid_sample with a dense field (adv_morph.py:546-557); the field is
+ *   clamped to [-1,1] on load (adv_morph.py:304, 489-490) and g_field is masked accordingly.
+ * src/out: N x C x S.  pad_values: NULL, or N per-sample constants v: sample (src - v) with
+ * zero padding and add v back ('lowest' / numeric padding, adv_affine.py:299-311,
+ * adv_morph.py:542-554).
+ * bwd: g_src (nullable) is ACCUMULATED with atomics; g_theta (nullable, N x d x (d+1)) is
+ * ACCUMULATED; g_field is written. */
+int advk_warp_affine_fwd(const advk_geom* g, int C, const float* src, const float* theta,
+                         int pad_mode, int interp, const float* pad_values, float* out,
+                         void* stream);
+int advk_warp_affine_bwd(const advk_geom* g, int C, const float* g_out, const float* src,
+                         const float* theta, int pad_mode, int interp, const float* pad_values,
+                         float* g_src, float* g_theta, void* stream);
+int advk_warp_field_fwd(const advk_geom* g, int C, const float* src, const void* field,
+                        int pad_mode, int interp, const float* pad_values, float* out,
+                        void* stream);
+int advk_warp_field_bwd(const advk_geom* g, int C, const float* g_out, const float* src,
+                        const void* field, int pad_mode, int interp, const float* pad_values,
+                        float* g_src, void* g_field, void* stream);
+
+/* ---- AdvMorph: velocity -> deformation field -------------------------------------------
+ * replaces DemonsCompose (adv_morph.py:454-491): depthwise Gaussian conv (low-res), F.interpolate,
+ * vectorFieldExponentiation2D/3D (:116-177: n grid_sample self-compositions, border padding),
+ * compose-with-base grid_sample, full-res depthwise Gaussian conv, clamp.
+ * v: N x d x lr (channel 0 = x displacement, like the reference).  `scale` = +-epsilon (or +-xi).
+ *
+ * advk_morph_unorm2: sum over the whole batch of |upsampled smoothed velocity|^2, for the 3-D
+ *   step-count rule of adv_morph.py:159-162 (the host picks nb_steps). out: 1 float, overwritten.
+ * levels: (nb_steps+1) fields of N*S elements each, phi_0 .. phi_n, kept for the backward.
+ * field_out: the UNCLAMPED composed field (consumers clamp on load); N*S elements.
+ * u_lr: scratch N x d x lr floats. */
+int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float* v, float scale,
+                      float* u_lr, float* out_norm2, void* stream);
+int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const float* v,
+                         float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
+                         void* stream);
+/* scratch: 3 fields of N*S elements; lr_scratch: advk_morph_lr_scratch_floats() floats.
+ * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
+size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
+int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
+                         const void* levels, const void* field_out, const void* g_field,
+                         void* scratch, float* lr_scratch, float* g_v, void* stream);
+
+/* ---- AdvNoise / AdvBias: intensity stage ------------------------------------------------
+ * advk_bias_lowfield_*: conv_transposeNd + crop (adv_bias.py:293-307) folded into per-axis
+ *   matrices (2-D: A[0] = NULL, n_cp[0] = low[0] = 1). cp: N x n_cp; low: N x low.
+ *   cp_scale: xi in power-iteration training else 1.
+ * advk_intensity_fwd: out = stage2(stage1(x)) with
+ *     noise:  x + noise_scale*delta                               (adv_noise.py:79-90)
+ *     bias:   x * clip(exp|1+ (upsample(low)))                    (adv_bias.py:313-356, 186)
+ *   `order`: 0 noise only, 1 bias only, 2 noise then bias, 3 bias then noise.
+ *   use_ignore/ignore_value: voxels with |x - ignore| < 1e-8 keep `ignore` (adv_noise.py:85-88,
+ *   adv_bias.py:176-182; applied after each stage like the reference).
+ *   bias_out (nullable): N x 1 x S clipped bias field (the reference's `bias_field` attribute).
+ * advk_intensity_bwd: g_x (nullable, written), g_delta (nullable, written),
+ *   g_up (nullable, written): N x S gradient w.r.t. the upsampled pre-exp field.
+ * advk_bias_upsample_adjoint: g_up (N x S) -> g_low (N x low), the adjoint of the
+ *   align_corners=False linear upsample; scratch: advk_bias_scratch_floats() floats. */
+int advk_bias_lowfield_fwd(const advk_bias_cfg* cfg, int N, const float* cp, float cp_scale,
+                           float* low, void* stream);
+int advk_bias_lowfield_bwd(const advk_bias_cfg* cfg, int N, const float* g_low, float cp_scale,
+                           float* g_cp, void* stream);
+int advk_intensity_fwd(const advk_geom* g, int C, int order, const float* x, const float* delta,
+                       float noise_scale, const float* low, const advk_bias_cfg* bias,
+                       int use_ignore, float ignore_value, float* out, float* bias_out,
+                       void* stream);
+int advk_intensity_bwd(const advk_geom* g, int C, int order, const float* g_out, const float* x,
+                       const float* delta, float noise_scale, const float* low,
+                       const advk_bias_cfg* bias, int use_ignore, float ignore_value, float* g_x,
+                       float* g_delta, float* g_up, void* stream);
+size_t advk_bias_scratch_floats(const advk_geom* g, const advk_bias_cfg* bias);
+int advk_bias_upsample_adjoint(const advk_geom* g, const advk_bias_cfg* bias, const float* g_up,
+                               float* scratch, float* g_low, void* stream);
+
+/* ---- PGD parameter update ---------------------------------------------------------------
+ * replaces unit_normalize (adv_transformation_base.py:129-156) + the optimize_parameters
+ * bodies cited at the ADVK_UPD_* enum.  sumsq: N doubles scratch (overwritten). `param` is
+ * updated in place; for the *_POWER modes `grad` may alias `param` (rescale_parameters,
+ * adv_noise.py:92-94, adv_morph.py:518-522). */
+int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
+                    size_t per_sample, double* sumsq, void* stream);
+
+/* ---- solver glue ------------------------------------------------------------------------
+ * advk_clamp: out = clamp(x, lo, hi)   (solver.forward if_norm_image, adv_compose_solver.py:167-175)
+ * advk_clamp_bwd: g_x = g_out * [lo <= x <= hi]
+ * advk_nonzero_mask: m = (x != 0) ? 1 : 0  in place (adv_compose_solver.py:325) */
+int advk_clamp(const float* x, float lo, float hi, float* out, size_t n, void* stream);
+int advk_clamp_bwd(const float* g_out, const float* x, float lo, float hi, float* g_x, size_t n,
+                   void* stream);
+int advk_nonzero_mask(float* x, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVK_H */

@@ -43,3 +43,26 @@ def oracle_solver(case, size=None):
         kw = {"padding": pad} if n in ("morph", "affine") else {}
         stages.append(orc.make_stage(n, cfgs[n], **kw))
     return orc.Solver(stages, if_norm_image=True)
+
+
+def cuda_solver(case, device, size=None, **solver_kw):
+    """The product (CUDA) transforms + solver for a golden case."""
+    from advchain_b200.augmentor import (AdvAffine, AdvBias, AdvMorph, AdvNoise,
+                                         ComposeAdversarialTransformSolver)
+    size = size or case["size"]
+    d = case["d"]
+    cfgs = stage_cfgs(d, size, vector=case.get("vector"))
+    pad = case.get("padding", "zeros")
+    chain = []
+    for n in case["chain"]:
+        if n == "noise":
+            chain.append(AdvNoise(d, cfgs[n], device=device))
+        elif n == "bias":
+            chain.append(AdvBias(d, cfgs[n], device=device))
+        elif n == "morph":
+            chain.append(AdvMorph(d, cfgs[n], image_padding_mode=pad, device=device))
+        else:
+            chain.append(AdvAffine(d, cfgs[n], image_padding_mode=pad, device=device))
+    kw = dict(divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5], if_norm_image=True)
+    kw.update(solver_kw)
+    return ComposeAdversarialTransformSolver(chain, **kw)

@@ -1,0 +1,85 @@
+"""GPU parity against the committed golden fixtures (outputs of the unmodified reference, see
+tests/golden/make_golden.py): every PGD step is replayed teacher-forced from the reference's own
+start parameters through the public drop-in API (transforms + solver), i.e. through the C ABI."""
+import pytest
+import torch
+
+from tests.golden.cases import CASES
+from tests.helpers import cuda_solver, load_golden, make_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-5      # north-star: outputs within 1e-5 relative fp32
+GRAD_TOL = 1e-4     # raw parameter gradients (fp32 atomics; the reference's CUDA path is itself
+                    # non-deterministic at ~1e-6)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_steps_match_reference_fixture(name):
+    dev = torch.device("cuda:0")
+    meta, z = load_golden(name)
+    case = meta["case"]
+    model = make_model(case, z, dev)
+    sol = cuda_solver(case, dev)
+    data, init_out = z["data"].to(dev), z["init_output"].to(dev)
+    chain = sol.chain_of_transforms
+    for t in chain:
+        t.init_parameters()
+    for s in range(case["n_iter"]):
+        for i, t in enumerate(chain):
+            t.param = z["s%d_param_%d" % (s, i)].to(dev)
+            t.train()
+        model.zero_grad()
+        aug = sol.forward(data)
+        out = model(aug)
+        if sol.if_contains_geo_transform():
+            pred = sol.predict_backward(out)
+            mask = sol.valid_region_mask(init_out)
+            dist = sol.loss_fn(pred, init_out, mask)
+        else:
+            pred, mask = out, None
+            dist = sol.loss_fn(pred, init_out)
+        dist.backward()
+        ref_dist = z["s%d_dist" % s].item()
+        assert abs(dist.item() - ref_dist) <= 2e-5 * abs(ref_dist), (s, dist.item(), ref_dist)
+        if s == 0:
+            assert rel_err(pred, z["s0_pred"]) < OUT_TOL
+            if mask is not None:
+                mism = (mask.cpu() != z["s0_mask"]).float().mean().item()
+                assert mism < 1e-3, mism      # a coordinate within 1 ulp of the border may flip a voxel
+        for i, t in enumerate(chain):
+            e = rel_err(t.param.grad, z["s%d_grad_%d" % (s, i)])
+            assert e < GRAD_TOL, (s, t.get_name(), e)
+        # the update from the reference's gradient must land on the reference's next parameters
+        if s + 1 < case["n_iter"]:
+            for i, t in enumerate(chain):
+                t.param.grad = z["s%d_grad_%d" % (s, i)].to(dev)
+                t.optimize_parameters(step_size=meta["steps"][0])
+                assert rel_err(t.param, z["s%d_param_%d" % (s + 1, i)]) < 2e-6, (s, t.get_name())
+    for i, t in enumerate(chain):
+        t.param = z["final_param_%d" % i].to(dev)
+        t.is_training = False
+    with torch.no_grad():
+        adv = sol.forward(data)
+        assert rel_err(adv, z["adv"]) < OUT_TOL
+        assert rel_err(sol.predict_forward(init_out), z["pf"]) < OUT_TOL
+        assert rel_err(sol.predict_backward(z["logits"].to(dev)), z["pb"]) < OUT_TOL
+    loss, _, _, _ = sol.calc_adv_consistency_loss(data, model, init_out)
+    assert abs(loss.item() - z["final_loss"].item()) <= 2e-5 * abs(z["final_loss"].item())
+
+
+def test_free_running_solver_runs_and_is_finite():
+    """adversarial_training end to end through the public API (own RNG, so no value comparison)."""
+    dev = torch.device("cuda:0")
+    meta, z = load_golden("c2d_full")
+    case = meta["case"]
+    model = make_model(case, z, dev)
+    sol = cuda_solver(case, dev)
+    torch.manual_seed(0)
+    loss = sol.adversarial_training(z["data"].to(dev), model, n_iter=2, step_sizes=1.0)
+    assert torch.isfinite(loss) and loss.item() > 0
+    loss.backward()
+    assert model.weight.grad is not None and torch.isfinite(model.weight.grad).all()
+    for t in sol.chain_of_transforms:
+        assert not t.is_training and not t.param.requires_grad
+    assert len(sol.diffs) == 4 and all(dd is not None for dd in sol.diffs)

@@ -1,0 +1,260 @@
+"""GPU parity, kernel by kernel: each advk_* entry point (through the autograd wrappers that
+call the C ABI) against the CPU oracle on the same seeded inputs.  Tolerances: fp32 path,
+north-star bound 1e-5 relative on outputs (normwise max|a-b|/max|b|); gradients that go through
+fp32 atomic accumulation are allowed 1e-4 (the reference's own CUDA backward is non-deterministic
+at that level)."""
+import math
+
+import pytest
+import torch
+
+from oracle import advchain_oracle as orc
+from tests.golden.cases import stage_cfgs
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from advchain_b200.augmentor import _ops
+    return _ops
+
+
+def _field_to_cf(field, d):
+    """[N,*sp,lanes] -> channel-first N x d x sp."""
+    return field[..., :d].permute(0, d + 1, *range(1, d + 1)).contiguous()
+
+
+def _cf_to_field(cf):
+    d = cf.shape[1]
+    f = cf.permute(0, *range(2, 2 + d), 1).contiguous()
+    if d == 3:
+        f = torch.cat([f, torch.zeros_like(f[..., :1])], -1).contiguous()
+    return f
+
+
+SIZES = [(2, [2, 3, 37, 53]), (3, [2, 2, 11, 19, 23])]
+
+
+@pytest.mark.parametrize("d,size", SIZES)
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection", -0.5, "lowest"])
+@pytest.mark.parametrize("interp", ["bilinear", "nearest"])
+def test_warp_affine(d, size, pad, interp):
+    from advchain_b200 import _lib
+    ops = _ops()
+    torch.manual_seed(1)
+    n = size[0]
+    src = torch.rand(*size)
+    eye = torch.eye(d, d + 1).unsqueeze(0).repeat(n, 1, 1)
+    theta = eye + 0.25 * torch.randn(n, d, d + 1)
+    gout = torch.randn(*size)
+    # oracle
+    s0, t0 = src.clone().requires_grad_(True), theta.clone().requires_grad_(True)
+    ref = orc.warp(s0, theta=t0, interp=interp, padding=pad)
+    ref.backward(gout)
+    # cuda
+    s1, t1 = src.to(_dev()).requires_grad_(True), theta.to(_dev()).requires_grad_(True)
+    pm, pv = ops.parse_padding(pad, s1)
+    out = ops.WarpAffine.apply(s1, t1, pm, ops.parse_interp(interp), pv)
+    out.backward(gout.to(_dev()))
+    if interp == "nearest":
+        # a coordinate within 1 ulp of a half-integer may round differently: allow a few voxels
+        bad = ((out.cpu() - ref).abs() > 1e-5).float().mean().item()
+        assert bad < 2e-3
+        return
+    assert rel_err(out, ref) < OUT_TOL
+    assert rel_err(s1.grad, s0.grad) < GRAD_TOL
+    if pad != "lowest":   # 'lowest' detaches the min in both; grads comparable too
+        assert rel_err(t1.grad, t0.grad) < GRAD_TOL
+    else:
+        assert rel_err(t1.grad, t0.grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("d,size", SIZES)
+@pytest.mark.parametrize("pad", ["zeros", "border", 0.25])
+def test_warp_field(d, size, pad):
+    ops = _ops()
+    torch.manual_seed(2)
+    n = size[0]
+    src = torch.rand(*size)
+    base = orc.base_grid(n, size[2:])
+    grid = base + 0.3 * torch.randn_like(base)          # partly outside [-1,1]
+    gout = torch.randn(*size)
+    s0, g0 = src.clone().requires_grad_(True), grid.clone().requires_grad_(True)
+    ref = orc.warp(s0, grid_cf=torch.clamp(g0, -1, 1), padding=pad)
+    ref.backward(gout)
+    s1 = src.to(_dev()).requires_grad_(True)
+    f1 = _cf_to_field(grid).to(_dev()).requires_grad_(True)
+    pm, pv = ops.parse_padding(pad, s1)
+    out = ops.WarpField.apply(s1, f1, pm, ops.parse_interp("bilinear"), pv)
+    out.backward(gout.to(_dev()))
+    assert rel_err(out, ref) < OUT_TOL
+    assert rel_err(s1.grad, s0.grad) < GRAD_TOL
+    assert rel_err(_field_to_cf(f1.grad, d), g0.grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("pscale", [1.0, 0.5])
+def test_affine_theta(d, pscale):
+    from advchain_b200.augmentor import AdvAffine
+    ops = _ops()
+    torch.manual_seed(3)
+    n = 7
+    size = [n, 1, 8, 8] if d == 2 else [n, 1, 8, 8, 8]
+    cfg = stage_cfgs(d, size)["affine"]
+    t = AdvAffine(d, cfg, device=_dev())
+    param = (2.4 * torch.rand(n, 5 if d == 2 else 9) - 1.2)          # some outside the Hardtanh range
+    gt, gi = torch.randn(n, d, d + 1), torch.randn(n, d, d + 1)
+    p0 = param.clone().requires_grad_(True)
+    th0 = orc.affine_theta(pscale * p0, cfg, d)
+    inv0 = orc.affine_inverse(th0)
+    ((th0 * gt).sum() + (inv0 * gi).sum()).backward()
+    p1 = param.to(_dev()).requires_grad_(True)
+    th1, inv1 = ops.AffineTheta.apply(p1, t._cfg(), pscale)
+    ((th1 * gt.to(_dev())).sum() + (inv1 * gi.to(_dev())).sum()).backward()
+    assert rel_err(th1, th0) < OUT_TOL
+    assert rel_err(inv1, inv0) < OUT_TOL
+    assert rel_err(p1.grad, p0.grad) < 2e-5
+
+
+MORPH = [(2, [2, 1, 48, 80], [3, 5], 1.5), (2, [1, 1, 64, 64], [4, 4], -1.5),
+         (3, [2, 1, 16, 24, 40], [2, 3, 4], 1.5), (3, [1, 1, 20, 20, 12], [3, 3, 2], -1.5)]
+
+
+@pytest.mark.parametrize("d,size,vsize,scale", MORPH)
+@pytest.mark.parametrize("vnorm", [1.0, 6.0])
+def test_morph_field(d, size, vsize, scale, vnorm):
+    """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp."""
+    from advchain_b200.augmentor import AdvMorph
+    ops = _ops()
+    torch.manual_seed(4)
+    n = size[0]
+    cfg = stage_cfgs(d, size, vector=vsize)["morph"]
+    t = AdvMorph(d, cfg, device=_dev())
+    v = orc.unit_l2(torch.rand(n, d, *vsize) * 2 - 1) * vnorm
+    gout = torch.randn(n, d, *size[2:])
+    v0 = v.clone().requires_grad_(True)
+    ref = orc.morph_field(v0, scale, size[2:])
+    ref.backward(gout)
+    t.param = v.to(_dev()).requires_grad_(True)
+    t.epsilon = abs(scale)
+    field = t._field(1 if scale > 0 else -1)
+    out = torch.clamp(_field_to_cf(field, d), -1, 1)
+    out.backward(gout.to(_dev()))
+    assert rel_err(out, ref) < OUT_TOL
+    assert rel_err(t.param.grad, v0.grad) < GRAD_TOL
+
+
+def test_morph_nb_steps_3d():
+    from advchain_b200.augmentor import AdvMorph
+    size, vsize = [2, 1, 16, 24, 40], [2, 3, 4]
+    cfg = stage_cfgs(3, size, vector=vsize)["morph"]
+    t = AdvMorph(3, cfg, device=_dev())
+    torch.manual_seed(5)
+    for vnorm in (1.0, 30.0, 200.0):
+        v = orc.unit_l2(torch.rand(2, 3, *vsize) * 2 - 1) * vnorm
+        u = torch.nn.functional.interpolate(orc.gaussian_smooth(1.5 * v), size=tuple(size[2:]),
+                                            mode="trilinear", align_corners=False)
+        t.param = v.to(_dev())
+        assert t._nb_steps() == orc.ss_steps_for(u)
+
+
+INTENS = [(2, [2, 2, 48, 64]), (3, [2, 1, 16, 24, 32])]
+
+
+@pytest.mark.parametrize("d,size", INTENS)
+@pytest.mark.parametrize("order", ["noise", "bias", "noise_bias", "bias_noise"])
+@pytest.mark.parametrize("ignore", [None, 0.0])
+def test_intensity(d, size, order, ignore):
+    from advchain_b200.augmentor import AdvBias, AdvNoise
+    ops = _ops()
+    torch.manual_seed(6)
+    cfgs = stage_cfgs(d, size)
+    x = torch.rand(*size)
+    x[x < 0.2] = 0.0                       # exact zeros so that ignore_values=0.0 bites
+    gout = torch.randn(*size)
+    on, ob = orc.Noise(cfgs["noise"], ignore), orc.Bias(cfgs["bias"], ignore)
+    on.init(); ob.init()
+    ob.param = ob.param * 1.7               # push part of the field into the clip
+    delta, cp = on.param.clone(), ob.param.clone()
+    on.param = delta.clone().requires_grad_(True)
+    ob.param = cp.clone().requires_grad_(True)
+    x0 = x.clone().requires_grad_(True)
+    stages = {"noise": [on], "bias": [ob], "noise_bias": [on, ob], "bias_noise": [ob, on]}[order]
+    ref = x0
+    for s in stages:
+        ref = s.fwd(ref)
+    ref.backward(gout)
+    bias_t = AdvBias(d, cfgs["bias"], device=_dev())
+    bias_t.init_parameters()
+    code = {"noise": ops.ORDER_NOISE, "bias": ops.ORDER_BIAS, "noise_bias": ops.ORDER_NOISE_BIAS,
+            "bias_noise": ops.ORDER_BIAS_NOISE}[order]
+    x1 = x.to(_dev()).requires_grad_(True)
+    d1 = delta.to(_dev()).requires_grad_(True)
+    c1 = cp.to(_dev()).requires_grad_(True)
+    out = ops.Intensity.apply(x1, d1 if "noise" in order else None, c1 if "bias" in order else None, code,
+                              cfgs["noise"]["epsilon"], bias_t._plan if "bias" in order else None, 1.0, ignore)
+    out.backward(gout.to(_dev()))
+    assert rel_err(out, ref) < OUT_TOL
+    assert rel_err(x1.grad, x0.grad) < OUT_TOL
+    if "noise" in order:
+        assert rel_err(d1.grad, on.param.grad) < OUT_TOL
+    if "bias" in order:
+        assert rel_err(c1.grad, ob.param.grad) < 2e-5
+        bf = orc.bias_field(cp, ob.geom, ob.eps)
+        bias_t.param = c1.detach()
+        assert rel_err(bias_t.bias_field, bf) < OUT_TOL
+
+
+@pytest.mark.parametrize("mode", ["l2", "sign", "l2_power", "sign_power"])
+def test_pgd_update(mode):
+    from advchain_b200 import _lib
+    ops = _ops()
+    torch.manual_seed(7)
+    p = torch.randn(3, 2, 33, 17)
+    g = torch.randn(3, 2, 33, 17) * 1e-6
+    g[0, 0, 0, :5] = 0.0
+    if mode == "l2":
+        ref = p + 0.7 * orc.unit_l2(g)
+    elif mode == "sign":
+        ref = p + 0.7 * g.sign()
+    elif mode == "l2_power":
+        ref = orc.unit_l2(g)
+    else:
+        ref = g.sign()
+    code = {"l2": _lib.UPD_L2_ASCENT, "sign": _lib.UPD_SIGN_ASCENT, "l2_power": _lib.UPD_L2_POWER,
+            "sign_power": _lib.UPD_SIGN_POWER}[mode]
+    out = ops.pgd_update_(p.to(_dev()).clone(), g.to(_dev()), 0.7, code)
+    assert rel_err(out, ref) < 2e-6
+
+
+def test_clamp_and_mask():
+    ops = _ops()
+    torch.manual_seed(8)
+    x = torch.randn(5, 1001)
+    g = torch.randn(5, 1001)
+    x0 = x.clone().requires_grad_(True)
+    torch.clamp(x0, -0.3, 0.4).backward(g)
+    x1 = x.to(_dev()).requires_grad_(True)
+    out = ops.Clamp.apply(x1, -0.3, 0.4)
+    out.backward(g.to(_dev()))
+    assert torch.equal(out.cpu(), torch.clamp(x, -0.3, 0.4))
+    assert torch.equal(x1.grad.cpu(), x0.grad)
+    m = x.clone()
+    m[m.abs() < 0.5] = 0
+    got = ops.nonzero_mask_(m.to(_dev()).clone())
+    assert torch.equal(got.cpu(), (m != 0).float())
+
+
+def test_no_cpu_fallback():
+    """The product path must refuse CPU tensors loudly instead of silently falling back."""
+    ops = _ops()
+    with pytest.raises(RuntimeError):
+        ops.Clamp.apply(torch.zeros(4), 0.0, 1.0)

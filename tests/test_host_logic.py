@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic and of the C-ABI boundary (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import advchain_oracle as orc
+from tests.golden.cases import stage_cfgs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from advchain_b200 import _lib
+    from advchain_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "advk.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(advk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().advk_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of every ABI struct, as gcc sees include/advk.h, equals the ctypes mirror."""
+    import subprocess
+    from advchain_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "advk.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(advk_geom), sizeof(advk_affine_cfg), sizeof(advk_morph_cfg),
+         sizeof(advk_bias_cfg), offsetof(advk_bias_cfg, A), offsetof(advk_bias_cfg, up_scale),
+         offsetof(advk_bias_cfg, magnitude));
+  return 0; }''')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_lib.Geom), ctypes.sizeof(_lib.AffineCfg), ctypes.sizeof(_lib.MorphCfg),
+            ctypes.sizeof(_lib.BiasCfg), _lib.BiasCfg.A.offset, _lib.BiasCfg.up_scale.offset,
+            _lib.BiasCfg.magnitude.offset]
+    assert got == want, (got, want)
+
+
+@pytest.mark.parametrize("d,size,spacing,down", [
+    (2, [2, 1, 64, 64], [32, 32], 2), (2, [1, 1, 48, 80], [24, 20], 2), (2, [1, 1, 40, 40], [10, 10], 1),
+    (3, [1, 1, 16, 24, 32], [8, 12, 16], 4), (3, [2, 1, 32, 32, 16], [16, 16, 8], 4),
+    (3, [1, 1, 24, 24, 24], [12, 12, 12], 2)])
+def test_bias_matrices_fold_conv_transpose_and_crop(d, size, spacing, down):
+    """low = (A_D x A_H x A_W) cp  must equal the reference's conv_transpose + crop."""
+    from advchain_b200.augmentor.bias import BiasPlan
+    cfg = stage_cfgs(d, size, spacing=spacing, downscale=down)["bias"]
+    g = orc.BiasGeometry(size, spacing, down, 3)
+    plan = BiasPlan(size[2:], g.stride, down, 3, d, 0.3, True)
+    assert plan.cp_grid == g.cp_shape
+    torch.manual_seed(0)
+    cp = torch.randn(size[0], 1, *g.cp_shape)
+    convt = torch.nn.functional.conv_transpose2d if d == 2 else torch.nn.functional.conv_transpose3d
+    f = convt(cp, g.kernel[None, None], padding=g.pad, stride=g.stride)
+    sl = [slice(None), slice(None)] + [slice(s + a, -s - b) for s, a, b in zip(g.stride, g.crop_start, g.crop_end)]
+    low_ref = f[tuple(sl)]
+    low = cp[:, 0]
+    for ax in range(d):
+        low = torch.tensordot(low, plan.A[ax], dims=([1], [1]))     # contracts the leading spatial axis
+    assert list(low.shape[1:]) == list(low_ref.shape[2:]) == plan.low_size
+    err = (low - low_ref[:, 0]).abs().max().item() / low_ref.abs().max().item()
+    assert err < 2e-6, err
+
+
+def test_gaussian_taps_are_the_separable_factor():
+    from advchain_b200.augmentor.morph import gaussian_taps
+    w = torch.from_numpy(gaussian_taps(1.0, 5))
+    assert w.numel() == 9
+    k2 = orc.gaussian_kernel(2)
+    k3 = orc.gaussian_kernel(3)
+    assert (k2 - w[:, None] * w[None, :]).abs().max() < 5e-7 * k2.max()
+    assert (k3 - w[:, None, None] * w[None, :, None] * w[None, None, :]).abs().max() < 5e-7 * k3.max()
+
+
+def test_drop_in_api_surface():
+    """Constructor signatures / method names of the reference classes."""
+    import inspect
+    from advchain_b200 import augmentor as A
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]
+    assert sig(A.AdvNoise) == ["spatial_dims", "config_dict", "power_iteration", "ignore_values", "use_gpu", "debug", "device"]
+    assert sig(A.AdvBias) == ["spatial_dims", "config_dict", "power_iteration", "ignore_values", "use_gpu", "debug", "device"]
+    assert sig(A.AdvMorph) == ["spatial_dims", "config_dict", "power_iteration", "device", "image_padding_mode", "use_gpu", "debug"]
+    assert sig(A.AdvAffine) == ["spatial_dims", "config_dict", "image_padding_mode", "power_iteration", "use_gpu", "debug", "device"]
+    assert sig(A.ComposeAdversarialTransformSolver) == [
+        "chain_of_transforms", "divergence_types", "divergence_weights", "use_gpu", "debug", "if_norm_image",
+        "min_intensity", "max_intensity", "is_gt"]
+    for cls in (A.AdvNoise, A.AdvBias, A.AdvMorph, A.AdvAffine):
+        for m in ("init_config", "init_parameters", "set_parameters", "get_parameters", "train", "eval", "forward",
+                  "backward", "predict_forward", "predict_backward", "optimize_parameters", "rescale_parameters",
+                  "get_name", "is_geometric", "unit_normalize", "set_step_size", "get_step_size"):
+            assert callable(getattr(cls, m)), (cls, m)
+    for m in ("adversarial_training", "forward", "predict_forward", "backward", "predict_backward", "loss_fn",
+              "calc_adv_consistency_loss", "optimizing_transform", "get_adv_data", "init_random_transformation",
+              "reset_transformation", "set_transformation", "train", "eval", "get_init_output", "get_net_output",
+              "if_contains_geo_transform", "make_learnable_transformation", "compute_anatomy_misoverlapping_loss"):
+        assert callable(getattr(A.ComposeAdversarialTransformSolver, m)), m
+
+
+def test_product_path_refuses_cpu_tensors():
+    from advchain_b200.augmentor import AdvNoise
+    t = AdvNoise(2, {"epsilon": 1.0, "xi": 1e-6, "data_size": [1, 1, 8, 8]}, use_gpu=False)
+    t.init_parameters()                       # parameter init is plain torch and may run anywhere
+    with pytest.raises(RuntimeError, match="no CPU"):
+        t.forward(torch.zeros(1, 1, 8, 8))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under advchain_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "advchain_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(base, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(base, f)
+
+
+def test_loss_matches_oracle_loss():
+    from advchain_b200.common.loss import calc_segmentation_consistency
+    torch.manual_seed(0)
+    for shape in ([2, 4, 24, 20], [2, 3, 10, 12, 8]):
+        a, b = torch.randn(*shape), torch.randn(*shape)
+        m = (torch.rand(shape[0], 1, *shape[2:]) > 0.2).float().expand(*shape)
+        for types, w in ((["mse", "contour"], [1.0, 0.5]), (["kl"], [1.0]), (["mse"], [1.0])):
+            x = calc_segmentation_consistency(a, b, types, w, mask=m)
+            y = orc.consistency_loss(a, b, types, w, mask=m)
+            assert abs(x.item() - y.item()) <= 1e-6 * abs(y.item())
