@@ -48,6 +48,11 @@ SIGNATURES = {
     "advk_abi_version": (_I, []),
     "advk_last_error": (C.c_char_p, []),
     "advk_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_Z)]),
+    "advk_kernel_count": (_I, []),
+    "advk_kernel_name": (C.c_char_p, [_I]),
+    "advk_launch_count": (C.c_ulonglong, [_I, _I]),
+    "advk_prof_configure": (_I, [_I, _I]),
+    "advk_prof_collect": (_I, [C.POINTER(_I), C.POINTER(_F), _I]),
     "advk_affine_theta_fwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P]),
     "advk_affine_theta_bwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P, _P]),
     "advk_warp_affine_fwd": (_I, [_G, _I, _P, _P, _I, _I, _P, _P, _P]),
@@ -137,3 +142,35 @@ def device_info():
     if rc != 0:
         raise RuntimeError(lib.advk_last_error().decode())
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)
+
+
+def kernel_names():
+    lib = load()
+    return [lib.advk_kernel_name(i).decode() for i in range(lib.advk_kernel_count())]
+
+
+def launch_count(kernel=None, reset=False):
+    """Kernels launched by the library since the last reset (all, or one kernel by name)."""
+    kid = -1 if kernel is None else kernel_names().index(kernel)
+    return int(load().advk_launch_count(kid, 1 if reset else 0))
+
+
+def prof_configure(kernel="all", capacity=8192):
+    """Bracket launches of `kernel` ("all", None = off, or a kernel name) with CUDA events."""
+    kid = -2 if kernel is None else (-1 if kernel == "all" else kernel_names().index(kernel))
+    call("advk_prof_configure", kid, capacity)
+
+
+def prof_collect(capacity=8192):
+    """-> {kernel name: [ms, ...]} for the records since the last collect."""
+    lib = load()
+    ids = (_I * capacity)()
+    ms = (_F * capacity)()
+    n = lib.advk_prof_collect(ids, ms, capacity)
+    if n < 0:
+        raise RuntimeError("advk_prof_collect failed: %s" % lib.advk_last_error().decode())
+    names = kernel_names()
+    out = {}
+    for i in range(n):
+        out.setdefault(names[ids[i]], []).append(float(ms[i]))
+    return out

@@ -37,6 +37,7 @@ class ComposeAdversarialTransformSolver(object):
         self.class_weights = None
         self._range_cache = None
         self._diff_sources = []
+        self.last_dist = None
 
     # ------------------------------------------------------------------ public entry points
     def adversarial_training(self, data, model, optimize_flags=None, init_output=None,
@@ -245,6 +246,7 @@ class ComposeAdversarialTransformSolver(object):
                 dist = self.loss_fn(pred=perturbed_output, reference=init_output.detach())
             if self.debug:
                 print('[inner loop], step {}: dist {}'.format(str(i_iter), dist.item()))
+            self.last_dist = dist.detach()
             if bool(torch.isfinite(dist)):            # the step's single host sync (NaN/Inf guard, :345)
                 dist.backward()
                 for flag, transform in zip(optimize_flags, self.chain_of_transforms):

@@ -198,8 +198,8 @@ extern "C" int advk_affine_theta_fwd(const advk_affine_cfg* cfg, const float* pa
   ADVK_REQUIRE(param && theta && N >= 1, "null pointer / bad N");
   cudaStream_t st = (cudaStream_t)stream;
   int thr = 64, blk = (N + thr - 1) / thr;
-  if (cfg->d == 2) affine_theta_fwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv);
-  else affine_theta_fwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv);
+  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_fwd, st, affine_theta_fwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv));
+  else ADVK_LAUNCH(K_affine_theta_fwd, st, affine_theta_fwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv));
   return check_launch("affine_theta_fwd");
 }
 
@@ -211,7 +211,7 @@ extern "C" int advk_affine_theta_bwd(const advk_affine_cfg* cfg, const float* pa
   ADVK_REQUIRE(param && g_param && N >= 1 && (g_theta || g_theta_inv), "null pointer / bad N");
   cudaStream_t st = (cudaStream_t)stream;
   int thr = 64, blk = (N + thr - 1) / thr;
-  if (cfg->d == 2) affine_theta_bwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param);
-  else affine_theta_bwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param);
+  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_bwd, st, affine_theta_bwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param));
+  else ADVK_LAUNCH(K_affine_theta_bwd, st, affine_theta_bwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param));
   return check_launch("affine_theta_bwd");
 }

@@ -14,6 +14,34 @@ typedef long long i64;
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// ---------------------------------------------------------------------------------------
+// Kernel registry: every launch goes through ADVK_LAUNCH so that the library can (a) count its
+// own launches (bench.py's `gpu_launches`) and (b) bracket chosen kernels with CUDA events on the
+// launching stream (bench.py's live roofline measurement; advk_prof_* in include/advk.h).
+#define ADVK_KERNELS(X)                                                                         \
+  X(affine_theta_fwd) X(affine_theta_bwd) X(lowfield_fwd) X(lowfield_bwd) X(intensity_fwd)       \
+  X(intensity_bwd) X(adjoint_axis_f) X(sumsq) X(update) X(clamp) X(clamp_bwd) X(nonzero)         \
+  X(smooth_fwd) X(smooth_bwd) X(adjoint_axis) X(lowres_smooth) X(init_phi0) X(ss_step)           \
+  X(ss_step_bwd) X(aos_to_planar) X(unorm2) X(warp_fwd) X(warp_bwd)
+enum KernelId {
+#define ADVK_X(n) K_##n,
+  ADVK_KERNELS(ADVK_X)
+#undef ADVK_X
+  K_COUNT
+};
+
+struct Prof {
+  int slot;
+  cudaStream_t st;
+  Prof(int kid, cudaStream_t s);
+  ~Prof();
+};
+#define ADVK_LAUNCH(kid, st, ...)  \
+  do {                             \
+    advk::Prof _prof((kid), (st)); \
+    __VA_ARGS__;                   \
+  } while (0)
+
 #define ADVK_REQUIRE(cond, msg)                 \
   do {                                          \
     if (!(cond)) {                              \

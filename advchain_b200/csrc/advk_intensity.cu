@@ -228,8 +228,8 @@ extern "C" int advk_bias_lowfield_fwd(const advk_bias_cfg* cfg, int N, const flo
   ADVK_REQUIRE(cp && low && N >= 1, "null pointer");
   i64 tot = (i64)N * b.lD * b.lH * b.lW;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d == 2) lowfield_fwd_kernel<2><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low);
-  else lowfield_fwd_kernel<3><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low);
+  if (d == 2) ADVK_LAUNCH(K_lowfield_fwd, st, lowfield_fwd_kernel<2><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low));
+  else ADVK_LAUNCH(K_lowfield_fwd, st, lowfield_fwd_kernel<3><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low));
   return check_launch("bias_lowfield_fwd");
 }
 
@@ -241,8 +241,8 @@ extern "C" int advk_bias_lowfield_bwd(const advk_bias_cfg* cfg, int N, const flo
   ADVK_REQUIRE(g_low && g_cp && N >= 1, "null pointer");
   unsigned blocks = (unsigned)((i64)N * b.nD * b.nH * b.nW);
   cudaStream_t st = (cudaStream_t)stream;
-  if (d == 2) lowfield_bwd_kernel<2><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp);
-  else lowfield_bwd_kernel<3><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp);
+  if (d == 2) ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<2><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
+  else ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<3><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
   return check_launch("bias_lowfield_bwd");
 }
 
@@ -261,9 +261,9 @@ extern "C" int advk_intensity_fwd(const advk_geom* gg, int C, int order, const f
   dim3 grid(blocks_for(g.S, 256), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    intensity_fwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out);
+    ADVK_LAUNCH(K_intensity_fwd, st, intensity_fwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
   else
-    intensity_fwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out);
+    ADVK_LAUNCH(K_intensity_fwd, st, intensity_fwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
   return check_launch("intensity_fwd");
 }
 
@@ -282,9 +282,9 @@ extern "C" int advk_intensity_bwd(const advk_geom* gg, int C, int order, const f
   dim3 grid(blocks_for(g.S, 256), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    intensity_bwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up);
+    ADVK_LAUNCH(K_intensity_bwd, st, intensity_bwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
   else
-    intensity_bwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up);
+    ADVK_LAUNCH(K_intensity_bwd, st, intensity_bwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
   return check_launch("intensity_bwd");
 }
 
@@ -312,12 +312,12 @@ extern "C" int advk_bias_upsample_adjoint(const advk_geom* gg, const advk_bias_c
   float* s1 = scratch;
   if (gg->d == 3) {
     i64 tot = (i64)g.N * b.lD * g.H * g.W;
-    adjoint_axis_f_kernel<<<blocks_for(tot, 256), 256, 0, st>>>(a, s1, g.N, g.D, b.lD, (i64)g.H * g.W, b.sD);
+    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot, 256), 256, 0, st>>>(a, s1, g.N, g.D, b.lD, (i64)g.H * g.W, b.sD));
     a = s1; s1 += tot;
   }
   i64 tot2 = (i64)g.N * b.lD * b.lH * g.W;
-  adjoint_axis_f_kernel<<<blocks_for(tot2, 256), 256, 0, st>>>(a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH);
+  ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot2, 256), 256, 0, st>>>(a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH));
   i64 tot3 = (i64)g.N * b.lD * b.lH * b.lW;
-  adjoint_axis_f_kernel<<<blocks_for(tot3, 256), 256, 0, st>>>(s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW);
+  ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot3, 256), 256, 0, st>>>(s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW));
   return check_launch("bias_upsample_adjoint");
 }

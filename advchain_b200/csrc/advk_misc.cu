@@ -24,6 +24,30 @@ int check_launch(const char* what) {
   return ADVK_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Launch accounting + optional per-kernel CUDA-event timing (see ADVK_LAUNCH).
+static const char* const g_kernel_names[K_COUNT + 1] = {
+#define ADVK_X(n) #n,
+    ADVK_KERNELS(ADVK_X)
+#undef ADVK_X
+    "?"};
+static unsigned long long g_launches[K_COUNT] = {0};
+static int g_prof_kid = -2;           // -2 off, -1 all kernels, >=0 one kernel id
+static int g_prof_cap = 0, g_prof_used = 0;
+static cudaEvent_t* g_prof_ev = nullptr;   // 2 events per record
+static int* g_prof_ids = nullptr;
+
+Prof::Prof(int kid, cudaStream_t s) : slot(-1), st(s) {
+  if (kid >= 0 && kid < K_COUNT) ++g_launches[kid];
+  if (g_prof_kid == -2 || (g_prof_kid >= 0 && g_prof_kid != kid) || g_prof_used >= g_prof_cap) return;
+  slot = g_prof_used++;
+  g_prof_ids[slot] = kid;
+  cudaEventRecord(g_prof_ev[2 * slot], st);
+}
+Prof::~Prof() {
+  if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st);
+}
+
 // sum of squares per sample, accumulated in double across blocks
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, size_t per, double* __restrict__ out) {
@@ -88,6 +112,47 @@ using namespace advk;
 extern "C" int advk_abi_version(void) { return ADVK_ABI_VERSION; }
 extern "C" const char* advk_last_error(void) { return g_err; }
 
+extern "C" int advk_kernel_count(void) { return K_COUNT; }
+extern "C" const char* advk_kernel_name(int kid) {
+  return g_kernel_names[(kid >= 0 && kid < K_COUNT) ? kid : K_COUNT];
+}
+extern "C" unsigned long long advk_launch_count(int kid, int reset) {
+  unsigned long long t = 0;
+  for (int i = 0; i < K_COUNT; ++i)
+    if (kid < 0 || kid == i) {
+      t += g_launches[i];
+      if (reset) g_launches[i] = 0;
+    }
+  return t;
+}
+extern "C" int advk_prof_configure(int kid, int capacity) {
+  ADVK_REQUIRE(kid >= -2 && kid < K_COUNT && capacity >= 0, "bad kernel id / capacity");
+  for (int i = 0; i < 2 * g_prof_cap; ++i) cudaEventDestroy(g_prof_ev[i]);
+  delete[] g_prof_ev; delete[] g_prof_ids;
+  g_prof_ev = nullptr; g_prof_ids = nullptr; g_prof_cap = 0; g_prof_used = 0; g_prof_kid = -2;
+  if (kid == -2 || capacity == 0) return ADVK_OK;
+  g_prof_ev = new cudaEvent_t[2 * (size_t)capacity];
+  g_prof_ids = new int[capacity];
+  for (int i = 0; i < 2 * capacity; ++i)
+    if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return check_launch("prof_configure");
+  g_prof_cap = capacity;
+  g_prof_kid = kid;
+  return ADVK_OK;
+}
+extern "C" int advk_prof_collect(int* kernel_ids, float* ms, int max_records) {
+  int n = g_prof_used < max_records ? g_prof_used : max_records;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof_ev[2 * i + 1]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms[i], g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) != cudaSuccess) {
+      check_launch("prof_collect");
+      return ADVK_ERR_CUDA;
+    }
+    kernel_ids[i] = g_prof_ids[i];
+  }
+  g_prof_used = 0;
+  return n;
+}
+
 extern "C" int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
   int dev = 0;
   cudaDeviceProp p;
@@ -114,28 +179,28 @@ extern "C" int advk_pgd_update(float* param, const float* grad, float step, int 
   if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) {
     ADVK_REQUIRE(sumsq != nullptr, "sumsq scratch is NULL");
     cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
-    sumsq_kernel<<<grid, 256, 0, st>>>(grad, per_sample, sumsq);
+    ADVK_LAUNCH(K_sumsq, st, sumsq_kernel<<<grid, 256, 0, st>>>(grad, per_sample, sumsq));
   }
-  update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq);
+  ADVK_LAUNCH(K_update, st, update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq));
   return check_launch("pgd_update");
 }
 
 extern "C" int advk_clamp(const float* x, float lo, float hi, float* out, size_t n, void* stream) {
   ADVK_REQUIRE(x && out, "null pointer");
   if (n == 0) return ADVK_OK;
-  clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, lo, hi, out, n);
+  ADVK_LAUNCH(K_clamp, (cudaStream_t)stream, clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, lo, hi, out, n));
   return check_launch("clamp");
 }
 extern "C" int advk_clamp_bwd(const float* g_out, const float* x, float lo, float hi, float* g_x, size_t n,
                               void* stream) {
   ADVK_REQUIRE(x && g_out && g_x, "null pointer");
   if (n == 0) return ADVK_OK;
-  clamp_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(g_out, x, lo, hi, g_x, n);
+  ADVK_LAUNCH(K_clamp_bwd, (cudaStream_t)stream, clamp_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(g_out, x, lo, hi, g_x, n));
   return check_launch("clamp_bwd");
 }
 extern "C" int advk_nonzero_mask(float* x, size_t n, void* stream) {
   ADVK_REQUIRE(x != nullptr, "null pointer");
   if (n == 0) return ADVK_OK;
-  nonzero_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n);
+  ADVK_LAUNCH(K_nonzero, (cudaStream_t)stream, nonzero_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n));
   return check_launch("nonzero_mask");
 }

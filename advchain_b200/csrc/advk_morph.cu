@@ -413,12 +413,12 @@ static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const
   for (int i = 0; i < KT; ++i) a.w[i] = c.w[i];
   if (DIM == 2) {
     dim3 grid((g.W + S2_TX - 1) / S2_TX, (g.H + S2_TY - 1) / S2_TY, g.N);
-    smooth2d_kernel<MODE><<<grid, S2_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<2>*>(&a));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth2d_kernel<MODE><<<grid, S2_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<2>*>(&a)));
   } else {
     int zchunk = 16;
     int nzc = (g.D + zchunk - 1) / zchunk;
     dim3 grid((g.W + S3_TX - 1) / S3_TX, (g.H + S3_TY - 1) / S3_TY, g.N * nzc);
-    smooth3d_kernel<MODE><<<grid, S3_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<3>*>(&a), zchunk, nzc);
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_kernel<MODE><<<grid, S3_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<3>*>(&a), zchunk, nzc));
   }
 }
 
@@ -473,7 +473,7 @@ template <typename T>
 static void launch_adjoint_axis(const T* a, const T* b, float vs, T* out, i64 outer, int n_in, int n_out,
                                 i64 inner, float scale, cudaStream_t st) {
   i64 tot = outer * n_out * inner;
-  adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, b, vs, out, outer, n_in, n_out, inner, scale);
+  ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, b, vs, out, outer, n_in, n_out, inner, scale));
 }
 
 template <int DIM>
@@ -495,13 +495,13 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   typedef typename V<DIM>::T T;
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   int NC = g.N * DIM;
-  lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
+  ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
   T* L = (T*)levels;
   i64 F = (i64)g.N * g.S;
   dim3 grid(blocks_for(g.S, 256), g.N);
   float inv2n = 1.0f / (float)(1u << nb);
-  init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, L);
-  for (int k = 1; k <= nb; ++k) ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F);
+  ADVK_LAUNCH(K_init_phi0, st, init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, L));
+  for (int k = 1; k <= nb; ++k) ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
   launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, st);
   return check_launch("morph_field_fwd");
 }
@@ -535,7 +535,7 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   for (int k = nb; k >= 1; --k) {
     T* nxt = bufs[(nb - k) & 1];
     cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
-    ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, cur, nxt);
+    ADVK_LAUNCH(K_ss_step_bwd, st, ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, cur, nxt));
     cur = nxt;
   }
   // dL/dphi_0 = cur - g_off (quirk Q1);  dL/du = that / 2^n;  then the upsample adjoint per axis
@@ -554,9 +554,9 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   T* s2 = s1 + (i64)g.N * c.Dl * c.Hl * g.W;
   launch_adjoint_axis<T>(s1, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
   float* planar = (float*)(s2 + (i64)g.N * lr);
-  aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr);
+  ADVK_LAUNCH(K_aos_to_planar, st, aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr));
   int NC = g.N * DIM;
-  lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, planar, scale, g_v);
+  ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, planar, scale, g_v));
   return check_launch("morph_field_bwd");
 }
 
@@ -576,11 +576,11 @@ extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg,
   cudaMemsetAsync(out_norm2, 0, sizeof(float), st);
   dim3 grid(blocks_for(g.S, 256), g.N);
   if (gg->d == 2) {
-    lowres_smooth_kernel<2><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
-    unorm2_kernel<2><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2);
+    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<2><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
+    ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<2><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
   } else {
-    lowres_smooth_kernel<3><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr);
-    unorm2_kernel<3><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2);
+    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<3><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
+    ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<3><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
   }
   return check_launch("morph_unorm2");
 }

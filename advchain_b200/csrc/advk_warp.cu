@@ -201,9 +201,9 @@ static int launch_fwd(const advk_geom* gg, int C, const float* src, const float*
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    warp_fwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out);
+    ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
   else
-    warp_fwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out);
+    ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
   return check_launch("warp_fwd");
 }
 
@@ -219,9 +219,9 @@ static int launch_bwd(const advk_geom* gg, int C, const float* g_out, const floa
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    warp_bwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field);
+    ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
   else
-    warp_bwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field);
+    ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
   return check_launch("warp_bwd");
 }
 

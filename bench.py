@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- adversarial inner-loop iterations/sec on 3-D 128^3 volumes (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one PGD inner-loop iteration (adv_compose_solver.py:308-368 of the reference):
+chain forward (noise -> bias -> morph -> affine), model forward, warp-back of the K-channel
+prediction, valid-region mask, consistency loss, backward to the four parameter sets and their
+PGD updates.  The transforms run in libadvchain_b200.so (sm_100a CUDA through the C ABI); the
+toy model `Conv3d(1,4,3,1,1)` and the consistency loss are PyTorch (out of the path's scope,
+SURVEY.md section 8) but are inside the timed step because the inner loop cannot run without them.
+
+Multi-GPU: one process per GPU (torchrun), every rank owns its own volumes (batch sharding, no
+data-path collective) -> weak scaling; value = volume-iterations of all ranks /
+max-over-ranks time.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port":
+the reference is pure Python on PyTorch ATen and `/root/reference` does not exist on the GPU box)
+on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "adv inner-loop iters/sec on 3D 128^3 volumes"
+UNIT = "iters/s"
+
+WORKLOADS = {
+    # name: (d, per-GPU size, chain)
+    "m128": (3, [1, 1, 128, 128, 128], ["noise", "bias", "morph", "affine"]),
+    "c3": (3, [2, 1, 128, 128, 64], ["noise", "bias", "morph", "affine"]),
+    "c2": (2, [8, 1, 256, 256], ["noise", "bias", "morph", "affine"]),
+    "c4shard": (2, [32, 1, 256, 256], ["noise", "bias", "morph", "affine"]),
+    "c5shard": (3, [2, 1, 256, 256, 128], ["morph", "affine"]),
+    "tiny3d": (3, [1, 1, 32, 32, 32], ["noise", "bias", "morph", "affine"]),
+}
+K_CLASSES = 4
+
+# Algorithmic 4-byte words per voxel moved by ONE launch of a kernel (SURVEY.md section 8d / DESIGN.md
+# "Kernels"): compulsory reads + writes with perfect reuse inside the launch.  d = spatial dims.
+ALGO_WORDS = {
+    "ss_step": lambda d: 2 * d,          # R phi_{k-1} (gather source == grid), W phi_k
+    "ss_step_bwd": lambda d: 3 * d,      # R phi_{k-1}, R g_k, W g_{k-1}
+    "ss_fused": lambda d: 2 * d,
+    "smooth_fwd": lambda d: 3 * d,       # R phi_n, R phi_0, W field
+    "smooth_bwd": lambda d: 5 * d,       # R g_field, R field, R phi_n, R phi_0, W g_off
+    "init_phi0": lambda d: d,
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="m128", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- helpers
+
+def make_cfgs(d, size):
+    from tests.golden.cases import stage_cfgs
+    return stage_cfgs(d, size)
+
+
+class ClockSampler(object):
+    """nvidia-smi clock / throttle-reason sampler running beside the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # under load = upper half of the samples (the sampler also sees the idle edges)
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+
+def cpu_port_step_time(d, size, chain, steps=1, warmup=0, threads=None):
+    """Times `steps` PGD inner-loop iterations of the CPU port (oracle/) on `size`; returns the
+    list of per-step seconds."""
+    from oracle import advchain_oracle as orc
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfgs = make_cfgs(d, size)
+    stages = [orc.make_stage(n, cfgs[n]) for n in chain]
+    sol = orc.Solver(stages, if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+    torch.manual_seed(0)
+    data = torch.rand(*size)
+    conv = torch.nn.Conv2d if d == 2 else torch.nn.Conv3d
+    model = conv(size[1], K_CLASSES, 3, 1, 1).eval()
+    for s in stages:
+        s.init()
+    with torch.no_grad():
+        init_out = model(data)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        sol.inner_loop(model, data, init_out, 1)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def sample_size(d, size):
+    """The bounded CPU sample: the same workload with every spatial axis halved (1/2^d of the
+    voxels); throughput is scaled by the voxel ratio."""
+    sp = [max(16, s // 2) for s in size[2:]]
+    return [size[0], size[1]] + sp
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    d, size, chain = WORKLOADS[args.workload]
+    ssz = sample_size(d, size)
+    ratio = 1.0
+    for a, b in zip(ssz[2:], size[2:]):
+        ratio *= float(a) / float(b)
+    cores = os.cpu_count() or 1
+    times = cpu_port_step_time(d, ssz, chain, steps=args.steps, warmup=args.warmup, threads=cores)
+    total = sum(times)
+    value = args.steps / total * ratio
+    sample = ("each step = 1 PGD inner-loop iteration of the CPU port on %s (%.4g of the voxels of %s); "
+              "iters/s scaled by that voxel ratio" % ("x".join(map(str, ssz)), ratio, "x".join(map(str, size))))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps / ratio,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, d, size, chain),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, d, size, chain):
+    return {"workload": "%s: %dD %s per GPU, chain %s, 1 PGD step per iteration, toy model Conv%dd(1,%d,3,1,1), "
+                        "loss mse+contour" % (args.workload, d, "x".join(map(str, size)), "->".join(chain), d,
+                                              K_CLASSES),
+            "per_gpu_size": size, "chain": chain, "n_gpus": args.gpus,
+            "l2": "per-step working set (field levels 2 signs x 9 x 32 MB at 128^3) exceeds the 126 MB L2; no flush"}
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+
+def build_solver(d, size, chain, dev):
+    from advchain_b200.augmentor import (AdvAffine, AdvBias, AdvMorph, AdvNoise,
+                                         ComposeAdversarialTransformSolver)
+    cfgs = make_cfgs(d, size)
+    ts = []
+    for n in chain:
+        cls = {"noise": AdvNoise, "bias": AdvBias, "morph": AdvMorph, "affine": AdvAffine}[n]
+        ts.append(cls(d, cfgs[n], device=dev))
+    return ComposeAdversarialTransformSolver(
+        ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5], if_norm_image=True,
+        min_intensity=0.0, max_intensity=1.0)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from advchain_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    _lib.load()   # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d, size, chain = WORKLOADS[args.workload]
+    torch.manual_seed(1234 + rank)
+    host_data = torch.rand(*size).pin_memory()
+    conv = torch.nn.Conv2d if d == 2 else torch.nn.Conv3d
+    torch.manual_seed(0)
+    model = conv(size[1], K_CLASSES, 3, 1, 1).eval().to(dev)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    sol = build_solver(d, size, chain, dev)
+    data = host_data.to(dev)
+    init_out = sol.get_init_output(model, data)
+    sol.init_random_transformation()
+    flags = [True] * len(chain)
+    steps_sz = [1.0] * len(chain)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def step(resident=True):
+        if not resident:
+            data.copy_(host_data, non_blocking=True)
+        sol.optimizing_transform(model=model, data=data, init_output=init_out, optimize_flags=flags,
+                                 n_iter=1, step_sizes=steps_sz)
+        if not resident:
+            host_loss.copy_(sol.last_dist.reshape(1), non_blocking=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, resident):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- warm-up; the last warm-up steps run with every kernel bracketed to find the dominant one
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    torch.cuda.synchronize()
+    _lib.prof_configure("all", 16384)
+    step(True)
+    step(True)
+    torch.cuda.synchronize()
+    breakdown = _lib.prof_collect(16384)
+    _lib.prof_configure(None)
+    tot = {k: sum(v) / 2.0 for k, v in breakdown.items()}          # ms per step
+    ranked = sorted(tot.items(), key=lambda kv: -kv[1])
+    dom = next((k for k, _ in ranked if k in ALGO_WORDS), None)
+
+    # ---- timed region 1: inputs resident in HBM
+    _lib.launch_count(reset=True)
+    if dom is not None:
+        _lib.prof_configure(dom, 16384)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(args.steps, True)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count(reset=True)
+    dom_ms = _lib.prof_collect(16384).get(dom, []) if dom is not None else []
+    _lib.prof_configure(None)
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    for _ in range(2):
+        step(False)
+    ms_e2e = timed(args.steps, False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    nvox = 1
+    for s in size[2:]:
+        nvox *= s
+    nvox *= size[0]
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    if dom_ms:
+        avg_ms = sum(dom_ms) / len(dom_ms)
+        algo_bytes = ALGO_WORDS[dom](d) * 4.0 * nvox
+        achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algo_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms,
+                "launches_timed": len(dom_ms),
+                "kernel_share_of_step": sum(dom_ms) / ms if ms > 0 else None}
+    # whole-step algorithmic bytes: full chain 102d+10C+5K+1 words / voxel
+    C = size[1]
+    if chain == ["noise", "bias", "morph", "affine"]:
+        words = 102 * d + 10 * C + 5 * K_CLASSES + 1
+    elif chain == ["morph", "affine"]:
+        words = 102 * d + 4 * C + 5 * K_CLASSES + 1
+    else:
+        words = None
+    value = world * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, d, size, chain),
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": host_data.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in ranked},
+        "advk_ms_per_step": round(sum(tot.values()), 4),
+    }
+    if words is not None:
+        line["step_roofline"] = {
+            "algo_bytes_per_step": words * 4.0 * nvox, "unit": "GB/s",
+            "achieved_whole_step": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9,
+            "achieved_advk_kernels_only": words * 4.0 * nvox / (sum(tot.values()) * 1e-3) / 1e9,
+            "peak": peak}
+    if not args.no_cpu_baseline and world == 1:
+        ssz = sample_size(d, size)
+        ratio = 1.0
+        for a, b in zip(ssz[2:], size[2:]):
+            ratio *= float(a) / float(b)
+        cores = os.cpu_count() or 1
+        ts = cpu_port_step_time(d, ssz, chain, steps=2, warmup=1, threads=cores)
+        line["cpu_baseline"] = {
+            "value": len(ts) / sum(ts) * ratio, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "2 PGD inner-loop iterations of the CPU port (oracle/) on %s (%.4g of the voxels), "
+                      "iters/s scaled by the voxel ratio" % ("x".join(map(str, ssz)), ratio)}
+    else:
+        line["cpu_baseline"] = None
+    if args.profile_out:
+        with open(args.profile_out, "w") as f:
+            json.dump({"breakdown_ms_per_step": dict(ranked), "line": line}, f, indent=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,19 @@ int advk_abi_version(void);
 const char* advk_last_error(void);                 /* thread-local, valid until the next call */
 int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes); /* host ptrs */
 
+/* ---- launch accounting / live kernel timing (measurement support; no reference counterpart) --
+ * advk_launch_count: number of kernels this library launched (kid < 0: all kernels) since the
+ *   last reset.  advk_prof_configure(kid, capacity): bracket every launch of kernel `kid`
+ *   (-1: every kernel, -2: off) with a pair of CUDA events recorded on the launching stream, up to
+ *   `capacity` records.  advk_prof_collect synchronises on the recorded events, writes
+ *   (kernel id, milliseconds) per record to the host arrays, resets the record list and returns
+ *   the number of records (<0 on error). */
+int advk_kernel_count(void);
+const char* advk_kernel_name(int kid);
+unsigned long long advk_launch_count(int kid, int reset);
+int advk_prof_configure(int kid, int capacity);
+int advk_prof_collect(int* kernel_ids, float* ms, int max_records);  /* host ptrs */
+
 /* ---- AdvAffine: parameters -> matrices -------------------------------------------------
  * replaces gen_batch_affine_matrix (adv_affine.py:210-273: Hardtanh, cos/sin, stack, matmul)
  * and get_inverse_matrix (adv_affine.py:316-324: batched .inverse()).
