@@ -52,7 +52,7 @@ def gaussian_kernel(d, sigma=1.0, ksize=5):
     """adv_morph.py:391-421: size is raised to 2*int(4*sigma+0.5)+1 (=9 for sigma 1),
     kernel = exp(-|r|^2 / (2 sigma^2)) normalised by its total sum."""
     ksize = max(ksize, 2 * int(4 * sigma + 0.5) + 1)
-    ax = torch.arange(ksize).float() - (ksize - 1) / 2.0
+    ax = torch.arange(ksize).to(torch.get_default_dtype()) - (ksize - 1) / 2.0
     sq = sum(m ** 2.0 for m in torch.meshgrid(*([ax] * d), indexing="ij"))
     k = torch.exp(-sq / (2 * sigma ** 2.0))
     return k / k.sum()

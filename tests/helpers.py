@@ -66,3 +66,40 @@ def cuda_solver(case, device, size=None, **solver_kw):
     kw = dict(divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5], if_norm_image=True)
     kw.update(solver_kw)
     return ComposeAdversarialTransformSolver(chain, **kw)
+
+
+def oracle_replay(case, z, params, dtype=torch.float64, train=True, size=None):
+    """Teacher-forced replay of one PGD step (or, with train=False, of the final eval-mode chain)
+    by the CPU oracle in `dtype`.  With float64 it gives the rounding-free value of every quantity
+    the fixtures hold in fp32, i.e. the reference's own fp32 noise floor
+    floor(q) = rel_err(fixture_q, oracle64_q)."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        sol = oracle_solver(case, size)
+        model = make_model(case, z).to(dtype)
+        data, init_out = z["data"].to(dtype), z["init_output"].to(dtype)
+        for s, p in zip(sol.stages, params):
+            s.init()
+            s.param = p.to(dtype)
+        out = {}
+        if train:
+            for s in sol.stages:
+                s.train()
+            dist, pred, mask = sol.step_loss(model, data, init_out)
+            dist.backward()
+            out["dist"], out["pred"] = dist.detach(), pred.detach()
+            out["grads"] = [s.param.grad.detach() for s in sol.stages]
+        else:
+            with torch.no_grad():
+                out["adv"] = sol.forward(data)
+                out["pf"] = sol.predict_forward(init_out)
+                out["pb"] = sol.predict_backward(z["logits"].to(dtype))
+        return out
+    finally:
+        torch.set_default_dtype(old)
+
+
+def noise_floor(fixture_value, value64):
+    """The reference's own fp32 rounding error for a quantity, measured against the fp64 oracle."""
+    return rel_err(fixture_value, value64)
