@@ -70,6 +70,9 @@ SIGNATURES = {
                                 _P, _P]),
     "advk_bias_scratch_floats": (_Z, [_G, C.POINTER(BiasCfg)]),
     "advk_bias_upsample_adjoint": (_I, [_G, C.POINTER(BiasCfg), _P, _P, _P, _P]),
+    "advk_loss_scratch_floats": (_Z, [_G, _I]),
+    "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _I, _P, _P, _P]),
+    "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _P, _P, _P, _P]),
     "advk_pgd_update": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P]),
     "advk_clamp": (_I, [_P, _F, _F, _P, _Z, _P]),
     "advk_clamp_bwd": (_I, [_P, _P, _F, _F, _P, _Z, _P]),

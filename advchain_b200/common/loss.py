@@ -1,8 +1,11 @@
 """Consistency loss the solver calls every inner step (reference: advchain/common/loss.py:8-249).
 
-Out of kernel scope this round: plain PyTorch on the device, written to
-reproduce the reference's numbers including its quirks -- Q9 (the 'mse' term is divided a second
-time by N*S) and Q10 (3-D contour loss uses the x-kernel for y and the last-assigned kernel for z).
+On CUDA tensors the default configuration of the solver -- scales=[0], divergence types 'mse'
+and/or 'contour', a channel-uniform mask -- runs in the fused advk_consistency_loss_* kernels
+(SURVEY.md section 8f rank f1).  Everything else ('kl', multi-scale, per-channel masks, CPU tensors)
+takes the plain PyTorch formulation below, written to reproduce the reference's numbers
+including its quirks -- Q9 (the 'mse' term is divided a second time by N*S) and Q10 (3-D contour
+loss uses the x-kernel for y and the last-assigned kernel for z).
 """
 import torch
 import torch.nn.functional as F
@@ -56,12 +59,37 @@ def kl_divergence(reference, pred, mask=None, is_gt=False):
     return torch.mean(plogp - plogq)
 
 
+def _fusable(output, reference, divergence_types, divergence_weights, scales, mask):
+    if not (output.is_cuda and reference.is_cuda and output.dtype == torch.float32):
+        return False
+    if list(scales) != [0] or output.shape != reference.shape or output.dim() not in (4, 5):
+        return False
+    if len(divergence_types) != len(divergence_weights) or not divergence_types:
+        return False
+    if any(t not in ('mse', 'contour') for t in divergence_types):
+        return False
+    if reference.requires_grad and torch.is_grad_enabled():
+        return False                      # the fused backward only produces dL/d(output)
+    if mask is not None:
+        if not mask.is_cuda or mask.shape[0] != output.shape[0] or mask.shape[2:] != output.shape[2:]:
+            return False
+        if mask.shape[1] != 1 and not (mask.shape[1] == output.shape[1] and mask.stride(1) == 0):
+            return False
+    return True
+
+
 def calc_segmentation_consistency(output, reference, divergence_types=['kl', 'contour'],
                                   divergence_weights=[1.0, 0.5], class_weights=None, scales=[0],
                                   mask=None, is_gt=False):
     """loss.py:8-87."""
     if class_weights is not None:
         raise NotImplementedError
+    if _fusable(output, reference, divergence_types, divergence_weights, scales, mask):
+        from ..augmentor import _ops
+        w = {'mse': 0.0, 'contour': 0.0}
+        for name, weight in zip(divergence_types, divergence_weights):
+            w[name] += float(weight)
+        return _ops.ConsistencyLoss.apply(output, reference, mask, w['mse'], w['contour'], bool(is_gt))
     num_classes = reference.size(1)
     spatial_dims = output.dim() - 2
     assert spatial_dims in (2, 3), 'only support 2d or 3d segmentation'

@@ -191,6 +191,22 @@ int advk_bias_upsample_adjoint(const advk_geom* g, const advk_bias_cfg* bias, co
 int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
                     size_t per_sample, double* sumsq, void* stream);
 
+/* ---- consistency loss -------------------------------------------
+ * replaces calc_segmentation_consistency (common/loss.py:8-87) for scales=[0] and divergence
+ * types 'mse' (:55-64, incl. the second division by N*S) and 'contour' (:65-79 -> contour_loss
+ * :102-220, incl. the 3-D gy := gx kernel re-use); a weight of 0 disables a term.
+ * output, reference: N x K x S logits (reference is used as probabilities when is_gt != 0);
+ * mask: N x S (one channel, broadcast over K) or NULL.  scratch: advk_loss_scratch_floats()
+ * floats, 8-byte aligned; it carries the softmax / edge maps from fwd to bwd.  loss: 1 float
+ * (device).  bwd: upstream = device pointer to dL/dloss (NULL = 1); g_output N x K x S, written. */
+size_t advk_loss_scratch_floats(const advk_geom* g, int K);
+int advk_consistency_loss_fwd(const advk_geom* g, int K, const float* output, const float* reference,
+                              const float* mask, float w_mse, float w_contour, int is_gt,
+                              float* scratch, float* loss, void* stream);
+int advk_consistency_loss_bwd(const advk_geom* g, int K, const float* mask, float w_mse,
+                              float w_contour, const float* scratch, const float* upstream,
+                              float* g_output, void* stream);
+
 /* ---- solver glue ------------------------------------------------------------------------
  * advk_clamp: out = clamp(x, lo, hi)   (solver.forward if_norm_image, adv_compose_solver.py:167-175)
  * advk_clamp_bwd: g_x = g_out * [lo <= x <= hi]

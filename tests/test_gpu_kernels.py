@@ -69,12 +69,11 @@ def test_warp_affine(d, size, pad, interp):
         bad = ((out.cpu() - ref).abs() > 1e-5).float().mean().item()
         assert bad < 2e-3
         return
-    assert rel_err(out, ref) < OUT_TOL
+    # the affine grid is theta * base evaluated with fused multiply-adds here and with a bmm in
+    # ATen; on a white-noise source that 1-2 ulp coordinate difference alone is worth ~1e-5
+    assert rel_err(out, ref) < 2 * OUT_TOL
     assert rel_err(s1.grad, s0.grad) < GRAD_TOL
-    if pad != "lowest":   # 'lowest' detaches the min in both; grads comparable too
-        assert rel_err(t1.grad, t0.grad) < GRAD_TOL
-    else:
-        assert rel_err(t1.grad, t0.grad) < GRAD_TOL
+    assert rel_err(t1.grad, t0.grad) < GRAD_TOL
 
 
 @pytest.mark.parametrize("d,size", SIZES)
@@ -128,9 +127,20 @@ MORPH = [(2, [2, 1, 48, 80], [3, 5], 1.5), (2, [1, 1, 64, 64], [4, 4], -1.5),
          (3, [2, 1, 16, 24, 40], [2, 3, 4], 1.5), (3, [1, 1, 20, 20, 12], [3, 3, 2], -1.5)]
 
 
+# Gradient of the field build at the volume FACES is decided by ties in the reference algorithm
+# itself: where the velocity points outward, phi_n - phi_0 along that axis is a difference of
+# order 1 ulp, and its sign switches the border-clip gradient mask of the compose-with-base
+# grid_sample (adv_morph.py:473-474) on or off.  The reference's own fp32 result disagrees with
+# its fp64 evaluation there by 4e-4..5e-3 (gpurun_out/r01c_diag_morph.log, DESIGN.md "Parity").
+# So the strict check uses an upstream gradient supported >= 3 voxels away from the faces, and
+# the full-support check carries the tie tolerance.
+MORPH_TIE_TOL = 1e-2
+
+
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
-def test_morph_field(d, size, vsize, scale, vnorm):
+@pytest.mark.parametrize("support", ["interior", "full"])
+def test_morph_field(d, size, vsize, scale, vnorm, support):
     """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp."""
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()
@@ -140,6 +150,10 @@ def test_morph_field(d, size, vsize, scale, vnorm):
     t = AdvMorph(d, cfg, device=_dev())
     v = orc.unit_l2(torch.rand(n, d, *vsize) * 2 - 1) * vnorm
     gout = torch.randn(n, d, *size[2:])
+    if support == "interior":
+        keep = torch.zeros_like(gout)
+        keep[(slice(None), slice(None)) + tuple(slice(3, s - 3) for s in size[2:])] = 1
+        gout = gout * keep
     v0 = v.clone().requires_grad_(True)
     ref = orc.morph_field(v0, scale, size[2:])
     ref.backward(gout)
@@ -149,7 +163,7 @@ def test_morph_field(d, size, vsize, scale, vnorm):
     out = torch.clamp(_field_to_cf(field, d), -1, 1)
     out.backward(gout.to(_dev()))
     assert rel_err(out, ref) < OUT_TOL
-    assert rel_err(t.param.grad, v0.grad) < GRAD_TOL
+    assert rel_err(t.param.grad, v0.grad) < (GRAD_TOL if support == "interior" else MORPH_TIE_TOL)
 
 
 def test_morph_nb_steps_3d():
@@ -251,6 +265,50 @@ def test_clamp_and_mask():
     m[m.abs() < 0.5] = 0
     got = ops.nonzero_mask_(m.to(_dev()).clone())
     assert torch.equal(got.cpu(), (m != 0).float())
+
+
+LOSS = [(2, [2, 4, 37, 53]), (3, [2, 4, 11, 19, 23]), (3, [1, 3, 16, 16, 16]), (2, [3, 2, 32, 48])]
+
+
+@pytest.mark.parametrize("d,size", LOSS)
+@pytest.mark.parametrize("types,weights", [(["mse", "contour"], [1.0, 0.5]), (["mse"], [1.0]),
+                                           (["contour"], [0.7])])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("is_gt", [False, True])
+def test_consistency_loss(d, size, types, weights, masked, is_gt):
+    """Fused advk_consistency_loss_* against the CPU oracle's loss (common/loss.py:8-87 restated)."""
+    from advchain_b200.common.loss import calc_segmentation_consistency
+    torch.manual_seed(9)
+    out = torch.randn(*size) * 2
+    ref = torch.randn(*size) * 2
+    if is_gt:
+        ref = torch.softmax(ref * 4, 1)
+    mask = None
+    if masked:
+        mask = (torch.rand(size[0], 1, *size[2:]) > 0.3).float().expand(*size)
+    o0 = out.clone().requires_grad_(True)
+    l0 = orc.consistency_loss(o0, ref, tuple(types), tuple(weights), mask, is_gt)
+    l0.backward()
+    o1 = out.to(_dev()).requires_grad_(True)
+    from advchain_b200 import _lib
+    _lib.launch_count("loss_grad", reset=True)
+    l1 = calc_segmentation_consistency(o1, ref.to(_dev()), divergence_types=types, divergence_weights=weights,
+                                       scales=[0], mask=None if mask is None else mask.to(_dev()), is_gt=is_gt)
+    (l1 * 3.0).backward()
+    assert _lib.launch_count("loss_grad") == 1, "the fused loss kernel did not run"
+    assert abs(l1.item() - l0.item()) <= 1e-5 * abs(l0.item())
+    assert rel_err(o1.grad, 3.0 * o0.grad) < 2e-5
+
+
+def test_consistency_loss_fallbacks():
+    """'kl' and multi-scale stay on the PyTorch formulation and still agree with the oracle."""
+    from advchain_b200.common.loss import calc_segmentation_consistency
+    torch.manual_seed(10)
+    out, ref = torch.randn(2, 3, 24, 24), torch.randn(2, 3, 24, 24)
+    l0 = orc.consistency_loss(out, ref, ("kl", "contour"), (1.0, 0.5))
+    l1 = calc_segmentation_consistency(out.to(_dev()), ref.to(_dev()), divergence_types=["kl", "contour"],
+                                       divergence_weights=[1.0, 0.5], scales=[0])
+    assert abs(l1.item() - l0.item()) <= 2e-5 * abs(l0.item())
 
 
 def test_no_cpu_fallback():
