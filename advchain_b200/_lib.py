@@ -37,6 +37,25 @@ class BiasCfg(C.Structure):
                 ("magnitude", C.c_float)]
 
 
+class ChainStage(C.Structure):
+    _fields_ = [("kind", C.c_int), ("intensity_order", C.c_int), ("noise_scale", C.c_float),
+                ("use_ignore", C.c_int), ("ignore_value", C.c_float), ("bias", C.POINTER(BiasCfg)),
+                ("delta", C.c_void_p), ("low", C.c_void_p), ("field", C.c_void_p), ("theta", C.c_void_p),
+                ("pad_mode", C.c_int), ("interp", C.c_int), ("pad_values", C.c_void_p),
+                ("g_delta", C.c_void_p), ("g_up", C.c_void_p), ("g_field", C.c_void_p),
+                ("g_theta", C.c_void_p)]
+
+
+CHAIN_MAX_STAGES = 6
+STAGE_INTENSITY, STAGE_WARP_FIELD, STAGE_WARP_AFFINE = 0, 1, 2
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("g", Geom), ("C", C.c_int), ("n_stages", C.c_int), ("stages", ChainStage * CHAIN_MAX_STAGES),
+                ("do_clamp", C.c_int), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
+                ("want_mask", C.c_int), ("binarize_mask", C.c_int)]
+
+
 _P = C.c_void_p
 _F = C.c_float
 _I = C.c_int
@@ -70,6 +89,10 @@ SIGNATURES = {
                                 _P, _P]),
     "advk_bias_scratch_floats": (_Z, [_G, C.POINTER(BiasCfg)]),
     "advk_bias_upsample_adjoint": (_I, [_G, C.POINTER(BiasCfg), _P, _P, _P, _P]),
+    "advk_chain_set_cooperative": (_I, [_I]),
+    "advk_chain_workspace_floats": (_I, [C.POINTER(ChainDesc), C.POINTER(_Z), C.POINTER(_Z)]),
+    "advk_chain_apply_fwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
+    "advk_chain_apply_bwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_loss_scratch_floats": (_Z, [_G, _I]),
     "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _I, _P, _P, _P]),
     "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _P, _P, _P, _P]),

@@ -45,6 +45,14 @@ def parse_padding(padding_mode, data):
     raise ValueError("unknown padding mode %r" % (padding_mode,))
 
 
+def fused_padding(padding_mode, data):
+    """Padding for a stage of the fused chain, or None when the mode needs the generic path
+    ('lowest' takes the minimum of the stage's own input, which only exists mid-kernel)."""
+    if isinstance(padding_mode, str) and padding_mode == "lowest":
+        return None
+    return parse_padding(padding_mode, data)
+
+
 def _f32c(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
@@ -259,6 +267,196 @@ def bias_field_only(cp, plan, size, cp_scale=1.0):
     call("advk_intensity_fwd", C.byref(g), 1, ORDER_BIAS, ptr(ones), None, 0.0, ptr(low), cfg_ref, 0, 0.0,
          ptr(out), None, stream())
     return out
+
+
+# --------------------------------------------------------------------------------------- fused chain
+
+
+class BiasLow(Function):
+    """control points -> low-res bias field (conv_transposeNd + crop, adv_bias.py:293-307)."""
+
+    @staticmethod
+    def forward(ctx, cp, plan, cp_scale):
+        cp = _f32c(cp)
+        n = cp.shape[0]
+        low = torch.empty((n,) + tuple(plan.low_size), dtype=torch.float32, device=cp.device)
+        call("advk_bias_lowfield_fwd", C.byref(plan.cfg(cp.device)), n, ptr(cp), float(cp_scale), ptr(low),
+             stream())
+        ctx.meta = (plan, float(cp_scale), cp.shape)
+        return low
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_low):
+        plan, cp_scale, shape = ctx.meta
+        g_low = _f32c(g_low)
+        g_cp = torch.empty(shape, dtype=torch.float32, device=g_low.device)
+        call("advk_bias_lowfield_bwd", C.byref(plan.cfg(g_low.device)), shape[0], ptr(g_low), cp_scale,
+             ptr(g_cp), stream())
+        return g_cp, None, None
+
+
+class ChainSpec(object):
+    """Host description of a fused chain: `stages` is a list of dicts
+         {"kind": "intensity", "order", "noise_scale", "ignore", "plan", "delta": slot|None, "low": slot|None}
+         {"kind": "field" | "affine", "pad", "interp", "padv": tensor|None, "param": slot}
+    where a slot indexes the flat tensor list handed to ChainApply.apply."""
+
+    def __init__(self, stages, clamp=None, want_mask=False, binarize=False):
+        self.stages = stages
+        self.clamp = clamp
+        self.want_mask = want_mask
+        self.binarize = binarize
+
+
+def _fill_desc(spec, g, channels, params, grads=None):
+    d = _lib.ChainDesc()
+    d.g, d.C, d.n_stages = g, channels, len(spec.stages)
+    keep = []
+    for k, st in enumerate(spec.stages):
+        e = d.stages[k]
+        if st["kind"] == "intensity":
+            e.kind = _lib.STAGE_INTENSITY
+            e.intensity_order = st["order"]
+            e.noise_scale = float(st["noise_scale"])
+            e.use_ignore = 0 if st["ignore"] is None else 1
+            e.ignore_value = float(st["ignore"] or 0.0)
+            if st["delta"] is not None:
+                e.delta = ptr(params[st["delta"]])
+            if st["low"] is not None:
+                cfg = st["plan"].cfg(params[st["low"]].device)
+                keep.append(cfg)
+                e.bias = C.pointer(cfg)
+                e.low = ptr(params[st["low"]])
+            if grads is not None:
+                if st["delta"] is not None and grads[st["delta"]] is not None:
+                    e.g_delta = ptr(grads[st["delta"]])
+                if st["low"] is not None and grads[st["low"]] is not None:
+                    e.g_up = ptr(grads[st["low"]])
+        else:
+            field = st["kind"] == "field"
+            e.kind = _lib.STAGE_WARP_FIELD if field else _lib.STAGE_WARP_AFFINE
+            e.pad_mode, e.interp = st["pad"], st["interp"]
+            e.pad_values = ptr(st["padv"])
+            if field:
+                e.field = ptr(params[st["param"]])
+            else:
+                e.theta = ptr(params[st["param"]])
+            if grads is not None and grads[st["param"]] is not None:
+                if field:
+                    e.g_field = ptr(grads[st["param"]])
+                else:
+                    e.g_theta = ptr(grads[st["param"]])
+    if spec.clamp is not None:
+        d.do_clamp, d.clamp_lo, d.clamp_hi = 1, float(spec.clamp[0]), float(spec.clamp[1])
+    d.want_mask = 1 if spec.want_mask else 0
+    d.binarize_mask = 1 if spec.binarize else 0
+    return d, keep
+
+
+class ChainApply(Function):
+    """The fused chain-apply launch (advk_chain_apply_fwd/bwd, include/advk.h): solver.forward,
+    predict_forward, backward / predict_backward and the valid-region mask of
+    adv_compose_solver.py:148-219, 321-325."""
+
+    @staticmethod
+    def forward(ctx, src, mask_src, spec, *params):
+        src = _f32c(src)
+        g = _lib.geom(src.shape)
+        params = [None if p is None else _f32c(p) for p in params]
+        d, keep = _fill_desc(spec, g, src.shape[1], params)
+        n_stash, n_scr = _lib._Z(), _lib._Z()
+        call("advk_chain_workspace_floats", C.byref(d), C.byref(n_stash), C.byref(n_scr))
+        stash = torch.empty(max(int(n_stash.value), 1), dtype=torch.float32, device=src.device)
+        out = torch.empty_like(src)
+        mask_out = None
+        if spec.want_mask:
+            mask_out = torch.empty((g.N, 1) + tuple(src.shape[2:]), dtype=torch.float32, device=src.device)
+            if mask_src is not None:
+                mask_src = _f32c(mask_src)
+        call("advk_chain_apply_fwd", C.byref(d), ptr(src), ptr(mask_src) if spec.want_mask else None,
+             ptr(stash), ptr(out), ptr(mask_out), stream())
+        ctx.save_for_backward(src, stash, *params)
+        ctx.meta = (spec, g, int(n_scr.value))
+        if mask_out is not None:
+            ctx.mark_non_differentiable(mask_out, stash)
+        else:
+            ctx.mark_non_differentiable(stash)
+        return out, mask_out, stash
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_out, _g_mask, _g_stash):
+        saved = ctx.saved_tensors
+        src, stash, params = saved[0], saved[1], list(saved[2:])
+        spec, g, n_scr = ctx.meta
+        need = ctx.needs_input_grad
+        grads = [None] * len(params)
+        ups = []
+        for st in spec.stages:
+            if st["kind"] == "intensity":
+                if st["delta"] is not None and need[3 + st["delta"]]:
+                    grads[st["delta"]] = torch.empty_like(params[st["delta"]])
+                if st["low"] is not None and need[3 + st["low"]]:
+                    grads[st["low"]] = torch.empty(g.N * g.D * g.H * g.W, dtype=torch.float32, device=src.device)
+                    ups.append(st)
+            elif need[3 + st["param"]]:
+                prm = params[st["param"]]
+                grads[st["param"]] = torch.empty_like(prm) if st["kind"] == "field" else torch.zeros_like(prm)
+        g_src = torch.empty_like(src) if need[0] else None
+        d, keep = _fill_desc(spec, g, src.shape[1], params, grads)
+        scratch = torch.empty(max(n_scr, 1), dtype=torch.float32, device=src.device)
+        call("advk_chain_apply_bwd", C.byref(d), ptr(_f32c(g_out)), ptr(src), ptr(stash), ptr(scratch),
+             ptr(g_src), stream())
+        for st in ups:           # g_up (N x S) -> g_low through the adjoint of the linear upsample
+            low = params[st["low"]]
+            cfg_ref = C.byref(st["plan"].cfg(src.device))
+            ns_ = _lib.load().advk_bias_scratch_floats(C.byref(g), cfg_ref)
+            tmp = torch.empty(max(int(ns_), 1), dtype=torch.float32, device=src.device)
+            g_low = torch.empty_like(low)
+            call("advk_bias_upsample_adjoint", C.byref(g), cfg_ref, ptr(grads[st["low"]]), ptr(tmp), ptr(g_low),
+                 stream())
+            grads[st["low"]] = g_low
+        return (g_src, None, None) + tuple(grads)
+
+
+def run_chain(src, stages, clamp=None, mask_src=None, want_mask=False, binarize=False):
+    """stages: list of host stage dicts holding TENSORS ("delta", "cp", "field", "theta"); adjacent
+    noise/bias stages with the same ignore value are merged into one INTENSITY stage.
+    Returns (out, mask_out or None, per-stage-boundary views of the stash)."""
+    merged = []
+    for st in stages:
+        if (st["kind"] == "intensity" and merged and merged[-1]["kind"] == "intensity"
+                and merged[-1]["ignore"] == st["ignore"] and merged[-1]["order"] in (ORDER_NOISE, ORDER_BIAS)
+                and st["order"] in (ORDER_NOISE, ORDER_BIAS) and merged[-1]["order"] != st["order"]):
+            a = merged[-1]
+            first_noise = a["order"] == ORDER_NOISE
+            n_, b_ = (a, st) if first_noise else (st, a)
+            merged[-1] = dict(kind="intensity", order=ORDER_NOISE_BIAS if first_noise else ORDER_BIAS_NOISE,
+                              noise_scale=n_["noise_scale"], ignore=a["ignore"], plan=b_["plan"],
+                              cp_scale=b_["cp_scale"], delta=n_["delta"], cp=b_["cp"], span=a.get("span", 1) + 1)
+        else:
+            merged.append(dict(st))
+    if len(merged) > _lib.CHAIN_MAX_STAGES:
+        return None
+    params, spec_stages = [], []
+    for st in merged:
+        if st["kind"] == "intensity":
+            e = dict(kind="intensity", order=st["order"], noise_scale=st.get("noise_scale", 0.0),
+                     ignore=st["ignore"], plan=st.get("plan"), delta=None, low=None)
+            if st["order"] != ORDER_BIAS:
+                e["delta"] = len(params)
+                params.append(st["delta"])
+            if st["order"] != ORDER_NOISE:
+                e["low"] = len(params)
+                params.append(BiasLow.apply(st["cp"], st["plan"], st["cp_scale"]))
+        else:
+            e = dict(kind=st["kind"], pad=st["pad"], interp=st["interp"], padv=st.get("padv"), param=len(params))
+            params.append(st["field"] if st["kind"] == "field" else st["theta"])
+        spec_stages.append(e)
+    spec = ChainSpec(spec_stages, clamp=clamp, want_mask=want_mask, binarize=binarize)
+    out, mask_out, stash = ChainApply.apply(src, mask_src, spec, *params)
+    return out, mask_out, (stash, merged)
 
 
 # --------------------------------------------------------------------------------------- loss

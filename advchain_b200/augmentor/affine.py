@@ -146,6 +146,27 @@ class AdvAffine(AdvTransformBase):
         pad, padv = _ops.parse_padding(padding_mode, data)
         return _ops.WarpAffine.apply(data, affine_matrix, pad, _ops.parse_interp(interp), padv)
 
+    def _stage(self, mode, data, interp=None, padding_mode=None):
+        if self.param is None:
+            self.init_parameters()
+        fwd = mode in ("fwd", "pfwd")
+        if interp is None:
+            interp = self.forward_interp if fwd else self.backward_interp
+        pp = _ops.fused_padding(self.image_padding_mode, data)      # quirk Q5
+        if pp is None:
+            return NotImplemented
+        theta, theta_inv = self._theta_pair()
+        if fwd:
+            self.affine_matrix = theta
+            self._inv_of = (theta, theta_inv)
+        else:
+            assert self.affine_matrix is not None, 'play forward before backward'
+            if self._inv_of is None or self._inv_of[0] is not self.affine_matrix:
+                return NotImplemented                                 # user-replaced matrix: generic path
+            theta_inv = self._inv_of[1]
+        return dict(kind="affine", theta=theta if fwd else theta_inv, pad=pp[0], padv=pp[1],
+                    interp=_ops.parse_interp(interp))
+
     def forward(self, data, interp=None, padding_mode=None):
         """adv_affine.py:121-146."""
         if self.param is None:

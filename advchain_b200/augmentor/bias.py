@@ -219,6 +219,17 @@ class AdvBias(AdvTransformBase):
         self.diff = lambda: self.bias_field.expand(*data.shape)
         return out
 
+    def _stage(self, mode, data, interp=None, padding_mode=None):
+        if mode != "fwd":
+            return None
+        if self.param is None:
+            self.init_parameters()
+        ignore = self.ignore_values
+        if ignore is not None and not isinstance(ignore, float):
+            raise TypeError('ignore values must be in float type, but got %r' % (ignore,))
+        return dict(kind="intensity", order=_ops.ORDER_BIAS, ignore=ignore, plan=self._plan,
+                    cp=self.param, cp_scale=self._cp_scale())
+
     def backward(self, data, **kwargs):
         return data
 

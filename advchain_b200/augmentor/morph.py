@@ -202,6 +202,18 @@ class AdvMorph(AdvTransformBase):
         pad, padv = _ops.parse_padding(padding_mode, data)
         return _ops.WarpField.apply(data, field, pad, _ops.parse_interp(interp), padv)
 
+    def _stage(self, mode, data, interp=None, padding_mode=None):
+        if self.param is None:
+            self.init_parameters()
+        fwd = mode in ("fwd", "pfwd")
+        if interp is None:
+            interp = self.forward_interp if fwd else self.backward_interp
+        pp = _ops.fused_padding(self.image_padding_mode if padding_mode is None else padding_mode, data)
+        if pp is None:
+            return NotImplemented
+        return dict(kind="field", field=self._field(+1 if fwd else -1), pad=pp[0], padv=pp[1],
+                    interp=_ops.parse_interp(interp))
+
     def forward(self, data, interp=None, padding_mode=None):
         """adv_morph.py:285-311."""
         if self.param is None:

@@ -53,6 +53,15 @@ class AdvNoise(AdvTransformBase):
         self.diff = lambda: out.detach() - src
         return out
 
+    def _stage(self, mode, data, interp=None, padding_mode=None):
+        """Stage of the fused chain (None: identity for the prediction paths)."""
+        if mode != "fwd":
+            return None
+        if self.param is None:
+            self.init_parameters()
+        return dict(kind="intensity", order=_ops.ORDER_NOISE, noise_scale=self._scale(),
+                    ignore=self.ignore_values, delta=self.param)
+
     def optimize_parameters(self, step_size=None):
         if step_size is None:
             step_size = self.step_size

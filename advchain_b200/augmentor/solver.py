@@ -16,6 +16,12 @@ import torch
 from ..common.loss import calc_segmentation_consistency
 from ..common.utils import _disable_tracking_bn_stats, _fix_dropout
 from . import _ops
+from .affine import AdvAffine
+from .bias import AdvBias
+from .morph import AdvMorph
+from .noise import AdvNoise
+
+_FUSABLE = (AdvNoise, AdvBias, AdvMorph, AdvAffine)
 
 
 class ComposeAdversarialTransformSolver(object):
@@ -38,6 +44,9 @@ class ComposeAdversarialTransformSolver(object):
         self._range_cache = None
         self._diff_sources = []
         self.last_dist = None
+        self.use_fused_chain = True       # one advk_chain_apply launch per chain pass
+        self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
+        self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
     # ------------------------------------------------------------------ public entry points
     def adversarial_training(self, data, model, optimize_flags=None, init_output=None,
@@ -122,14 +131,71 @@ class ComposeAdversarialTransformSolver(object):
         return (self._range_cache[1] if lo is None else lo,
                 self._range_cache[2] if hi is None else hi)
 
+    # -- fused path ---------------------------------------------------------------------
+    @staticmethod
+    def _chain_key(chain):
+        return [(t, t.param, -1 if t.param is None else t.param._version, t.is_training, t.power_iteration)
+                for t in chain]
+
+    @staticmethod
+    def _same_key(a, b):
+        return (a is not None and len(a) == len(b)
+                and all(x[0] is y[0] and x[1] is y[1] and x[2:] == y[2:] for x, y in zip(a, b)))
+
+    def _stages_for(self, chain, mode, data, interp, padding_mode):
+        """Stage list of the fused executor for `chain` ('fwd' image chain, 'pfwd' prediction forward,
+        'bwd' reversed inverse chain), or None when some transform needs the generic path."""
+        if not self.use_fused_chain or not data.is_cuda or data.dim() not in (4, 5):
+            return None
+        seq = chain if mode in ("fwd", "pfwd") else list(reversed(chain))
+        stages = []
+        for t in seq:
+            if type(t) not in _FUSABLE or tuple(t.data_size[2:]) != tuple(data.shape[2:]) \
+                    or t.data_size[0] != data.shape[0]:
+                return None
+            st = t._stage(mode, data, interp, padding_mode)
+            if st is NotImplemented:
+                return None
+            if st is not None:
+                if st["kind"] == "intensity" and t.data_size[1] != data.shape[1]:
+                    return None
+                stages.append(st)
+        return stages
+
+    def _lazy_diffs(self, data, chain, interp, padding_mode):
+        """`transform.diff` after a fused pass: recomputed per transform on first access (quirk Q11)."""
+        state = {}
+
+        def ensure():
+            if not state:
+                with torch.no_grad():
+                    t_data = data
+                    for t in chain:
+                        t_data = t.forward(t_data, interp=interp, padding_mode=padding_mode)
+                        state[id(t)] = t.diff
+            return state
+
+        for t in chain:
+            t.diff = (lambda t=t: ensure()[id(t)])
+
     def forward(self, data, chain_of_transforms=None, interp=None, padding_mode=None):
         """adv_compose_solver.py:148-176."""
         if chain_of_transforms is None:
             chain_of_transforms = self.chain_of_transforms
+        self._diff_sources = list(chain_of_transforms)
+        stages = self._stages_for(chain_of_transforms, "fwd", data, interp, padding_mode)
+        if stages:
+            clamp = self._intensity_range(data) if self.if_norm_image else None
+            has_geo = any(st["kind"] != "intensity" for st in stages)
+            res = _ops.run_chain(data.detach(), stages, clamp=clamp, want_mask=has_geo)
+            if res is not None:
+                out, mask, _ = res
+                self._fwd_mask = (self._chain_key(chain_of_transforms), mask) if has_geo else None
+                self._lazy_diffs(data.detach(), chain_of_transforms, interp, padding_mode)
+                return out
         t_data = data.detach()
         for transform in chain_of_transforms:
             t_data = transform.forward(t_data, interp=interp, padding_mode=padding_mode)
-        self._diff_sources = list(chain_of_transforms)
         if self.if_norm_image:
             lo, hi = self._intensity_range(data)
             t_data = _ops.Clamp.apply(t_data, lo, hi)
@@ -141,23 +207,46 @@ class ComposeAdversarialTransformSolver(object):
         """adv_compose_solver.py:184-197."""
         if chain_of_transforms is None:
             chain_of_transforms = self.chain_of_transforms
+        self._diff_sources = list(chain_of_transforms)
+        stages = self._stages_for(chain_of_transforms, "pfwd", data, interp, padding_mode)
+        if stages:
+            res = _ops.run_chain(data, stages)
+            if res is not None:
+                return res[0]
         for transform in chain_of_transforms:
             data = transform.predict_forward(data, interp=interp, padding_mode=padding_mode)
-        self._diff_sources = list(chain_of_transforms)
         return data
 
     def backward(self, data, chain_of_transforms=None, interp=None, padding_mode=None):
         """adv_compose_solver.py:199-208."""
         if chain_of_transforms is None:
             chain_of_transforms = self.chain_of_transforms
+        stages = self._stages_for(chain_of_transforms, "bwd", data, interp, padding_mode)
+        if stages:
+            res = _ops.run_chain(data, stages)
+            if res is not None:
+                return res[0]
         for transform in reversed(chain_of_transforms):
             data = transform.backward(data, interp=interp, padding_mode=padding_mode)
         return data
 
     def predict_backward(self, data, chain_of_transforms=None, interp=None, padding_mode=None):
-        """adv_compose_solver.py:210-219."""
+        """adv_compose_solver.py:210-219.  Fused path: the K prediction channels and the valid-region
+        mask (started by the last forward()) go through the reversed inverse chain in one launch."""
         if chain_of_transforms is None:
             chain_of_transforms = self.chain_of_transforms
+        stages = self._stages_for(chain_of_transforms, "bwd", data, interp, padding_mode)
+        if stages:
+            key = self._chain_key(chain_of_transforms)
+            fm = self._fwd_mask
+            with_mask = (fm is not None and self._same_key(fm[0], key) and interp is None
+                         and padding_mode is None and fm[1].shape[0] == data.shape[0])
+            res = _ops.run_chain(data, stages, mask_src=fm[1] if with_mask else None, want_mask=with_mask,
+                                 binarize=True)
+            if res is not None:
+                if with_mask:
+                    self._mask_cache = (key, res[1])
+                return res[0]
         for transform in reversed(chain_of_transforms):
             data = transform.predict_backward(data, interp=interp, padding_mode=padding_mode)
         return data
@@ -165,7 +254,14 @@ class ComposeAdversarialTransformSolver(object):
     def valid_region_mask(self, like, chain_of_transforms=None):
         """predict_backward(predict_forward(ones)) != 0 (adv_compose_solver.py:321-325), computed
         forward-only on ONE channel (all K channels of the reference's mask are identical) and
-        returned as an expanded N x K x spatial view."""
+        returned as an expanded N x K x spatial view.  After a fused forward() + predict_backward()
+        the mask has already been produced by those two launches."""
+        if chain_of_transforms is None:
+            chain_of_transforms = self.chain_of_transforms
+        mc = self._mask_cache
+        if mc is not None and self._same_key(mc[0], self._chain_key(chain_of_transforms)) \
+                and mc[1].shape[0] == like.shape[0] and mc[1].shape[2:] == like.shape[2:]:
+            return mc[1].expand_as(like)
         with torch.no_grad():
             ones = torch.ones((like.shape[0], 1) + tuple(like.shape[2:]), dtype=torch.float32,
                               device=like.device)
@@ -194,8 +290,8 @@ class ComposeAdversarialTransformSolver(object):
         with _fix_dropout(model):
             adv_output = self.get_net_output(model, adv_data.detach().clone())
         if self.if_contains_geo_transform(chain_of_transforms):
-            mask = self.valid_region_mask(init_output, chain_of_transforms)
             warped_back_adv_output = self.predict_backward(adv_output, chain_of_transforms)
+            mask = self.valid_region_mask(init_output, chain_of_transforms)
             dist = self.loss_fn(pred=warped_back_adv_output, reference=init_output.detach(), mask=mask)
         else:
             warped_back_adv_output = adv_output

@@ -1,0 +1,590 @@
+// advk_chain.cu -- the fused chain-apply kernels: ONE persistent cooperative launch applies a
+// whole chain of transforms (forward), ONE applies its adjoint (backward).
+//
+// A chain is a short program of stages over an N x C x S tensor:
+//     INTENSITY   x -> x + eps*delta, x * bias(cp)        adv_noise.py:79-90, adv_bias.py:152-188
+//     WARP_FIELD  x -> grid_sample(x, phi)                adv_morph.py:524-558
+//     WARP_AFFINE x -> grid_sample(x, affine_grid(theta)) adv_affine.py:289-314
+// in any order (the reference's solver.forward / predict_backward loops, adv_compose_solver.py:
+// 148-176, 210-219, issue one ATen call sequence per transform).  Two resampling stages in a row
+// are a gather of a gather with unbounded displacement, so each stage needs the COMPLETE output
+// of the previous one; the stages therefore run as phases of one grid separated by grid-wide
+// barriers, with the (N x C x S) intermediates living in L2 (8 MB per channel at 128^3 against
+// 126 MB of L2).  The same executor runs
+//   * the image chain            noise -> bias -> morph -> affine (+ the if_norm_image clamp),
+//     with a one-channel "valid region" mask riding along the geometric stages, and
+//   * the prediction warp-back   affine^-1 -> morph(-v) on K channels + the mask, binarised.
+// Backward: zero the scatter targets, then walk the stages in reverse; a warp stage scatters the
+// upstream gradient to its source (fp32 RED), computes the spatial Jacobian from the stashed
+// source, and reduces it to d x (d+1) per sample (affine) or writes it per voxel (field).
+//
+// Work distribution: the flattened (sample, voxel) space is cut into tiles of 256 voxels that
+// never straddle a sample; block b owns a contiguous range of tiles (good L1 locality for the
+// gathers, and per-sample reductions are flushed only when the sample changes).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "advk_intensity.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace advk {
+
+constexpr int CT = 256;
+constexpr int MAX_STAGES = ADVK_CHAIN_MAX_STAGES;
+
+struct Stage {
+  int kind;
+  // intensity
+  int order; float ns; int use_ig; float ig; BiasCfg b;
+  const float* delta; const float* low;
+  // warp
+  const void* phi; const float* theta; int pad, interp; const float* pv;
+  // data path
+  const float* src; float* dst;
+  const float* msrc; float* mdst; int binarize;
+  // adjoint
+  const float* g_dst; float* g_src; int zero_g_src;
+  float* g_delta; float* g_up; void* g_phi; float* g_theta;
+};
+
+struct Program {
+  Dims g; int C; int n; int first_bwd;
+  int do_clamp; float lo, hi; int want_mask;
+  int tps;          // tiles per sample
+  i64 n_tiles;
+  Stage st[MAX_STAGES];
+};
+
+template <int DIM> struct Stencil { Axis x, y, z; };
+
+template <int DIM>
+__device__ __forceinline__ Stencil<DIM> make_stencil(float cx, float cy, float cz, const Dims& g, int pad, int interp) {
+  Stencil<DIM> s;
+  s.x = make_axis(cx, g.W, pad, interp);
+  s.y = make_axis(cy, g.H, pad, interp);
+  if (DIM == 3) s.z = make_axis(cz, g.D, pad, interp);
+  else { s.z.i0 = 0; s.z.w0 = 1.f; s.z.w1 = 0.f; s.z.v0 = true; s.z.v1 = false; s.z.mult = 0.f; }
+  return s;
+}
+
+// f(q, wx, wy, wz, dx, dy, dz) for every in-bounds corner; q = linear voxel index in the sample.
+template <int DIM, class F>
+__device__ __forceinline__ void for_corners(const Stencil<DIM>& s, const Dims& g, F f) {
+  const i64 HW = (i64)g.H * g.W;
+#pragma unroll
+  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+    const bool vz = dz ? s.z.v1 : s.z.v0;
+    const float wz = dz ? s.z.w1 : s.z.w0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const bool vy = dy ? s.y.v1 : s.y.v0;
+      const float wy = dy ? s.y.w1 : s.y.w0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const bool vx = dx ? s.x.v1 : s.x.v0;
+        const float wx = dx ? s.x.w1 : s.x.w0;
+        if (vx && vy && vz)
+          f((i64)(s.z.i0 + dz) * HW + (i64)(s.y.i0 + dy) * g.W + (s.x.i0 + dx), wx, wy, wz, dx, dy, dz);
+      }
+    }
+  }
+}
+
+struct Vox { int n, x, y, z; i64 p; bool ok; };
+
+__device__ __forceinline__ Vox tile_voxel(const Program& P, i64 t) {
+  Vox v;
+  v.n = (int)(t / P.tps);
+  v.p = (t % P.tps) * CT + threadIdx.x;
+  v.ok = v.p < P.g.S;
+  v.x = (int)(v.p % P.g.W);
+  v.y = (int)((v.p / P.g.W) % P.g.H);
+  v.z = (int)(v.p / ((i64)P.g.W * P.g.H));
+  return v;
+}
+
+__device__ __forceinline__ void tile_range(const Program& P, i64& t0, i64& t1) {
+  i64 per = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+  t0 = (i64)blockIdx.x * per;
+  t1 = t0 + per < P.n_tiles ? t0 + per : P.n_tiles;
+}
+
+// sampling coordinates of output voxel v; r* = raw field values (for the clamp-range mask),
+// b* = base coordinates (affine only)
+template <int DIM, bool FIELD>
+__device__ __forceinline__ void stage_coords(const Program& P, const Stage& s, const Vox& v, float& cx, float& cy,
+                                             float& cz, float& rx, float& ry, float& rz, float& bx, float& by,
+                                             float& bz) {
+  const Dims& g = P.g;
+  if (FIELD) {
+    if (DIM == 2) {
+      float2 f = reinterpret_cast<const float2*>(s.phi)[(i64)v.n * g.S + v.p];
+      rx = f.x; ry = f.y; rz = 0.f;
+    } else {
+      float4 f = reinterpret_cast<const float4*>(s.phi)[(i64)v.n * g.S + v.p];
+      rx = f.x; ry = f.y; rz = f.z;
+    }
+    cx = clampf(rx, -1.f, 1.f); cy = clampf(ry, -1.f, 1.f); cz = clampf(rz, -1.f, 1.f);
+    bx = by = bz = 0.f;
+  } else {
+    bx = base_coord(v.x, g.W, 0.f); by = base_coord(v.y, g.H, 0.f);
+    if (DIM == 2) {
+      const float* t = s.theta + v.n * 6;
+      cx = t[0] * bx + t[1] * by + t[2];
+      cy = t[3] * bx + t[4] * by + t[5];
+      cz = 0.f; bz = 0.f;
+    } else {
+      bz = base_coord(v.z, g.D, 0.f);
+      const float* t = s.theta + v.n * 12;
+      cx = t[0] * bx + t[1] * by + t[2] * bz + t[3];
+      cy = t[4] * bx + t[5] * by + t[6] * bz + t[7];
+      cz = t[8] * bx + t[9] * by + t[10] * bz + t[11];
+    }
+    rx = cx; ry = cy; rz = cz;
+  }
+}
+
+// ------------------------------------------------------------------------------------ forward
+
+template <int DIM>
+__device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last) {
+  const Dims& g = P.g;
+  i64 t0, t1;
+  tile_range(P, t0, t1);
+  const bool clamp = last && P.do_clamp;
+  for (i64 t = t0; t < t1; ++t) {
+    Vox v = tile_voxel(P, t);
+    if (!v.ok) continue;
+    float bv = 1.f;
+    if (s.order != 0) {
+      float braw; bool pass;
+      bv = bias_value(s.b, bias_up<DIM>(s.b, s.low + (i64)v.n * s.b.lD * s.b.lH * s.b.lW, v.z, v.y, v.x, g, v.p), braw, pass);
+    }
+    for (int c = 0; c < P.C; ++c) {
+      i64 q = ((i64)v.n * P.C + c) * g.S + v.p;
+      float val = intensity_point(s.order, s.src[q], s.order != 1 ? s.delta[q] : 0.f, s.ns, bv, s.use_ig, s.ig);
+      if (clamp) val = clampf(val, P.lo, P.hi);
+      s.dst[q] = val;
+    }
+  }
+}
+
+template <int DIM, bool FIELD>
+__device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
+  const Dims& g = P.g;
+  i64 t0, t1;
+  tile_range(P, t0, t1);
+  const bool clamp = last && P.do_clamp;
+  for (i64 t = t0; t < t1; ++t) {
+    Vox v = tile_voxel(P, t);
+    if (!v.ok) continue;
+    float cx, cy, cz, rx, ry, rz, bx, by, bz;
+    stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    const float pv = s.pv ? s.pv[v.n] : 0.f;
+    for (int c = 0; c < P.C; ++c) {
+      const i64 cb = ((i64)v.n * P.C + c) * g.S;
+      const float* src = s.src + cb;
+      float acc = 0.f;
+      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
+        acc += (__ldg(src + q) - pv) * (wx * wy * wz);
+      });
+      float val = acc + pv;
+      if (clamp) val = clampf(val, P.lo, P.hi);
+      s.dst[cb + v.p] = val;
+    }
+    if (s.mdst) {
+      const float* ms = s.msrc ? s.msrc + (i64)v.n * g.S : nullptr;
+      float acc = 0.f;
+      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
+        acc += ((ms ? __ldg(ms + q) : 1.f) - pv) * (wx * wy * wz);
+      });
+      float m = acc + pv;
+      if (s.binarize) m = (m != 0.f) ? 1.f : 0.f;
+      s.mdst[(i64)v.n * g.S + v.p] = m;
+    }
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void run_stage_fwd(const Program& P, int k) {
+  const Stage& s = P.st[k];
+  const bool last = (k == P.n - 1);
+  if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_fwd<DIM>(P, s, last);
+  else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_fwd<DIM, true>(P, s, last);
+  else stage_warp_fwd<DIM, false>(P, s, last);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(CT)
+chain_fwd_kernel(const __grid_constant__ Program P) {
+  cg::grid_group grid = cg::this_grid();
+  for (int k = 0; k < P.n; ++k) {
+    if (k) grid.sync();
+    run_stage_fwd<DIM>(P, k);
+  }
+}
+
+// one stage per launch (used when a cooperative launch is not possible / for A-B timing)
+template <int DIM>
+__global__ void __launch_bounds__(CT)
+chain_fwd_stage_kernel(const __grid_constant__ Program P, int k) {
+  run_stage_fwd<DIM>(P, k);
+}
+
+// ------------------------------------------------------------------------------------ backward
+
+__device__ void zero_buffers(const Program& P) {
+  const i64 n4 = ((i64)P.g.N * P.C * P.g.S) / 4;     // host guarantees N*C*S % 4 == 0 or handles tail
+  const i64 tail0 = n4 * 4, tot = (i64)P.g.N * P.C * P.g.S;
+  for (int k = P.first_bwd; k < P.n; ++k) {
+    const Stage& s = P.st[k];
+    if (!s.zero_g_src || !s.g_src) continue;
+    float4* d4 = reinterpret_cast<float4*>(s.g_src);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (i64)gridDim.x * blockDim.x)
+      d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (i64 i = tail0 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (i64)gridDim.x * blockDim.x)
+      s.g_src[i] = 0.f;
+  }
+}
+
+template <int DIM>
+__device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last) {
+  const Dims& g = P.g;
+  i64 t0, t1;
+  tile_range(P, t0, t1);
+  const bool clamp = last && P.do_clamp;
+  for (i64 t = t0; t < t1; ++t) {
+    Vox v = tile_voxel(P, t);
+    if (!v.ok) continue;
+    float bv = 1.f, braw = 1.f;
+    bool pass = true;
+    if (s.order != 0)
+      bv = bias_value(s.b, bias_up<DIM>(s.b, s.low + (i64)v.n * s.b.lD * s.b.lH * s.b.lW, v.z, v.y, v.x, g, v.p), braw, pass);
+    float gb = 0.f;
+    for (int c = 0; c < P.C; ++c) {
+      i64 q = ((i64)v.n * P.C + c) * g.S + v.p;
+      float go = s.g_dst[q];
+      const float x0 = s.src[q];
+      const float dl = (s.order != 1) ? s.delta[q] : 0.f;
+      if (clamp) {
+        float val = intensity_point(s.order, x0, dl, s.ns, bv, s.use_ig, s.ig);
+        if (!(val >= P.lo && val <= P.hi)) go = 0.f;
+      }
+      float gd;
+      float gi = intensity_point_bwd(s.order, go, x0, dl, s.ns, bv, s.use_ig, s.ig, gd, gb);
+      if (s.g_delta) s.g_delta[q] = gd;
+      if (s.g_src) s.g_src[q] = gi;
+    }
+    if (s.g_up) s.g_up[(i64)v.n * g.S + v.p] = pass ? gb * (s.b.use_log ? braw : 1.f) : 0.f;
+  }
+}
+
+template <int DIM, bool FIELD>
+__device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, float* red) {
+  constexpr int NG = DIM * (DIM + 1);
+  const Dims& g = P.g;
+  i64 t0, t1;
+  tile_range(P, t0, t1);
+  const bool clamp = last && P.do_clamp;
+  const bool want_theta = !FIELD && s.g_theta != nullptr;
+  float acc[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) acc[i] = 0.f;
+  int cur_n = -1;
+  for (i64 t = t0; t < t1; ++t) {
+    Vox v = tile_voxel(P, t);
+    if (want_theta && v.n != cur_n) {            // block-uniform
+      if (cur_n >= 0) {
+        block_sum<NG>(acc, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int i = 0; i < NG; ++i) atomicAdd(s.g_theta + cur_n * NG + i, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NG; ++i) acc[i] = 0.f;
+      }
+      cur_n = v.n;
+    }
+    if (!v.ok) continue;
+    float cx, cy, cz, rx, ry, rz, bx, by, bz;
+    stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    const float pv = s.pv ? s.pv[v.n] : 0.f;
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    for (int c = 0; c < P.C; ++c) {
+      const i64 cb = ((i64)v.n * P.C + c) * g.S;
+      const float* src = s.src + cb;
+      float go = s.g_dst[cb + v.p];
+      if (clamp) {
+        float a = 0.f;
+        for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
+          a += (__ldg(src + q) - pv) * (wx * wy * wz);
+        });
+        a += pv;
+        if (!(a >= P.lo && a <= P.hi)) go = 0.f;
+      }
+      float* gs = s.g_src ? s.g_src + cb : nullptr;
+      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int dx, int dy, int dz) {
+        if (gs) atomicAdd(gs + q, go * (wx * wy * wz));
+        float val = (__ldg(src + q) - pv) * go;
+        ggx += (dx ? val : -val) * (wy * wz);
+        ggy += (dy ? val : -val) * (wx * wz);
+        if (DIM == 3) ggz += (dz ? val : -val) * (wx * wy);
+      });
+    }
+    ggx *= st.x.mult; ggy *= st.y.mult; ggz *= st.z.mult;
+    if (FIELD) {
+      if (s.g_phi) {
+        // consumers clamp the stored field to [-1,1]; torch.clamp passes gradient on the closed interval
+        if (!(rx >= -1.f && rx <= 1.f)) ggx = 0.f;
+        if (!(ry >= -1.f && ry <= 1.f)) ggy = 0.f;
+        if (DIM == 2) {
+          reinterpret_cast<float2*>(s.g_phi)[(i64)v.n * g.S + v.p] = make_float2(ggx, ggy);
+        } else {
+          if (!(rz >= -1.f && rz <= 1.f)) ggz = 0.f;
+          reinterpret_cast<float4*>(s.g_phi)[(i64)v.n * g.S + v.p] = make_float4(ggx, ggy, ggz, 0.f);
+        }
+      }
+    } else if (want_theta) {
+      if (DIM == 2) {
+        acc[0] += ggx * bx; acc[1] += ggx * by; acc[2] += ggx;
+        acc[3] += ggy * bx; acc[4] += ggy * by; acc[5] += ggy;
+      } else {
+        acc[0] += ggx * bx; acc[1] += ggx * by; acc[2] += ggx * bz; acc[3] += ggx;
+        acc[4] += ggy * bx; acc[5] += ggy * by; acc[6] += ggy * bz; acc[7] += ggy;
+        acc[8] += ggz * bx; acc[9] += ggz * by; acc[10] += ggz * bz; acc[11] += ggz;
+      }
+    }
+  }
+  if (want_theta && cur_n >= 0) {
+    block_sum<NG>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NG; ++i) atomicAdd(s.g_theta + cur_n * NG + i, acc[i]);
+    }
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void run_stage_bwd(const Program& P, int k, float* red) {
+  const Stage& s = P.st[k];
+  const bool last = (k == P.n - 1);
+  if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_bwd<DIM>(P, s, last);
+  else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_bwd<DIM, true>(P, s, last, red);
+  else stage_warp_bwd<DIM, false>(P, s, last, red);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(CT)
+chain_bwd_kernel(const __grid_constant__ Program P) {
+  __shared__ float red[12 * 32];
+  cg::grid_group grid = cg::this_grid();
+  zero_buffers(P);
+  for (int k = P.n - 1; k >= P.first_bwd; --k) {
+    grid.sync();
+    run_stage_bwd<DIM>(P, k, red);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(CT)
+chain_bwd_stage_kernel(const __grid_constant__ Program P, int k) {
+  __shared__ float red[12 * 32];
+  if (k < 0) zero_buffers(P);
+  else run_stage_bwd<DIM>(P, k, red);
+}
+
+// ------------------------------------------------------------------------------------ host
+
+static int g_coop = -1;   // -1: decide on first use
+
+static bool coop_enabled() {
+  int& v = g_coop;
+  if (v < 0) {
+    const char* e = getenv("ADVK_CHAIN_COOP");
+    int dev = 0, sup = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sup, cudaDevAttrCooperativeLaunch, dev);
+    v = (sup && !(e && e[0] == '0')) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename K>
+static int coop_grid(K kernel) {
+  int dev = 0, sms = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CT, 0);
+  if (occ < 1) occ = 1;
+  return sms * occ;
+}
+
+// intermediates are laid out in slots rounded up to 4 floats so that every slot is 16-byte aligned
+static inline i64 slot_floats(i64 n) { return (n + 3) & ~(i64)3; }
+
+// Stash layout (floats): for k = 0 .. n-2: dst of stage k (N*C*S); then, if want_mask, one N*S
+// mask buffer per warp stage except the last warp stage (whose mask output is `mask_out`).
+static bool build_program(const advk_chain_desc* d, Program& P, const float* src, const float* mask_src,
+                          float* stash, float* out, float* mask_out) {
+  if (!d || !make_dims(&d->g, P.g) || d->C < 1 || d->n_stages < 1 || d->n_stages > MAX_STAGES) return false;
+  P.C = d->C; P.n = d->n_stages; P.first_bwd = 0;
+  P.do_clamp = d->do_clamp; P.lo = d->clamp_lo; P.hi = d->clamp_hi; P.want_mask = d->want_mask;
+  P.tps = (int)((P.g.S + CT - 1) / CT);
+  P.n_tiles = (i64)P.tps * P.g.N;
+  const i64 ncs = slot_floats((i64)P.g.N * P.C * P.g.S), ns = slot_floats((i64)P.g.N * P.g.S);
+  int last_warp = -1;
+  for (int k = 0; k < P.n; ++k)
+    if (d->stages[k].kind != ADVK_STAGE_INTENSITY) last_warp = k;
+  float* mstash = stash ? stash + (i64)(P.n - 1) * ncs : nullptr;
+  const float* cur = src;
+  const float* mcur = mask_src;
+  for (int k = 0; k < P.n; ++k) {
+    const advk_chain_stage& a = d->stages[k];
+    Stage& s = P.st[k];
+    memset(&s, 0, sizeof(s));
+    s.kind = a.kind;
+    if (a.kind == ADVK_STAGE_INTENSITY) {
+      if (a.intensity_order < 0 || a.intensity_order > 3) return false;
+      s.order = a.intensity_order; s.ns = a.noise_scale; s.use_ig = a.use_ignore; s.ig = a.ignore_value;
+      if (s.order != 1 && !a.delta) return false;
+      if (s.order != 0) {
+        if (!make_bias(a.bias, d->g.d, s.b) || !a.low) return false;
+        if (!s.b.upsample && !(s.b.lD == P.g.D && s.b.lH == P.g.H && s.b.lW == P.g.W)) return false;
+      }
+      s.delta = a.delta; s.low = a.low;
+    } else if (a.kind == ADVK_STAGE_WARP_FIELD) {
+      if (!a.field) return false;
+      s.phi = a.field;
+    } else if (a.kind == ADVK_STAGE_WARP_AFFINE) {
+      if (!a.theta) return false;
+      s.theta = a.theta;
+    } else return false;
+    if (a.kind != ADVK_STAGE_INTENSITY) {
+      if (a.pad_mode < 0 || a.pad_mode > 2 || a.interp < 0 || a.interp > 1) return false;
+      s.pad = a.pad_mode; s.interp = a.interp; s.pv = a.pad_values;
+    }
+    s.src = cur;
+    if (k == P.n - 1) s.dst = out;
+    else {
+      if (!stash) return false;
+      s.dst = stash + (i64)k * ncs;
+    }
+    cur = s.dst;
+    if (P.want_mask && a.kind != ADVK_STAGE_INTENSITY) {
+      s.msrc = mcur;
+      if (k == last_warp) { s.mdst = mask_out; s.binarize = d->binarize_mask; if (!mask_out) return false; }
+      else { s.mdst = mstash; mstash += ns; }
+      mcur = s.mdst;
+    }
+  }
+  return true;
+}
+
+template <int DIM>
+static int launch_fwd(Program& P, cudaStream_t st) {
+  if (coop_enabled() && P.n > 1) {
+    static int gmax = coop_grid(chain_fwd_kernel<DIM>);
+    int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
+    void* args[] = {(void*)&P};
+    ADVK_LAUNCH(K_chain_fwd, st,
+                cudaLaunchCooperativeKernel((void*)chain_fwd_kernel<DIM>, dim3(grid), dim3(CT), args, 0, st));
+  } else {
+    int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
+    for (int k = 0; k < P.n; ++k)
+      ADVK_LAUNCH(K_chain_fwd_stage, st, chain_fwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, k));
+  }
+  return check_launch("chain_apply_fwd");
+}
+
+template <int DIM>
+static int launch_bwd(Program& P, cudaStream_t st) {
+  if (coop_enabled()) {
+    static int gmax = coop_grid(chain_bwd_kernel<DIM>);
+    int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
+    void* args[] = {(void*)&P};
+    ADVK_LAUNCH(K_chain_bwd, st,
+                cudaLaunchCooperativeKernel((void*)chain_bwd_kernel<DIM>, dim3(grid), dim3(CT), args, 0, st));
+  } else {
+    int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
+    ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, -1));
+    for (int k = P.n - 1; k >= P.first_bwd; --k)
+      ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, k));
+  }
+  return check_launch("chain_apply_bwd");
+}
+
+}  // namespace advk
+
+using namespace advk;
+
+extern "C" int advk_chain_set_cooperative(int enable) {
+  int prev = coop_enabled() ? 1 : 0;
+  if (enable) {
+    g_coop = -1;
+    (void)coop_enabled();      // re-probe the device attribute / environment
+  } else {
+    g_coop = 0;
+  }
+  return prev;
+}
+
+extern "C" int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* stash_floats,
+                                           size_t* scratch_floats) {
+  Dims g;
+  ADVK_REQUIRE(d && make_dims(&d->g, g) && d->C >= 1 && d->n_stages >= 1 && d->n_stages <= MAX_STAGES,
+               "bad chain descriptor");
+  const i64 ncs = slot_floats((i64)g.N * d->C * g.S), ns = slot_floats((i64)g.N * g.S);
+  int warps = 0;
+  for (int k = 0; k < d->n_stages; ++k)
+    if (d->stages[k].kind != ADVK_STAGE_INTENSITY) ++warps;
+  if (stash_floats)
+    *stash_floats = (size_t)((i64)(d->n_stages - 1) * ncs + ((d->want_mask && warps > 1) ? (i64)(warps - 1) * ns : 0));
+  if (scratch_floats) *scratch_floats = (size_t)((i64)(d->n_stages - 1) * ncs);
+  return ADVK_OK;
+}
+
+extern "C" int advk_chain_apply_fwd(const advk_chain_desc* d, const float* src, const float* mask_src,
+                                    float* stash, float* out, float* mask_out, void* stream) {
+  Program P;
+  ADVK_REQUIRE(src && out, "null pointer");
+  ADVK_REQUIRE(build_program(d, P, src, mask_src, stash, out, mask_out), "bad chain descriptor");
+  cudaStream_t st = (cudaStream_t)stream;
+  return d->g.d == 2 ? launch_fwd<2>(P, st) : launch_fwd<3>(P, st);
+}
+
+extern "C" int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out, const float* src,
+                                    const float* stash, float* scratch, float* g_src, void* stream) {
+  Program P;
+  ADVK_REQUIRE(src && g_out, "null pointer");
+  // data-path pointers are rebuilt exactly as in the forward (dst of the last stage / masks unused)
+  advk_chain_desc dd = *d;
+  dd.want_mask = 0;
+  ADVK_REQUIRE(build_program(&dd, P, src, nullptr, const_cast<float*>(stash), nullptr, nullptr),
+               "bad chain descriptor");
+  const i64 slot = slot_floats((i64)P.g.N * P.C * P.g.S);
+  // gradient plumbing: g_dst of stage k = g_src of stage k+1 (scratch slot k), last = g_out
+  int first = P.n;   // earliest stage that produces a requested gradient
+  for (int k = 0; k < P.n; ++k) {
+    const advk_chain_stage& a = d->stages[k];
+    Stage& s = P.st[k];
+    s.g_delta = a.g_delta; s.g_up = a.g_up; s.g_phi = a.g_field; s.g_theta = a.g_theta;
+    bool wants = a.g_delta || a.g_up || a.g_field || a.g_theta;
+    if (wants && k < first) first = k;
+  }
+  if (g_src) first = 0;
+  if (first == P.n) return ADVK_OK;       // nothing requested
+  P.first_bwd = first;
+  if (first < P.n - 1 || (first > 0 && false)) ADVK_REQUIRE(scratch != nullptr, "scratch is NULL");
+  for (int k = P.n - 1; k >= first; --k) {
+    Stage& s = P.st[k];
+    s.g_dst = (k == P.n - 1) ? g_out : scratch + (i64)k * slot;
+    if (k == 0) s.g_src = g_src;                  // may be NULL: gradient w.r.t. the chain input not wanted
+    else if (k == first) s.g_src = nullptr;       // nobody consumes it
+    else s.g_src = scratch + (i64)(k - 1) * slot;
+    s.zero_g_src = (s.kind != ADVK_STAGE_INTENSITY && s.g_src != nullptr) ? 1 : 0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return d->g.d == 2 ? launch_bwd<2>(P, st) : launch_bwd<3>(P, st);
+}

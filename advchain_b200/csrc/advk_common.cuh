@@ -23,7 +23,8 @@ int check_launch(const char* what);
   X(intensity_bwd) X(adjoint_axis_f) X(sumsq) X(update) X(clamp) X(clamp_bwd) X(nonzero)         \
   X(smooth_fwd) X(smooth_bwd) X(adjoint_axis) X(lowres_smooth) X(init_phi0) X(ss_step)           \
   X(ss_step_bwd) X(aos_to_planar) X(unorm2) X(warp_fwd) X(warp_bwd) X(loss_softmax)               \
-  X(loss_contour) X(loss_finalize) X(loss_grad)
+  X(loss_contour) X(loss_finalize) X(loss_grad) X(chain_fwd) X(chain_fwd_stage) X(chain_bwd)         \
+  X(chain_bwd_stage)
 enum KernelId {
 #define ADVK_X(n) K_##n,
   ADVK_KERNELS(ADVK_X)

@@ -7,31 +7,9 @@
 // A_ax (built once on the host from the reference's own kernel construction), so the low-res field
 // is  low = (A_D (x) A_H (x) A_W) cp  -- a few hundred FMAs per low-res voxel -- and the full-res
 // bias is evaluated on the fly per voxel (linear upsample + exp + clip) without ever being stored.
-#include "advk_common.cuh"
+#include "advk_intensity.cuh"
 
 namespace advk {
-
-struct BiasCfg {
-  int nD, nH, nW;     // control points
-  int lD, lH, lW;     // low-res field
-  const float* AD; const float* AH; const float* AW;
-  float sD, sH, sW;
-  int upsample, use_log;
-  float mag;
-};
-
-static bool make_bias(const advk_bias_cfg* b, int d, BiasCfg& o) {
-  if (!b) return false;
-  o.nD = b->n_cp[0]; o.nH = b->n_cp[1]; o.nW = b->n_cp[2];
-  o.lD = b->low[0]; o.lH = b->low[1]; o.lW = b->low[2];
-  o.AD = b->A[0]; o.AH = b->A[1]; o.AW = b->A[2];
-  o.sD = b->up_scale[0]; o.sH = b->up_scale[1]; o.sW = b->up_scale[2];
-  o.upsample = b->upsample; o.use_log = b->use_log; o.mag = b->magnitude;
-  if (o.nD < 1 || o.nH < 1 || o.nW < 1 || o.lD < 1 || o.lH < 1 || o.lW < 1) return false;
-  if (d == 2 && (o.nD != 1 || o.lD != 1)) return false;
-  if (!o.AH || !o.AW || (d == 3 && !o.AD)) return false;
-  return true;
-}
 
 // low[n,z,y,x] = sum_{i,j,k} AD[z,i] AH[y,j] AW[x,k] * (s * cp[n,i,j,k])
 template <int DIM>
@@ -78,32 +56,6 @@ lowfield_bwd_kernel(BiasCfg b, int N, const float* __restrict__ g_low, float s, 
   if (threadIdx.x == 0) g_cp[e] = s * v[0];
 }
 
-// upsampled (pre-exp) field at a voxel
-template <int DIM>
-__device__ __forceinline__ float bias_up(const BiasCfg& b, const float* __restrict__ low_n, int z, int y,
-                                         int x, const Dims& g, i64 p) {
-  if (!b.upsample) return low_n[p];
-  UpAxis ux = up_axis(x, b.lW, b.sW), uy = up_axis(y, b.lH, b.sH);
-  float acc = 0.f;
-#pragma unroll
-  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-    int zi = 0; float lz = 1.f;
-    if (DIM == 3) { UpAxis uz = up_axis(z, b.lD, b.sD); zi = dz ? uz.i1 : uz.i0; lz = dz ? uz.l1 : uz.l0; }
-    const float* r0 = low_n + ((i64)zi * b.lH + uy.i0) * b.lW;
-    const float* r1 = low_n + ((i64)zi * b.lH + uy.i1) * b.lW;
-    acc += lz * (uy.l0 * (ux.l0 * __ldg(r0 + ux.i0) + ux.l1 * __ldg(r0 + ux.i1)) +
-                 uy.l1 * (ux.l0 * __ldg(r1 + ux.i0) + ux.l1 * __ldg(r1 + ux.i1)));
-  }
-  return acc;
-}
-
-__device__ __forceinline__ float bias_value(const BiasCfg& b, float up, float& braw, bool& pass) {
-  braw = b.use_log ? expf(up) : 1.f + up;
-  float t = braw - 1.f;
-  pass = (t >= -b.mag && t <= b.mag);
-  return 1.f + clampf(t, -b.mag, b.mag);
-}
-
 // order: 0 noise, 1 bias, 2 noise->bias, 3 bias->noise
 template <int DIM>
 __global__ void __launch_bounds__(256)
@@ -122,22 +74,7 @@ intensity_fwd_kernel(Dims g, int C, int order, const float* __restrict__ x, cons
   }
   for (int c = 0; c < C; ++c) {
     i64 q = ((i64)n * C + c) * g.S + p;
-    float t = x[q];
-    if (order == 0 || order == 2) {
-      float t0 = t;
-      t = t0 + ns * delta[q];
-      if (use_ig && fabsf(t0 - ig) < 1e-8f) t = ig;
-    }
-    if (order != 0) {
-      float t0 = t;
-      t = t0 * bv;
-      if (use_ig && fabsf(t0 - ig) < 1e-8f) t = ig;
-    }
-    if (order == 3) {
-      float t0 = t;
-      t = t0 + ns * delta[q];
-      if (use_ig && fabsf(t0 - ig) < 1e-8f) t = ig;
-    }
+    float t = intensity_point(order, x[q], order != 1 ? delta[q] : 0.f, ns, bv, use_ig, ig);
     out[q] = t;
   }
 }
@@ -159,35 +96,8 @@ intensity_bwd_kernel(Dims g, int C, int order, const float* __restrict__ g_out, 
   float gb = 0.f;
   for (int c = 0; c < C; ++c) {
     i64 q = ((i64)n * C + c) * g.S + p;
-    float go = g_out[q];
-    float x0 = x[q];
-    float gd = 0.f;
-    if (order == 0) {
-      if (use_ig && fabsf(x0 - ig) < 1e-8f) go = 0.f;
-      gd = ns * go;
-    } else if (order == 1) {
-      if (use_ig && fabsf(x0 - ig) < 1e-8f) go = 0.f;
-      gb += go * x0;
-      go *= bv;
-    } else if (order == 2) {
-      float t1 = x0 + ns * delta[q];
-      bool ig1 = use_ig && fabsf(x0 - ig) < 1e-8f;
-      if (ig1) t1 = ig;
-      if (use_ig && fabsf(t1 - ig) < 1e-8f) go = 0.f;
-      gb += go * t1;
-      go *= bv;
-      if (ig1) go = 0.f;
-      gd = ns * go;
-    } else {
-      float t1 = x0 * bv;
-      bool ig1 = use_ig && fabsf(x0 - ig) < 1e-8f;
-      if (ig1) t1 = ig;
-      if (use_ig && fabsf(t1 - ig) < 1e-8f) go = 0.f;
-      gd = ns * go;
-      if (ig1) go = 0.f;
-      gb += go * x0;
-      go *= bv;
-    }
+    float gd;
+    float go = intensity_point_bwd(order, g_out[q], x[q], (order >= 2) ? delta[q] : 0.f, ns, bv, use_ig, ig, gd, gb);
     if (g_delta) g_delta[q] = gd;
     if (g_x) g_x[q] = go;
   }

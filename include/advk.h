@@ -191,6 +191,81 @@ int advk_bias_upsample_adjoint(const advk_geom* g, const advk_bias_cfg* bias, co
 int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
                     size_t per_sample, double* sumsq, void* stream);
 
+/* ---- fused chain apply ---------------------------------------------------------------------
+ * ONE launch applies a whole chain of transforms to an N x C x S tensor, ONE launch applies its
+ * adjoint.  Replaces the per-transform loops of ComposeAdversarialTransformSolver.forward
+ * (adv_compose_solver.py:148-176: t.forward per transform + the if_norm_image clamp),
+ * predict_forward (:184-197), backward / predict_backward (:199-219) and the valid-region mask
+ * predict_backward(predict_forward(ones)) != 0 (:321-325), i.e. the F.grid_sample /
+ * F.affine_grid / elementwise ATen sequences of adv_noise.py:79-90, adv_bias.py:152-188,
+ * adv_morph.py:524-558 and adv_affine.py:289-314 -- and autograd's backward of all of them.
+ *
+ * A chain is a program of 1..ADVK_CHAIN_MAX_STAGES stages in application order.  Each stage is
+ *   INTENSITY   (noise and/or bias, `intensity_order` as in advk_intensity_fwd),
+ *   WARP_FIELD  (grid_sample with a dense field, clamped to [-1,1] on load), or
+ *   WARP_AFFINE (affine grid generated on the fly from theta: N x d x (d+1)).
+ * The stages run as phases of one persistent cooperative grid separated by grid barriers (a
+ * resampling needs the complete output of the stage before it); intermediates go to `stash`.
+ * do_clamp: clamp(out, lo, hi) after the last stage (gradient passes on the closed interval).
+ * want_mask: a one-channel N x S mask rides along the WARP stages: mask_src (NULL = ones) is
+ *   resampled by every WARP stage with that stage's padding; the last one writes mask_out,
+ *   as (value != 0) when binarize_mask.
+ * The prediction warp-back is the same call with the reversed geometric stages
+ * (theta_inv, field of -v), C = K classes, mask_src = the image chain's mask_out.
+ *
+ * advk_chain_workspace_floats: sizes of `stash` (fwd -> bwd) and `scratch` (bwd only).
+ * bwd: per-stage gradient outputs are the g_* pointers of the descriptor (NULL = not wanted):
+ *   g_delta N x C x S written; g_up N x S written (-> advk_bias_upsample_adjoint);
+ *   g_field N x S field elements written; g_theta N x d x (d+1) ACCUMULATED (caller zeroes).
+ *   g_src (nullable): gradient w.r.t. the chain input, N x C x S, written (16-byte aligned).
+ * Stages before the first one with a requested gradient are skipped. */
+#define ADVK_CHAIN_MAX_STAGES 6
+enum { ADVK_STAGE_INTENSITY = 0, ADVK_STAGE_WARP_FIELD = 1, ADVK_STAGE_WARP_AFFINE = 2 };
+
+typedef struct advk_chain_stage {
+  int kind;
+  /* INTENSITY */
+  int intensity_order;
+  float noise_scale;
+  int use_ignore;
+  float ignore_value;
+  const advk_bias_cfg* bias; /* host pointer; NULL unless the stage has a bias */
+  const float* delta;        /* N x C x S */
+  const float* low;          /* low-res bias field from advk_bias_lowfield_fwd */
+  /* WARP_* */
+  const void* field;
+  const float* theta;
+  int pad_mode;
+  int interp;
+  const float* pad_values;   /* NULL or N per-sample constants, as in advk_warp_*_fwd */
+  /* gradient outputs, used by advk_chain_apply_bwd only */
+  float* g_delta;
+  float* g_up;
+  void* g_field;
+  float* g_theta;
+} advk_chain_stage;
+
+typedef struct advk_chain_desc {
+  advk_geom g;
+  int C;
+  int n_stages;
+  advk_chain_stage stages[ADVK_CHAIN_MAX_STAGES];
+  int do_clamp;
+  float clamp_lo, clamp_hi;
+  int want_mask;
+  int binarize_mask;
+} advk_chain_desc;
+
+/* 1: one cooperative launch per chain pass (default when the device supports it and the
+ * environment variable ADVK_CHAIN_COOP is not "0"); 0: one plain launch per stage.  Returns the
+ * previous setting.  Results are identical; exists for A/B timing. */
+int advk_chain_set_cooperative(int enable);
+int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* stash_floats, size_t* scratch_floats);
+int advk_chain_apply_fwd(const advk_chain_desc* d, const float* src, const float* mask_src,
+                         float* stash, float* out, float* mask_out, void* stream);
+int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out, const float* src,
+                         const float* stash, float* scratch, float* g_src, void* stream);
+
 /* ---- consistency loss -------------------------------------------
  * replaces calc_segmentation_consistency (common/loss.py:8-87) for scales=[0] and divergence
  * types 'mse' (:55-64, incl. the second division by N*S) and 'contour' (:65-79 -> contour_loss

@@ -285,15 +285,15 @@ def test_consistency_loss(d, size, types, weights, masked, is_gt):
         ref = torch.softmax(ref * 4, 1)
     mask = None
     if masked:
-        mask = (torch.rand(size[0], 1, *size[2:]) > 0.3).float().expand(*size)
+        mask = (torch.rand(size[0], 1, *size[2:]) > 0.3).float()
     o0 = out.clone().requires_grad_(True)
-    l0 = orc.consistency_loss(o0, ref, tuple(types), tuple(weights), mask, is_gt)
+    l0 = orc.consistency_loss(o0, ref, tuple(types), tuple(weights), None if mask is None else mask.expand(*size), is_gt)
     l0.backward()
     o1 = out.to(_dev()).requires_grad_(True)
     from advchain_b200 import _lib
     _lib.launch_count("loss_grad", reset=True)
     l1 = calc_segmentation_consistency(o1, ref.to(_dev()), divergence_types=types, divergence_weights=weights,
-                                       scales=[0], mask=None if mask is None else mask.to(_dev()), is_gt=is_gt)
+                                       scales=[0], mask=None if mask is None else mask.to(_dev()).expand(*size), is_gt=is_gt)
     (l1 * 3.0).backward()
     assert _lib.launch_count("loss_grad") == 1, "the fused loss kernel did not run"
     assert abs(l1.item() - l0.item()) <= 1e-5 * abs(l0.item())
@@ -316,3 +316,80 @@ def test_no_cpu_fallback():
     ops = _ops()
     with pytest.raises(RuntimeError):
         ops.Clamp.apply(torch.zeros(4), 0.0, 1.0)
+
+
+# ------------------------------------------------------------------------------- fused chain
+
+CHAINS = [
+    (2, [2, 1, 40, 56], ["noise", "bias", "morph", "affine"], "zeros", "bilinear"),
+    (2, [2, 2, 32, 48], ["bias", "noise", "affine", "morph"], -0.25, "bilinear"),
+    (2, [1, 1, 36, 36], ["morph", "noise", "affine"], "border", "bilinear"),
+    (2, [2, 1, 32, 40], ["affine", "morph"], "reflection", "nearest"),
+    (3, [2, 1, 12, 20, 24], ["noise", "bias", "morph", "affine"], "zeros", "bilinear"),
+    (3, [1, 1, 16, 12, 20], ["morph", "affine"], "border", "bilinear"),
+    (3, [1, 2, 10, 14, 18], ["affine", "noise"], 0.5, "bilinear"),
+]
+
+
+def _chain_solver(d, size, chain, pad, interp, fused):
+    from advchain_b200.augmentor import (AdvAffine, AdvBias, AdvMorph, AdvNoise,
+                                         ComposeAdversarialTransformSolver)
+    cfgs = stage_cfgs(d, size, vector=[max(2, s // 8) for s in size[2:]])
+    cfgs["morph"]["forward_interp"] = cfgs["morph"]["backward_interp"] = interp
+    cfgs["affine"]["forward_interp"] = cfgs["affine"]["backward_interp"] = interp
+    ts = []
+    for n in chain:
+        if n == "noise":
+            ts.append(AdvNoise(d, cfgs[n], device=_dev()))
+        elif n == "bias":
+            ts.append(AdvBias(d, cfgs[n], device=_dev()))
+        elif n == "morph":
+            ts.append(AdvMorph(d, cfgs[n], image_padding_mode=pad, device=_dev()))
+        else:
+            ts.append(AdvAffine(d, cfgs[n], image_padding_mode=pad, device=_dev()))
+    sol = ComposeAdversarialTransformSolver(ts, if_norm_image=True)
+    sol.use_fused_chain = fused
+    return sol
+
+
+@pytest.mark.parametrize("d,size,chain,pad,interp", CHAINS)
+@pytest.mark.parametrize("coop", [1, 0])
+def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, coop):
+    """The fused executor (advk_chain_apply_*) against the per-transform kernels on the same
+    parameters: image chain + clamp, prediction warp-back, valid-region mask, and every parameter
+    gradient -- for arbitrary stage orders, paddings and interpolation modes."""
+    from advchain_b200 import _lib
+    lib = _lib.load()
+    prev = lib.advk_chain_set_cooperative(coop)
+    try:
+        k = 3
+        torch.manual_seed(11)
+        data = torch.rand(*size).to(_dev())
+        gpred = torch.randn(size[0], k, *size[2:]).to(_dev())
+        conv = (torch.nn.Conv2d if d == 2 else torch.nn.Conv3d)(size[1], k, 3, 1, 1).to(_dev())
+        sols = [_chain_solver(d, size, chain, pad, interp, fused) for fused in (False, True)]
+        for t in sols[0].chain_of_transforms:
+            t.init_parameters()
+        res = []
+        for sol in sols:
+            for t, t0 in zip(sol.chain_of_transforms, sols[0].chain_of_transforms):
+                t.init_parameters()
+                t.param = t0.param.detach().clone()
+                t.train()
+            _lib.launch_count(reset=True)
+            adv = sol.forward(data)
+            pred = sol.predict_backward(conv(adv))
+            mask = sol.valid_region_mask(pred)
+            (pred * gpred).sum().backward()
+            fused_launches = _lib.launch_count("chain_fwd") + _lib.launch_count("chain_fwd_stage")
+            res.append((adv.detach(), pred.detach(), mask.detach().clone(),
+                        [t.param.grad.clone() for t in sol.chain_of_transforms], fused_launches))
+        assert res[0][4] == 0 and res[1][4] > 0, "fused path did not run"
+        assert rel_err(res[1][0], res[0][0]) < 2e-6
+        assert rel_err(res[1][1], res[0][1]) < 2e-6
+        assert (res[1][2] != res[0][2]).float().mean().item() < 1e-3
+        for g1, g0, t in zip(res[1][3], res[0][3], sols[0].chain_of_transforms):
+            tol = 1e-2 if interp == "nearest" else 2e-5
+            assert rel_err(g1, g0) < tol, (t.get_name(), rel_err(g1, g0))
+    finally:
+        lib.advk_chain_set_cooperative(prev)
