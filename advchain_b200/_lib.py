@@ -90,6 +90,7 @@ SIGNATURES = {
     "advk_bias_scratch_floats": (_Z, [_G, C.POINTER(BiasCfg)]),
     "advk_bias_upsample_adjoint": (_I, [_G, C.POINTER(BiasCfg), _P, _P, _P, _P]),
     "advk_chain_set_cooperative": (_I, [_I]),
+    "advk_chain_tune": (_I, [_I, _I]),
     "advk_chain_workspace_floats": (_I, [C.POINTER(ChainDesc), C.POINTER(_Z), C.POINTER(_Z)]),
     "advk_chain_apply_fwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_chain_apply_bwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
@@ -97,6 +98,8 @@ SIGNATURES = {
     "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _I, _P, _P, _P]),
     "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _P, _P, _P, _P]),
     "advk_pgd_update": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P]),
+    "advk_pgd_update_guarded": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P, _P]),
+    "advk_morph_steps_check": (_I, [_P, _I, _I, _P, _P]),
     "advk_clamp": (_I, [_P, _F, _F, _P, _Z, _P]),
     "advk_clamp_bwd": (_I, [_P, _P, _F, _F, _P, _Z, _P]),
     "advk_nonzero_mask": (_I, [_P, _Z, _P]),

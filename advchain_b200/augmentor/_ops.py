@@ -523,10 +523,12 @@ def nonzero_mask_(t):
     return t
 
 
-def pgd_update_(param, grad, step, mode):
-    """In-place PGD update of a parameter tensor; see ADVK_UPD_* in include/advk.h."""
+def pgd_update_(param, grad, step, mode, guard=None):
+    """In-place PGD update of a parameter tensor; see ADVK_UPD_* in include/advk.h.  `guard`: device
+    scalar (the step's loss); a non-finite value leaves `param` unchanged (device-side NaN guard)."""
     n = param.shape[0]
     per = param.numel() // n
     ss = torch.empty(n, dtype=torch.float64, device=param.device)
-    call("advk_pgd_update", ptr(param), ptr(_f32c(grad)), float(step), mode, n, per, ptr(ss), stream())
+    call("advk_pgd_update_guarded", ptr(param), ptr(_f32c(grad)), float(step), mode, n, per, ptr(ss),
+         None if guard is None else ptr(guard), stream())
     return param

@@ -99,7 +99,7 @@ class AdvAffine(AdvTransformBase):
             step_size = self.step_size
         p = self.param.detach().clone().float().contiguous()
         mode = _lib.UPD_SIGN_POWER if self.power_iteration else _lib.UPD_SIGN_ASCENT
-        self.param = _ops.pgd_update_(p, self.param.grad, step_size, mode)
+        self.param = _ops.pgd_update_(p, self.param.grad, step_size, mode, guard=self._guard)
         return self.param
 
     def rescale_parameters(self):

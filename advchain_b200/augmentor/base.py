@@ -26,6 +26,7 @@ class AdvTransformBase(object):
         self.device = torch.device(device) if self.use_gpu else torch.device("cpu")
         self.debug = debug
         self._diff = None
+        self._guard = None          # device scalar: skip the update when it is NaN/Inf (graph mode)
         self.power_iteration = False
         self.init_config(self.config_dict)
         self.step_size = 1
@@ -133,5 +134,6 @@ class AdvTransformBase(object):
         grad = self.param.grad
         p = self.param.detach().clone().float().contiguous()
         mode = _lib.UPD_L2_POWER if self.power_iteration else _lib.UPD_L2_ASCENT
-        self.param = _ops.pgd_update_(p, grad, 0.0 if self.power_iteration else step_size, mode)
+        self.param = _ops.pgd_update_(p, grad, 0.0 if self.power_iteration else step_size, mode,
+                                      guard=self._guard)
         return self.param

@@ -62,6 +62,7 @@ class AdvMorph(AdvTransformBase):
         self._cache = {}
         self._steps_cache = None
         self._cfg = None
+        self._fixed_steps = None    # (n, int32 device counter): graph mode, rule verified on the device
 
     def init_config(self, config_dict):
         self.epsilon = config_dict['epsilon']
@@ -159,6 +160,13 @@ class AdvMorph(AdvTransformBase):
         if e is not None and e[0]() is self.param and e[1] == self.param._version and e[2] == self._scale():
             return e[3]
         n2 = _ops.morph_unorm2(self.param.detach(), self.data_size, self._morph_cfg(), self._scale())
+        if self._fixed_steps is not None:
+            # no host round trip: run with the captured count, let the device count rule violations
+            n, viol = self._fixed_steps
+            _ops.call("advk_morph_steps_check", _ops.ptr(n2), int(n), int(self.num_steps), viol.data_ptr(),
+                      _ops.stream())
+            self._steps_cache = (weakref.ref(self.param), self.param._version, self._scale(), n)
+            return n
         norm = math.sqrt(float(n2.item()))
         n = self.num_steps
         while norm / (2.0 ** n) > 0.5:

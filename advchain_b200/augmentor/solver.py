@@ -45,6 +45,8 @@ class ComposeAdversarialTransformSolver(object):
         self._diff_sources = []
         self.last_dist = None
         self.use_fused_chain = True       # one advk_chain_apply launch per chain pass
+        self.use_cuda_graph = False       # capture one PGD iteration in a CUDA graph and replay it
+        self._graphs = {}
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
@@ -316,6 +318,9 @@ class ComposeAdversarialTransformSolver(object):
         if step_sizes is None:
             step_sizes = [1] * len(self.chain_of_transforms)
         use_anatomy = anatomy_mask_images is not None and abs(anatomy_reg_weight) > 1e-32
+        if (self.use_cuda_graph and not use_anatomy and not self.debug and n_iter > 0 and data.is_cuda
+                and self._optimize_with_graph(model, data, init_output, optimize_flags, n_iter, step_sizes)):
+            return self._finish_loop(optimize_flags)
         stop_flag = False if n_iter > 0 else True
         i_iter = 0
         one_time_iter = n_iter
@@ -386,6 +391,140 @@ class ComposeAdversarialTransformSolver(object):
                 else:
                     stop_flag = True
         return transforms
+
+    # ------------------------------------------------------------------ CUDA-graph PGD loop
+    def _finish_loop(self, optimize_flags):
+        """Last-iteration bookkeeping of adv_compose_solver.py:369-375."""
+        transforms = []
+        for flag, transform in zip(optimize_flags, self.chain_of_transforms):
+            if flag:
+                transform.rescale_parameters()
+                transform.eval()
+            transforms.append(transform)
+        return transforms
+
+    def _graph_iteration(self, model, st):
+        """One pass of adv_compose_solver.py:308-368 without any host synchronisation: parameters are
+        read from and written back to static buffers, the NaN/Inf guard runs on the device."""
+        chain = self.chain_of_transforms
+        model.zero_grad()
+        for t, buf in zip(chain, st["params"]):
+            t.param = buf
+            t.is_training = False
+        self.make_learnable_transformation(optimize_flags=st["flags"], chain_of_transforms=chain)
+        augmented = self.forward(st["data"])
+        with _disable_tracking_bn_stats(model):
+            out = self.get_net_output(model, augmented)
+        if self.if_contains_geo_transform(chain):
+            warped = self.predict_backward(out)
+            mask = self.valid_region_mask(st["init_output"])
+            dist = self.loss_fn(pred=warped, reference=st["init_output"], mask=mask)
+        else:
+            dist = self.loss_fn(pred=out, reference=st["init_output"].detach())
+        st["dist"].copy_(dist.detach().reshape(1))
+        dist.backward()
+        for flag, t, buf in zip(st["flags"], chain, st["params"]):
+            if flag:
+                t._guard = st["dist"]
+                try:
+                    t.optimize_parameters(step_size=st["step"])      # quirk Q15: step_sizes[0] for all
+                finally:
+                    t._guard = None
+                buf.copy_(t.param.detach())
+        model.zero_grad()
+
+    def _optimize_with_graph(self, model, data, init_output, optimize_flags, n_iter, step_sizes):
+        """Runs the n_iter PGD iterations as replays of one captured CUDA graph.  Returns False when the
+        loop has to run eagerly (capture unsupported for this model, 3-D step-count rule violated)."""
+        chain = self.chain_of_transforms
+        for t in chain:
+            if t.param is None:
+                t.init_parameters()
+            t.eval()
+        try:
+            step = step_sizes[0]
+        except Exception:
+            return False
+        morph3d = [t for t in chain if isinstance(t, AdvMorph) and t.spatial_dims == 3]
+        for t in morph3d:
+            t._fixed_steps = None
+            t._steps_cache = None
+        nsteps = tuple(t._nb_steps() for t in morph3d)
+        rng = self._intensity_range(data) if self.if_norm_image else None
+        key = (id(model), model.training, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
+               float(step), tuple(id(t) for t in chain), tuple(t.power_iteration for t in chain),
+               tuple(tuple(t.param.shape) for t in chain), nsteps, rng, self.use_fused_chain,
+               tuple(self.divergence_types), tuple(self.divergence_weights))
+        st = self._graphs.get(key)
+        start = [t.param.detach().clone() for t in chain]
+        if st is None:
+            st = dict(flags=list(optimize_flags), step=step,
+                      data=data.detach().clone(), init_output=init_output.detach().clone(),
+                      params=[p.clone() for p in start],
+                      dist=torch.zeros(1, dtype=torch.float32, device=data.device),
+                      viol=torch.zeros(1, dtype=torch.int32, device=data.device))
+            saved_range = (self.min_intensity, self.max_intensity)
+            if rng is not None:
+                self.min_intensity, self.max_intensity = rng      # bake the bounds, no aminmax in the graph
+            for t, n in zip(morph3d, nsteps):
+                t._fixed_steps = (n, st["viol"])
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._graph_iteration(model, st)                 # warm-up (allocator, cuDNN plans)
+                torch.cuda.current_stream().wait_stream(side)
+                for buf, p in zip(st["params"], start):
+                    buf.copy_(p)
+                graph = torch.cuda.CUDAGraph()
+                from .. import _lib
+                before = _lib.launch_count()
+                with torch.cuda.graph(graph):
+                    self._graph_iteration(model, st)
+                st["graph"] = graph
+                st["advk_launches"] = _lib.launch_count() - before     # per replay
+                st["range"] = rng
+            except Exception as exc:                                 # model or driver refuses capture
+                logging.warning("advchain_b200: CUDA-graph capture failed (%s); running eagerly", exc)
+                torch.cuda.synchronize()
+                st = None
+            finally:
+                self.min_intensity, self.max_intensity = saved_range
+                for t in morph3d:
+                    t._fixed_steps = None
+                    t._steps_cache = None
+            if st is None:
+                for t, p in zip(chain, start):
+                    t.param = p
+                    t.is_training = False
+                self._graphs[key] = False
+                return False
+            self._graphs[key] = st
+        elif st is False:
+            return False
+        st["data"].copy_(data.detach())
+        st["init_output"].copy_(init_output.detach())
+        for buf, p in zip(st["params"], start):
+            buf.copy_(p)
+        st["viol"].zero_()
+        for _ in range(n_iter):
+            st["graph"].replay()
+        self.graph_replays = getattr(self, "graph_replays", 0) + n_iter
+        self.graph_launches_per_replay = st["advk_launches"]
+        self.last_dist = st["dist"][0]
+        if morph3d and int(st["viol"].item()) != 0:
+            # the 3-D step count grew during the loop: redo it eagerly from the start parameters
+            for t, p in zip(chain, start):
+                t.param = p
+                t.is_training = False
+            return False
+        for t, buf in zip(chain, st["params"]):
+            t.param = buf.clone()
+        for flag, t in zip(optimize_flags, chain):
+            t.is_training = bool(flag)          # _finish_loop's eval() detaches and clears the flag
+        self._mask_cache = None
+        self._fwd_mask = None
+        return True
 
     def rescale_intensity(self, data, new_min=0, new_max=1, eps=1e-20):
         flat = data.reshape(data.size(0), -1)

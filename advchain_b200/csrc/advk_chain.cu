@@ -51,6 +51,7 @@ struct Program {
   Dims g; int C; int n; int first_bwd;
   int do_clamp; float lo, hi; int want_mask;
   int tps;          // tiles per sample
+  int interleave;   // 0: block owns a contiguous tile range; 1: tiles dealt round-robin
   i64 n_tiles;
   Stage st[MAX_STAGES];
 };
@@ -103,10 +104,16 @@ __device__ __forceinline__ Vox tile_voxel(const Program& P, i64 t) {
   return v;
 }
 
-__device__ __forceinline__ void tile_range(const Program& P, i64& t0, i64& t1) {
-  i64 per = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-  t0 = (i64)blockIdx.x * per;
-  t1 = t0 + per < P.n_tiles ? t0 + per : P.n_tiles;
+// tile loop: for (t = t0; t < t1; t += dt)
+__device__ __forceinline__ void tile_range(const Program& P, i64& t0, i64& t1, i64& dt) {
+  if (P.interleave) {
+    t0 = blockIdx.x; t1 = P.n_tiles; dt = gridDim.x;
+  } else {
+    i64 per = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+    t0 = (i64)blockIdx.x * per;
+    t1 = t0 + per < P.n_tiles ? t0 + per : P.n_tiles;
+    dt = 1;
+  }
 }
 
 // sampling coordinates of output voxel v; r* = raw field values (for the clamp-range mask),
@@ -149,10 +156,10 @@ __device__ __forceinline__ void stage_coords(const Program& P, const Stage& s, c
 template <int DIM>
 __device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1;
-  tile_range(P, t0, t1);
+  i64 t0, t1, dt;
+  tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; ++t) {
+  for (i64 t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float bv = 1.f;
@@ -172,10 +179,10 @@ __device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last)
 template <int DIM, bool FIELD>
 __device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1;
-  tile_range(P, t0, t1);
+  i64 t0, t1, dt;
+  tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; ++t) {
+  for (i64 t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
@@ -215,8 +222,8 @@ __device__ __forceinline__ void run_stage_fwd(const Program& P, int k) {
   else stage_warp_fwd<DIM, false>(P, s, last);
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(CT)
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 chain_fwd_kernel(const __grid_constant__ Program P) {
   cg::grid_group grid = cg::this_grid();
   for (int k = 0; k < P.n; ++k) {
@@ -226,8 +233,8 @@ chain_fwd_kernel(const __grid_constant__ Program P) {
 }
 
 // one stage per launch (used when a cooperative launch is not possible / for A-B timing)
-template <int DIM>
-__global__ void __launch_bounds__(CT)
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 chain_fwd_stage_kernel(const __grid_constant__ Program P, int k) {
   run_stage_fwd<DIM>(P, k);
 }
@@ -251,10 +258,10 @@ __device__ void zero_buffers(const Program& P) {
 template <int DIM>
 __device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1;
-  tile_range(P, t0, t1);
+  i64 t0, t1, dt;
+  tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; ++t) {
+  for (i64 t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float bv = 1.f, braw = 1.f;
@@ -284,15 +291,15 @@ template <int DIM, bool FIELD>
 __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, float* red) {
   constexpr int NG = DIM * (DIM + 1);
   const Dims& g = P.g;
-  i64 t0, t1;
-  tile_range(P, t0, t1);
+  i64 t0, t1, dt;
+  tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
   const bool want_theta = !FIELD && s.g_theta != nullptr;
   float acc[NG];
 #pragma unroll
   for (int i = 0; i < NG; ++i) acc[i] = 0.f;
   int cur_n = -1;
-  for (i64 t = t0; t < t1; ++t) {
+  for (i64 t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (want_theta && v.n != cur_n) {            // block-uniform
       if (cur_n >= 0) {
@@ -375,8 +382,8 @@ __device__ __forceinline__ void run_stage_bwd(const Program& P, int k, float* re
   else stage_warp_bwd<DIM, false>(P, s, last, red);
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(CT)
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 chain_bwd_kernel(const __grid_constant__ Program P) {
   __shared__ float red[12 * 32];
   cg::grid_group grid = cg::this_grid();
@@ -387,8 +394,8 @@ chain_bwd_kernel(const __grid_constant__ Program P) {
   }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(CT)
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 chain_bwd_stage_kernel(const __grid_constant__ Program P, int k) {
   __shared__ float red[12 * 32];
   if (k < 0) zero_buffers(P);
@@ -482,42 +489,89 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
   return true;
 }
 
-template <int DIM>
-static int launch_fwd(Program& P, cudaStream_t st) {
+// Tuning knobs (environment, read once; advk_chain_tune() overrides): resident blocks per SM the
+// kernels are compiled for (register cap) and the tile-to-block assignment.
+static int g_minb = -1, g_interleave = -1;
+static void tune_defaults() {
+  if (g_minb < 0) {
+    const char* e = getenv("ADVK_CHAIN_MINB");
+    g_minb = e ? atoi(e) : 4;
+    if (g_minb != 2 && g_minb != 3 && g_minb != 4 && g_minb != 6) g_minb = 4;
+  }
+  if (g_interleave < 0) {
+    const char* e = getenv("ADVK_CHAIN_INTERLEAVE");
+    g_interleave = (e && e[0] == '1') ? 1 : 0;
+  }
+}
+
+template <int DIM, int MINB>
+static int launch_fwd_t(Program& P, cudaStream_t st) {
   if (coop_enabled() && P.n > 1) {
-    static int gmax = coop_grid(chain_fwd_kernel<DIM>);
+    static int gmax = coop_grid(chain_fwd_kernel<DIM, MINB>);
     int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
     void* args[] = {(void*)&P};
     ADVK_LAUNCH(K_chain_fwd, st,
-                cudaLaunchCooperativeKernel((void*)chain_fwd_kernel<DIM>, dim3(grid), dim3(CT), args, 0, st));
+                cudaLaunchCooperativeKernel((void*)chain_fwd_kernel<DIM, MINB>, dim3(grid), dim3(CT), args, 0, st));
   } else {
     int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
     for (int k = 0; k < P.n; ++k)
-      ADVK_LAUNCH(K_chain_fwd_stage, st, chain_fwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, k));
+      ADVK_LAUNCH(K_chain_fwd_stage, st, chain_fwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, k));
   }
   return check_launch("chain_apply_fwd");
 }
 
-template <int DIM>
-static int launch_bwd(Program& P, cudaStream_t st) {
+template <int DIM, int MINB>
+static int launch_bwd_t(Program& P, cudaStream_t st) {
   if (coop_enabled()) {
-    static int gmax = coop_grid(chain_bwd_kernel<DIM>);
+    static int gmax = coop_grid(chain_bwd_kernel<DIM, MINB>);
     int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
     void* args[] = {(void*)&P};
     ADVK_LAUNCH(K_chain_bwd, st,
-                cudaLaunchCooperativeKernel((void*)chain_bwd_kernel<DIM>, dim3(grid), dim3(CT), args, 0, st));
+                cudaLaunchCooperativeKernel((void*)chain_bwd_kernel<DIM, MINB>, dim3(grid), dim3(CT), args, 0, st));
   } else {
     int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
-    ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, -1));
+    ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, -1));
     for (int k = P.n - 1; k >= P.first_bwd; --k)
-      ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM><<<grid, CT, 0, st>>>(P, k));
+      ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, k));
   }
   return check_launch("chain_apply_bwd");
+}
+
+template <int DIM>
+static int launch_fwd(Program& P, cudaStream_t st) {
+  tune_defaults();
+  P.interleave = g_interleave;
+  switch (g_minb) {
+    case 2: return launch_fwd_t<DIM, 2>(P, st);
+    case 3: return launch_fwd_t<DIM, 3>(P, st);
+    case 6: return launch_fwd_t<DIM, 6>(P, st);
+    default: return launch_fwd_t<DIM, 4>(P, st);
+  }
+}
+
+template <int DIM>
+static int launch_bwd(Program& P, cudaStream_t st) {
+  tune_defaults();
+  P.interleave = g_interleave;
+  switch (g_minb) {
+    case 2: return launch_bwd_t<DIM, 2>(P, st);
+    case 3: return launch_bwd_t<DIM, 3>(P, st);
+    case 6: return launch_bwd_t<DIM, 6>(P, st);
+    default: return launch_bwd_t<DIM, 4>(P, st);
+  }
 }
 
 }  // namespace advk
 
 using namespace advk;
+
+extern "C" int advk_chain_tune(int min_blocks_per_sm, int interleave) {
+  tune_defaults();
+  if (min_blocks_per_sm == 2 || min_blocks_per_sm == 3 || min_blocks_per_sm == 4 || min_blocks_per_sm == 6)
+    g_minb = min_blocks_per_sm;
+  if (interleave == 0 || interleave == 1) g_interleave = interleave;
+  return g_minb * 10 + g_interleave;
+}
 
 extern "C" int advk_chain_set_cooperative(int enable) {
   int prev = coop_enabled() ? 1 : 0;

@@ -65,7 +65,13 @@ sumsq_kernel(const float* __restrict__ g, size_t per, double* __restrict__ out) 
 
 __global__ void __launch_bounds__(256)
 update_kernel(float* param, const float* grad, float step, int mode, size_t per,
-              const double* __restrict__ ss) {
+              const double* __restrict__ ss, const float* __restrict__ guard) {
+  // NaN/Inf guard of the PGD loop (adv_compose_solver.py:345-346) evaluated on the device: a
+  // non-finite loss leaves the parameters untouched, without a host round trip
+  if (guard) {
+    float gv = guard[0];
+    if (isnan(gv) || isinf(gv)) return;
+  }
   const int n = blockIdx.y;
   float inv = 0.f;
   if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) inv = 1.f / ((float)sqrt(ss[n]) + 1e-20f);
@@ -168,8 +174,32 @@ extern "C" int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, siz
   return ADVK_OK;
 }
 
+// 3-D scaling-and-squaring step rule (adv_morph.py:159-162) checked on the device: counts a
+// violation when the smallest n >= 8 with sqrt(norm2)/2^n <= 0.5 differs from `nb_steps`.
+__global__ void steps_check_kernel(const float* __restrict__ norm2, int nb_steps, int min_steps,
+                                   int* __restrict__ violations) {
+  float nrm = sqrtf(norm2[0]);
+  int n = min_steps;
+  while (nrm / exp2f((float)n) > 0.5f && n < 64) ++n;
+  if (n != nb_steps) atomicAdd(violations, 1);
+}
+
+extern "C" int advk_morph_steps_check(const float* norm2, int nb_steps, int min_steps, int* violations,
+                                      void* stream) {
+  ADVK_REQUIRE(norm2 && violations, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  ADVK_LAUNCH(K_steps_check, st, steps_check_kernel<<<1, 1, 0, st>>>(norm2, nb_steps, min_steps, violations));
+  return check_launch("morph_steps_check");
+}
+
 extern "C" int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
                                size_t per_sample, double* sumsq, void* stream) {
+  return advk_pgd_update_guarded(param, grad, step, mode, N, per_sample, sumsq, nullptr, stream);
+}
+
+extern "C" int advk_pgd_update_guarded(float* param, const float* grad, float step, int mode, int N,
+                                       size_t per_sample, double* sumsq, const float* guard,
+                                       void* stream) {
   ADVK_REQUIRE(param && grad && N >= 1 && per_sample >= 1, "null pointer / bad size");
   ADVK_REQUIRE(mode >= 0 && mode <= 3, "bad mode");
   cudaStream_t st = (cudaStream_t)stream;
@@ -181,7 +211,7 @@ extern "C" int advk_pgd_update(float* param, const float* grad, float step, int 
     cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
     ADVK_LAUNCH(K_sumsq, st, sumsq_kernel<<<grid, 256, 0, st>>>(grad, per_sample, sumsq));
   }
-  ADVK_LAUNCH(K_update, st, update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq));
+  ADVK_LAUNCH(K_update, st, update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq, guard));
   return check_launch("pgd_update");
 }
 

@@ -190,6 +190,17 @@ int advk_bias_upsample_adjoint(const advk_geom* g, const advk_bias_cfg* bias, co
  * adv_noise.py:92-94, adv_morph.py:518-522). */
 int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
                     size_t per_sample, double* sumsq, void* stream);
+/* Same, with the loop's NaN/Inf guard (adv_compose_solver.py:345-346) evaluated on the device:
+ * `guard` points to the step's loss (1 float); when it is NaN or Inf the parameters are left
+ * unchanged.  This removes the step's only host synchronisation, so a whole PGD iteration can be
+ * captured in a CUDA graph. */
+int advk_pgd_update_guarded(float* param, const float* grad, float step, int mode, int N,
+                            size_t per_sample, double* sumsq, const float* guard, void* stream);
+/* Device-side check of the 3-D step-count rule (adv_morph.py:159-162) for graph-captured loops
+ * that run with a fixed nb_steps: *violations is incremented when the rule applied to *norm2
+ * (from advk_morph_unorm2) gives a different count. */
+int advk_morph_steps_check(const float* norm2, int nb_steps, int min_steps, int* violations,
+                           void* stream);
 
 /* ---- fused chain apply ---------------------------------------------------------------------
  * ONE launch applies a whole chain of transforms to an N x C x S tensor, ONE launch applies its
@@ -260,6 +271,10 @@ typedef struct advk_chain_desc {
  * environment variable ADVK_CHAIN_COOP is not "0"); 0: one plain launch per stage.  Returns the
  * previous setting.  Results are identical; exists for A/B timing. */
 int advk_chain_set_cooperative(int enable);
+/* Tuning (A/B timing): resident blocks per SM the chain kernels are compiled for (2, 3, 4 or 6 =
+ * register cap 128/80/64/40; other values keep the current one) and tile assignment (0 contiguous
+ * ranges per block, 1 round-robin; other values keep).  Returns 10*min_blocks + interleave. */
+int advk_chain_tune(int min_blocks_per_sm, int interleave);
 int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* stash_floats, size_t* scratch_floats);
 int advk_chain_apply_fwd(const advk_chain_desc* d, const float* src, const float* mask_src,
                          float* stash, float* out, float* mask_out, void* stream);
