@@ -5,6 +5,7 @@ from .bias import AdvBias
 from .morph import AdvMorph, get_base_grid
 from .affine import AdvAffine
 from .solver import ComposeAdversarialTransformSolver
+from .sharding import ShardContext, shard_slice
 
 __all__ = ["AdvTransformBase", "AdvNoise", "AdvBias", "AdvMorph", "AdvAffine",
-           "ComposeAdversarialTransformSolver", "get_base_grid"]
+           "ComposeAdversarialTransformSolver", "get_base_grid", "ShardContext", "shard_slice"]

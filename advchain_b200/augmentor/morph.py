@@ -63,6 +63,7 @@ class AdvMorph(AdvTransformBase):
         self._steps_cache = None
         self._cfg = None
         self._fixed_steps = None    # (n, int32 device counter): graph mode, rule verified on the device
+        self.shard = None           # sharding.ShardContext: whole-batch norm for the 3-D step rule (quirk Q2)
 
     def init_config(self, config_dict):
         self.epsilon = config_dict['epsilon']
@@ -167,6 +168,8 @@ class AdvMorph(AdvTransformBase):
                       _ops.stream())
             self._steps_cache = (weakref.ref(self.param), self.param._version, self._scale(), n)
             return n
+        if self.shard is not None:
+            n2 = self.shard.global_norm2(n2)
         norm = math.sqrt(float(n2.item()))
         n = self.num_steps
         while norm / (2.0 ** n) > 0.5:

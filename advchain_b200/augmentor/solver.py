@@ -46,6 +46,7 @@ class ComposeAdversarialTransformSolver(object):
         self.last_dist = None
         self.use_fused_chain = True       # one advk_chain_apply launch per chain pass
         self.use_cuda_graph = False       # capture one PGD iteration in a CUDA graph and replay it
+        self.shard = None                 # sharding.ShardContext: "exact-global" multi-GPU semantics
         self._graphs = {}
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
@@ -128,7 +129,10 @@ class ComposeAdversarialTransformSolver(object):
             return lo, hi
         key = (data.data_ptr(), data._version, tuple(data.shape))
         if self._range_cache is None or self._range_cache[0] != key:
-            mn, mx = torch.aminmax(data.detach())
+            if self.shard is not None:
+                mn, mx = self.shard.global_minmax(data)           # min/max of the whole (sharded) batch
+            else:
+                mn, mx = torch.aminmax(data.detach())
             self._range_cache = (key, float(mn), float(mx))
         return (self._range_cache[1] if lo is None else lo,
                 self._range_cache[2] if hi is None else hi)
@@ -275,9 +279,12 @@ class ComposeAdversarialTransformSolver(object):
 
     def loss_fn(self, pred, reference, mask=None):
         """adv_compose_solver.py:221-234."""
+        weights = self.divergence_weights
+        if self.shard is not None:       # quirk Q9: shard losses must sum to the whole-batch loss
+            weights = self.shard.scaled_weights(self.divergence_types, weights, pred.shape[0])
         return calc_segmentation_consistency(
             output=pred, reference=reference, divergence_types=self.divergence_types,
-            divergence_weights=self.divergence_weights, scales=[0], mask=mask,
+            divergence_weights=weights, scales=[0], mask=mask,
             class_weights=self.class_weights, is_gt=self.is_gt)
 
     def calc_adv_consistency_loss(self, data, model, init_output, chain_of_transforms=None):
@@ -317,6 +324,9 @@ class ComposeAdversarialTransformSolver(object):
         """adv_compose_solver.py:289-405."""
         if step_sizes is None:
             step_sizes = [1] * len(self.chain_of_transforms)
+        for t in self.chain_of_transforms:
+            if hasattr(t, "shard"):
+                t.shard = self.shard
         use_anatomy = anatomy_mask_images is not None and abs(anatomy_reg_weight) > 1e-32
         if (self.use_cuda_graph and not use_anatomy and not self.debug and n_iter > 0 and data.is_cuda
                 and self._optimize_with_graph(model, data, init_output, optimize_flags, n_iter, step_sizes)):
@@ -348,7 +358,9 @@ class ComposeAdversarialTransformSolver(object):
             if self.debug:
                 print('[inner loop], step {}: dist {}'.format(str(i_iter), dist.item()))
             self.last_dist = dist.detach()
-            if bool(torch.isfinite(dist)):            # the step's single host sync (NaN/Inf guard, :345)
+            if self.shard is not None:   # the guard looks at the whole-batch loss, like the reference
+                self.last_dist = self.shard.global_scalar(dist)
+            if bool(torch.isfinite(self.last_dist)):            # the step's single host sync (NaN/Inf guard, :345)
                 dist.backward()
                 for flag, transform in zip(optimize_flags, self.chain_of_transforms):
                     if flag:
@@ -437,6 +449,8 @@ class ComposeAdversarialTransformSolver(object):
         """Runs the n_iter PGD iterations as replays of one captured CUDA graph.  Returns False when the
         loop has to run eagerly (capture unsupported for this model, 3-D step-count rule violated)."""
         chain = self.chain_of_transforms
+        if self.shard is not None:
+            return False                 # the scalar all-reduces of exact-global mode run eagerly
         for t in chain:
             if t.param is None:
                 t.init_parameters()

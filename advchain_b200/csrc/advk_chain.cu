@@ -500,7 +500,7 @@ static void tune_defaults() {
   }
   if (g_interleave < 0) {
     const char* e = getenv("ADVK_CHAIN_INTERLEAVE");
-    g_interleave = (e && e[0] == '1') ? 1 : 0;
+    g_interleave = (e && e[0] == '0') ? 0 : 1;      // measured: round-robin tiles 5-15 % faster (r01f)
   }
 }
 

@@ -78,6 +78,56 @@ __global__ void lowres_smooth_kernel(MorphCfg c, int NC, const float* __restrict
   out[idx] = acc;
 }
 
+// Same smoothing, separable, one CTA per (sample, channel) with the whole lattice in shared memory
+// (the default lattices are 16x16 / 8x8x8; the direct kernel above stays for lattices > 4096).
+constexpr int LRS_MAX = 4096;
+template <int DIM>
+__global__ void __launch_bounds__(256)
+lowres_smooth_smem_kernel(MorphCfg c, const float* __restrict__ in, float scale, float* __restrict__ out) {
+  __shared__ float a[LRS_MAX];
+  __shared__ float b[LRS_MAX];
+  const int lr = c.Dl * c.Hl * c.Wl;
+  const float* src = in + (i64)blockIdx.x * lr;
+  for (int i = threadIdx.x; i < lr; i += blockDim.x) a[i] = scale * src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < lr; i += blockDim.x) {          // along W
+    int x = i % c.Wl, row = i - x;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { int xx = x + k - KR; if (xx >= 0 && xx < c.Wl) acc += c.w[k] * a[row + xx]; }
+    b[i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < lr; i += blockDim.x) {          // along H
+    int y = (i / c.Wl) % c.Hl;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { int yy = y + k - KR; if (yy >= 0 && yy < c.Hl) acc += c.w[k] * b[i + (yy - y) * c.Wl]; }
+    a[i] = acc;
+  }
+  __syncthreads();
+  float* dst = out + (i64)blockIdx.x * lr;
+  for (int i = threadIdx.x; i < lr; i += blockDim.x) {          // along D
+    float acc;
+    if (DIM == 3) {
+      int z = i / (c.Wl * c.Hl);
+      acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { int zz = z + k - KR; if (zz >= 0 && zz < c.Dl) acc += c.w[k] * a[i + (zz - z) * c.Wl * c.Hl]; }
+    } else acc = a[i];
+    dst[i] = acc;
+  }
+}
+
+template <int DIM>
+static void launch_lowres_smooth(const MorphCfg& c, int NC, const float* in, float scale, float* out, cudaStream_t st) {
+  i64 lr = (i64)c.Dl * c.Hl * c.Wl;
+  if (lr <= LRS_MAX)
+    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_smem_kernel<DIM><<<NC, 256, 0, st>>>(c, in, scale, out));
+  else
+    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, in, scale, out));
+}
+
 // upsampled velocity at one voxel; u_lr planar [N][DIM][lr]
 template <int DIM>
 __device__ __forceinline__ void upsample_u(const MorphCfg& c, const Dims& g, const float* __restrict__ u_lr,
@@ -495,7 +545,7 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   typedef typename V<DIM>::T T;
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   int NC = g.N * DIM;
-  ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
+  launch_lowres_smooth<DIM>(c, NC, v, scale, u_lr, st);
   T* L = (T*)levels;
   i64 F = (i64)g.N * g.S;
   dim3 grid(blocks_for(g.S, 256), g.N);
@@ -556,7 +606,7 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   float* planar = (float*)(s2 + (i64)g.N * lr);
   ADVK_LAUNCH(K_aos_to_planar, st, aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr));
   int NC = g.N * DIM;
-  ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, planar, scale, g_v));
+  launch_lowres_smooth<DIM>(c, NC, planar, scale, g_v, st);
   return check_launch("morph_field_bwd");
 }
 
@@ -576,10 +626,10 @@ extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg,
   cudaMemsetAsync(out_norm2, 0, sizeof(float), st);
   dim3 grid(blocks_for(g.S, 256), g.N);
   if (gg->d == 2) {
-    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<2><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
+    launch_lowres_smooth<2>(c, NC, v, scale, u_lr, st);
     ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<2><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
   } else {
-    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<3><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, v, scale, u_lr));
+    launch_lowres_smooth<3>(c, NC, v, scale, u_lr, st);
     ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<3><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
   }
   return check_launch("morph_unorm2");
