@@ -185,7 +185,7 @@ class MorphField(Function):
         levels, field = ctx.saved_tensors
         g, cfg, scale, nb, vshape = ctx.meta
         g_field = _f32c(g_field)
-        scratch = torch.empty(3 * field.numel(), dtype=torch.float32, device=field.device)
+        scratch = torch.empty(5 * field.numel(), dtype=torch.float32, device=field.device)
         nlr = _lib.load().advk_morph_lr_scratch_floats(C.byref(g), C.byref(cfg))
         lr_scratch = torch.empty(nlr, dtype=torch.float32, device=field.device)
         g_v = torch.empty(vshape, dtype=torch.float32, device=field.device)

@@ -46,14 +46,16 @@ lowfield_bwd_kernel(BiasCfg b, int N, const float* __restrict__ g_low, float s, 
   int k = (int)(e % b.nW), j = (int)((e / b.nW) % b.nH), i = (int)((e / ((i64)b.nW * b.nH)) % b.nD);
   const float* gl = g_low + n * L;
   float v[1] = {0.f};
-  for (i64 q = threadIdx.x; q < L; q += blockDim.x) {
-    int x = (int)(q % b.lW), y = (int)((q / b.lW) % b.lH), z = (int)(q / ((i64)b.lW * b.lH));
+  // blockIdx.y splits the low-res volume; partial sums are combined with one atomic per block
+  const int Li = (int)L, lW = b.lW, lHW = b.lW * b.lH;
+  for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < Li; q += gridDim.y * blockDim.x) {
+    int x = q % lW, y = (q / lW) % b.lH, z = q / lHW;
     float w = b.AW[x * b.nW + k] * b.AH[y * b.nH + j];
     if (DIM == 3) w *= b.AD[z * b.nD + i];
     if (w != 0.f) v[0] += w * gl[q];
   }
   block_sum<1>(v, red);
-  if (threadIdx.x == 0) g_cp[e] = s * v[0];
+  if (threadIdx.x == 0) atomicAdd(g_cp + e, s * v[0]);
 }
 
 // order: 0 noise, 1 bias, 2 noise->bias, 3 bias->noise
@@ -150,9 +152,16 @@ extern "C" int advk_bias_lowfield_bwd(const advk_bias_cfg* cfg, int N, const flo
   ADVK_REQUIRE(make_bias(cfg, d, b), "bad bias config");
   ADVK_REQUIRE(g_low && g_cp && N >= 1, "null pointer");
   unsigned blocks = (unsigned)((i64)N * b.nD * b.nH * b.nW);
+  i64 L = (i64)b.lD * b.lH * b.lW;
+  ADVK_REQUIRE(L < 2147483647LL, "low-res bias field too large");
+  unsigned split = (unsigned)((L + 1023) / 1024);
+  if (split > 32) split = 32;
+  if (split < 1) split = 1;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d == 2) ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<2><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
-  else ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<3><<<blocks, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
+  cudaMemsetAsync(g_cp, 0, sizeof(float) * blocks, st);
+  dim3 grid(blocks, split);
+  if (d == 2) ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<2><<<grid, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
+  else ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<3><<<grid, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
   return check_launch("bias_lowfield_bwd");
 }
 

@@ -90,6 +90,42 @@ update_kernel(float* param, const float* grad, float step, int mode, size_t per,
   }
 }
 
+// Small parameters (control points, velocities, affine): norm + update in ONE launch, one CTA per
+// sample.  Same arithmetic as sumsq_kernel + update_kernel (fp32 partials, double across warps).
+__global__ void __launch_bounds__(256)
+small_update_kernel(float* param, const float* grad, float step, int mode, int per,
+                    const float* __restrict__ guard) {
+  __shared__ float red[32];
+  __shared__ float s_inv;
+  if (guard) {
+    float gv = guard[0];
+    if (isnan(gv) || isinf(gv)) return;
+  }
+  const int n = blockIdx.x;
+  const float* g = grad + (size_t)n * per;
+  float* p = param + (size_t)n * per;
+  if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) {
+    float v[1] = {0.f};
+    for (int i = threadIdx.x; i < per; i += blockDim.x) { float t = g[i]; v[0] += t * t; }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) s_inv = 1.f / ((float)sqrt((double)v[0]) + 1e-20f);
+    __syncthreads();
+  }
+  const float inv = (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) ? s_inv : 0.f;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float gval = g[i];
+    float sg = (gval > 0.f) ? 1.f : ((gval < 0.f) ? -1.f : 0.f);
+    float r;
+    switch (mode) {
+      case ADVK_UPD_L2_ASCENT: r = p[i] + step * (gval * inv); break;
+      case ADVK_UPD_SIGN_ASCENT: r = p[i] + step * sg; break;
+      case ADVK_UPD_L2_POWER: r = gval * inv; break;
+      default: r = sg; break;
+    }
+    p[i] = r;
+  }
+}
+
 __global__ void clamp_kernel(const float* __restrict__ x, float lo, float hi, float* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = fminf(fmaxf(x[i], lo), hi);
@@ -203,6 +239,10 @@ extern "C" int advk_pgd_update_guarded(float* param, const float* grad, float st
   ADVK_REQUIRE(param && grad && N >= 1 && per_sample >= 1, "null pointer / bad size");
   ADVK_REQUIRE(mode >= 0 && mode <= 3, "bad mode");
   cudaStream_t st = (cudaStream_t)stream;
+  if (per_sample <= 8192) {
+    ADVK_LAUNCH(K_update, st, small_update_kernel<<<N, 256, 0, st>>>(param, grad, step, mode, (int)per_sample, guard));
+    return check_launch("pgd_update");
+  }
   size_t b = (per_sample + 255) / 256;
   unsigned bx = (unsigned)(b > 1024 ? 1024 : b);
   dim3 grid(bx, N);

@@ -231,53 +231,90 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
   out[(i64)n * g.S + p] = V<DIM>::make(ox, oy, oz);
 }
 
-// Backward of one squaring step: given g_out = dL/dphi_k and phi_{k-1}, accumulate
-// dL/dphi_{k-1} = scatter-adjoint of the gather + spatial Jacobian.  g_in must be zeroed.
+// Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}.  Upstream dL/dphi_k = gS + gJ (two
+// buffers, gJ nullable); output dL/dphi_{k-1} = outS (scatter adjoint of the gather, accumulated
+// with vector REDs, must be zero on entry) + outJ (spatial-Jacobian term, plain store).
+//
+// Scatter traffic is the bottleneck of this kernel (ncu: L1TEX 74 %, every RED.128 is processed
+// sector by sector), so neighbouring lanes first combine the contributions that land on the same
+// voxel: lane i's x1-corner is lane i+1's x0-corner whenever both sample the same source row with
+// consecutive x0 (always, for a smooth field with sub-voxel variation) -- one warp shuffle hands the
+// x1 contribution to the neighbour, halving the REDs (8 -> 4 per voxel in 3-D).  Lanes whose
+// neighbour does not match fall back to their own RED, so the result is exact for any field.
+// `zero_next` (nullable): scatter buffer of the NEXT level, zeroed here to save a memset launch.
 template <int DIM>
 __global__ void __launch_bounds__(256)
 ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
-                   const typename V<DIM>::T* __restrict__ g_out, typename V<DIM>::T* __restrict__ g_in) {
+                   const typename V<DIM>::T* __restrict__ gS, const typename V<DIM>::T* __restrict__ gJ,
+                   typename V<DIM>::T* __restrict__ outS, typename V<DIM>::T* __restrict__ outJ,
+                   typename V<DIM>::T* __restrict__ zero_next) {
   typedef typename V<DIM>::T T;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= g.S) return;
-  const T* src = phi_prev + (i64)n * g.S;
-  T* dst = g_in + (i64)n * g.S;
-  const T f = src[p];
-  const T go = g_out[(i64)n * g.S + p];
+  const bool live = p < g.S;
+  const i64 nb = (i64)n * g.S;
+  const T* src = phi_prev + nb;
+  T* dst = outS + nb;
+  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
+  if (live) {
+    f = src[p];
+    go = gS[nb + p];
+    if (gJ) { T j = gJ[nb + p]; go.x += j.x; go.y += j.y; if (DIM == 3) go = V<DIM>::make(go.x, go.y, V<DIM>::z(go) + V<DIM>::z(j)); }
+    if (zero_next) zero_next[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
+  }
   Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   Axis az;
   if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
-  const i64 HW = (i64)g.H * g.W;
+  const int HW = g.H * g.W;
+  const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
   float jx = 0.f, jy = 0.f, jz = 0.f;
 #pragma unroll
   for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-    bool vz = dz ? az.v1 : az.v0;
-    float wz = dz ? az.w1 : az.w0;
+    const bool vz = dz ? az.v1 : az.v0;
+    const float wz = dz ? az.w1 : az.w0;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      bool vy = dy ? ay.v1 : ay.v0;
-      float wy = dy ? ay.w1 : ay.w0;
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        bool vx = dx ? ax.v1 : ax.v0;
-        float wx = dx ? ax.w1 : ax.w0;
-        if (vx && vy && vz) {
-          i64 q = (i64)(az.i0 + dz) * HW + (i64)(ay.i0 + dy) * g.W + (ax.i0 + dx);
-          float w = wx * wy * wz;
-          atomicAdd(dst + q, V<DIM>::make(go.x * w, go.y * w, V<DIM>::z(go) * w));
-          T s = __ldg(src + q);
-          float dot = s.x * go.x + s.y * go.y + V<DIM>::z(s) * V<DIM>::z(go);
-          jx += (dx ? dot : -dot) * (wy * wz);
-          jy += (dy ? dot : -dot) * (wx * wz);
-          if (DIM == 3) jz += (dz ? dot : -dot) * (wx * wy);
-        }
+      const bool vy = dy ? ay.v1 : ay.v0;
+      const float wy = dy ? ay.w1 : ay.w0;
+      const bool row = live && vy && vz;
+      const bool v0 = row && ax.v0, v1 = row && ax.v1;
+      const int a0 = (az.i0 + dz) * HW + (ay.i0 + dy) * g.W + ax.i0;      // S < 2^31 (host-checked)
+      const float wyz = wy * wz;
+      // Jacobian: sum over corners of (+-) <phi(corner), g> * (other-axis weights)
+      if (v0) {
+        T s0 = __ldg(src + a0);
+        float dot = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
+        jx -= dot * wyz;
+        jy += (dy ? dot : -dot) * (ax.w0 * wz);
+        if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w0 * wy);
       }
+      if (v1) {
+        T s1 = __ldg(src + a0 + 1);
+        float dot = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
+        jx += dot * wyz;
+        jy += (dy ? dot : -dot) * (ax.w1 * wz);
+        if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w1 * wy);
+      }
+      // scatter, with the x1 contribution handed to lane+1 when it lands on that lane's x0 corner
+      const float w0 = ax.w0 * wyz, w1 = ax.w1 * wyz;
+      float c0x = gx * w0, c0y = gy * w0, c0z = gz * w0;
+      const float c1x = gx * w1, c1y = gy * w1, c1z = gz * w1;
+      const int a0_next = __shfl_down_sync(FULL, v0 ? a0 : -1, 1);
+      const bool hand = v1 && lane < 31 && a0_next == a0 + 1;
+      const float rx = __shfl_up_sync(FULL, hand ? c1x : 0.f, 1);
+      const float ry = __shfl_up_sync(FULL, hand ? c1y : 0.f, 1);
+      float rz = 0.f;
+      if (DIM == 3) rz = __shfl_up_sync(FULL, hand ? c1z : 0.f, 1);
+      if (lane > 0) { c0x += rx; c0y += ry; c0z += rz; }
+      if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
+      if (v1 && !hand) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
     }
   }
-  atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+  if (live) outJ[nb + p] = V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -487,14 +524,17 @@ __device__ __forceinline__ void t_fma(float2& acc, float w, float2 a, float2 b, 
 __device__ __forceinline__ void t_fma(float4& acc, float w, float4 a, float4 b, bool hb) {
   acc.x += w * (hb ? a.x - b.x : a.x); acc.y += w * (hb ? a.y - b.y : a.y); acc.z += w * (hb ? a.z - b.z : a.z);
 }
+__device__ __forceinline__ float t_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 t_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float4 t_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, 0.f); }
 __device__ __forceinline__ float t_scale(float a, float s) { return a * s; }
 __device__ __forceinline__ float2 t_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 __device__ __forceinline__ float4 t_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, 0.f); }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out,
-                    i64 outer, int n_in, int n_out, i64 inner, float scale) {
+adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ a2, const T* __restrict__ b, float vs,
+                    T* __restrict__ out, i64 outer, int n_in, int n_out, i64 inner, float scale) {
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= outer * n_out * inner) return;
   i64 i = idx % inner;
@@ -513,17 +553,19 @@ adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, 
     float w = (u.i0 == j ? u.l0 : 0.f) + (u.i1 == j ? u.l1 : 0.f);
     if (w != 0.f) {
       i64 q = (o * n_in + p) * inner + i;
-      t_fma(acc, w, a[q], hb ? b[q] : a[q], hb);
+      T av = a[q];
+      if (a2) av = t_add(av, a2[q]);
+      t_fma(acc, w, av, hb ? b[q] : av, hb);
     }
   }
   out[idx] = t_scale(acc, vs);
 }
 
 template <typename T>
-static void launch_adjoint_axis(const T* a, const T* b, float vs, T* out, i64 outer, int n_in, int n_out,
-                                i64 inner, float scale, cudaStream_t st) {
+static void launch_adjoint_axis(const T* a, const T* a2, const T* b, float vs, T* out, i64 outer, int n_in,
+                                int n_out, i64 inner, float scale, cudaStream_t st) {
   i64 tot = outer * n_out * inner;
-  ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, b, vs, out, outer, n_in, n_out, inner, scale));
+  ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, a2, b, vs, out, outer, n_in, n_out, inner, scale));
 }
 
 template <int DIM>
@@ -574,35 +616,38 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   const T* L = (const T*)levels;
   i64 F = (i64)g.N * g.S;
   T* g_off = (T*)scratch;
-  T* ping = g_off + F;
-  T* pong = ping + F;
+  T* bufS[2] = {g_off + F, g_off + 3 * F};
+  T* bufJ[2] = {g_off + 2 * F, g_off + 4 * F};
   // (9)+(8)+(7): clamp mask, Gaussian (self-adjoint), compose-with-base border mask -> g_off = dL/d(off)
   launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, st);
-  // dL/dphi_n = g_off ; walk the squaring steps back
+  // dL/dphi_n = g_off ; walk the squaring steps back.  dL/dphi_{k-1} = S + J (two buffers).
   dim3 grid(blocks_for(g.S, 256), g.N);
-  const T* cur = g_off;
-  T* bufs[2] = {ping, pong};
+  const T* curS = g_off;
+  const T* curJ = nullptr;
+  cudaMemsetAsync(bufS[0], 0, sizeof(T) * F, st);
   for (int k = nb; k >= 1; --k) {
-    T* nxt = bufs[(nb - k) & 1];
-    cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
-    ADVK_LAUNCH(K_ss_step_bwd, st, ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, cur, nxt));
-    cur = nxt;
+    const int i = (nb - k) & 1;
+    T* zero_next = (k > 1) ? bufS[i ^ 1] : nullptr;
+    ADVK_LAUNCH(K_ss_step_bwd, st, ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, curS, curJ, bufS[i], bufJ[i], zero_next));
+    curS = bufS[i];
+    curJ = bufJ[i];
   }
-  // dL/dphi_0 = cur - g_off (quirk Q1);  dL/du = that / 2^n;  then the upsample adjoint per axis
+  // dL/dphi_0 = S + J - g_off (quirk Q1);  dL/du = that / 2^n;  then the upsample adjoint per axis
   float inv2n = 1.0f / (float)(1u << nb);
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   T* s1 = (T*)lr_scratch;
-  const T* a = cur;
+  const T* a = curS;
+  const T* a2 = curJ;
   const T* b = g_off;
   float vs = inv2n;
   if (DIM == 3) {
-    launch_adjoint_axis<T>(a, b, vs, s1, g.N, g.D, c.Dl, (i64)g.H * g.W, c.sD, st);
-    a = s1; b = nullptr; vs = 1.f;
+    launch_adjoint_axis<T>(a, a2, b, vs, s1, g.N, g.D, c.Dl, (i64)g.H * g.W, c.sD, st);
+    a = s1; a2 = nullptr; b = nullptr; vs = 1.f;
     s1 += (i64)g.N * c.Dl * g.H * g.W;
   }
-  launch_adjoint_axis<T>(a, b, vs, s1, (i64)g.N * c.Dl, g.H, c.Hl, g.W, c.sH, st);
+  launch_adjoint_axis<T>(a, a2, b, vs, s1, (i64)g.N * c.Dl, g.H, c.Hl, g.W, c.sH, st);
   T* s2 = s1 + (i64)g.N * c.Dl * c.Hl * g.W;
-  launch_adjoint_axis<T>(s1, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
+  launch_adjoint_axis<T>(s1, nullptr, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
   float* planar = (float*)(s2 + (i64)g.N * lr);
   ADVK_LAUNCH(K_aos_to_planar, st, aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr));
   int NC = g.N * DIM;
@@ -662,6 +707,7 @@ extern "C" int advk_morph_field_bwd(const advk_geom* gg, const advk_morph_cfg* c
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
   ADVK_REQUIRE(levels && field_out && g_field && scratch && lr_scratch && g_v, "null pointer");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
   cudaStream_t st = (cudaStream_t)stream;
   return gg->d == 2 ? field_bwd<2>(g, c, scale, nb_steps, levels, field_out, g_field, scratch, lr_scratch, g_v, st)

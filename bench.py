@@ -242,6 +242,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     _lib.load()   # fail loudly if the CUDA library is missing
+    torch.backends.cudnn.benchmark = True      # the user model's convolutions: let cuDNN pick its plan
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

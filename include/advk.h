@@ -145,7 +145,7 @@ int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float
 int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const float* v,
                          float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
                          void* stream);
-/* scratch: 3 fields of N*S elements; lr_scratch: advk_morph_lr_scratch_floats() floats.
+/* scratch: 5 fields of N*S elements; lr_scratch: advk_morph_lr_scratch_floats() floats.
  * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
 size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
 int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
