@@ -361,7 +361,7 @@ class ComposeAdversarialTransformSolver(object):
             if self.shard is not None:   # the guard looks at the whole-batch loss, like the reference
                 self.last_dist = self.shard.global_scalar(dist)
             if bool(torch.isfinite(self.last_dist)):            # the step's single host sync (NaN/Inf guard, :345)
-                dist.backward()
+                self._backward_to_params(dist)
                 for flag, transform in zip(optimize_flags, self.chain_of_transforms):
                     if flag:
                         # quirk Q15 (adv_compose_solver.py:349-357): the reference indexes step_sizes with
@@ -434,7 +434,7 @@ class ComposeAdversarialTransformSolver(object):
         else:
             dist = self.loss_fn(pred=out, reference=st["init_output"].detach())
         st["dist"].copy_(dist.detach().reshape(1))
-        dist.backward()
+        self._backward_to_params(dist)
         for flag, t, buf in zip(st["flags"], chain, st["params"]):
             if flag:
                 t._guard = st["dist"]
@@ -617,6 +617,18 @@ class ComposeAdversarialTransformSolver(object):
         if self.chain_of_transforms is not None:
             for transform in self.chain_of_transforms:
                 transform.eval()
+
+    def _backward_to_params(self, dist):
+        """`dist.backward()` of adv_compose_solver.py:348 restricted to the transformation parameters.
+        The reference back-propagates into the model weights as well and throws those gradients away
+        two lines later (`model.zero_grad()`, :366); asking autograd for the parameter gradients only
+        gives the same `param.grad` without the model's weight-gradient kernels."""
+        leaves = [t.param for t in self.chain_of_transforms
+                  if isinstance(getattr(t, "param", None), torch.Tensor) and t.param.requires_grad]
+        if leaves:
+            dist.backward(inputs=leaves)
+        else:
+            dist.backward()
 
     def make_learnable_transformation(self, optimize_flags, chain_of_transforms=None):
         if chain_of_transforms is None:

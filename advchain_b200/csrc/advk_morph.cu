@@ -11,6 +11,7 @@
 //
 // Fields are interleaved float2 / float4 per voxel so that every stencil corner is ONE vector
 // load and every backward scatter ONE vector reduction (REDG.E.ADD.F32x2/x4).
+#include <stdlib.h>
 #include "advk_common.cuh"
 
 namespace advk {
@@ -231,38 +232,63 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
   out[(i64)n * g.S + p] = V<DIM>::make(ox, oy, oz);
 }
 
-// Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}.  Upstream dL/dphi_k = gS + gJ (two
-// buffers, gJ nullable); output dL/dphi_{k-1} = outS (scatter adjoint of the gather, accumulated
-// with vector REDs, must be zero on entry) + outJ (spatial-Jacobian term, plain store).
+// Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
+//     dL/dphi_{k-1}(y) = sum_x g_k(x) * w(phi_{k-1}(x), y)            scatter adjoint of the gather
+//                      + mult * < d(sample)/d(coord) at y , g_k(y) >   spatial-Jacobian term
+// accumulated with vector REDs into ONE buffer `out` that must be zero on entry.
 //
-// Scatter traffic is the bottleneck of this kernel (ncu: L1TEX 74 %, every RED.128 is processed
-// sector by sector), so neighbouring lanes first combine the contributions that land on the same
-// voxel: lane i's x1-corner is lane i+1's x0-corner whenever both sample the same source row with
-// consecutive x0 (always, for a smooth field with sub-voxel variation) -- one warp shuffle hands the
-// x1 contribution to the neighbour, halving the REDs (8 -> 4 per voxel in 3-D).  Lanes whose
-// neighbour does not match fall back to their own RED, so the result is exact for any field.
-// `zero_next` (nullable): scatter buffer of the NEXT level, zeroed here to save a memset launch.
-template <int DIM>
+// Measured on B200 (profiles/r01i, r01j): the kernel is bound by L2 request traffic (2^d L1-missing
+// gathers + 2^d + 1 REDs per voxel).  A shared-memory tile version (stage phi on tile + halo, scatter
+// into a shared accumulator with an owner election, flush once) executed 1.55x the instructions at
+// 25 % occupancy and ran 2x slower, so the scatter goes straight to L2.  Variants (advk_morph_tune bits):
+//   LANE  neighbouring lanes combine contributions that land on the same voxel before the RED: lane
+//         i's x1 corner is lane i+1's x0 corner whenever both sample the same source row with
+//         consecutive x0 (always, for a smooth field) -- one shuffle hands the x1 contribution over,
+//         halving the REDs.  Lanes without a matching neighbour issue their own RED (exact for any field).
+//         (128^3, 8 steps: 494 us plain -> 399 us; pairing voxels in z per thread on top: 477 us, dropped.)
+//   ZSTORE zero the consumed upstream buffer in the kernel instead of by a memset node: 2 = after the
+//         REDs (default; 522 us vs 494 + 8 memsets), 1 = before them (1311 us: a store to a line whose
+//         load is still in flight stalls the LSU -- the counter-example is kept selectable).
+
+// Emits one corner row (y,z fixed; corners a0 and a0+1 along x) of one voxel: RED of c0 to a0 and c1
+// to a0+1, with the lane hand-off described above when LANE.
+template <int DIM, bool LANE>
+__device__ __forceinline__ void ssb_emit_row(typename V<DIM>::T* __restrict__ dst, int lane, bool v0, bool v1, int a0,
+                                             float c0x, float c0y, float c0z, float c1x, float c1y, float c1z) {
+  if (LANE) {
+    const unsigned FULL = 0xffffffffu;
+    const int a0_next = __shfl_down_sync(FULL, v0 ? a0 : -1, 1);
+    const bool hand = v1 && lane < 31 && a0_next == a0 + 1;
+    const float rx = __shfl_up_sync(FULL, hand ? c1x : 0.f, 1);
+    const float ry = __shfl_up_sync(FULL, hand ? c1y : 0.f, 1);
+    float rz = 0.f;
+    if (DIM == 3) rz = __shfl_up_sync(FULL, hand ? c1z : 0.f, 1);
+    if (lane > 0) { c0x += rx; c0y += ry; c0z += rz; }
+    if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
+    if (v1 && !hand) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
+  } else {
+    if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
+    if (v1) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
+  }
+}
+
+template <int DIM, bool LANE, int ZSTORE>
 __global__ void __launch_bounds__(256)
-ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
-                   const typename V<DIM>::T* __restrict__ gS, const typename V<DIM>::T* __restrict__ gJ,
-                   typename V<DIM>::T* __restrict__ outS, typename V<DIM>::T* __restrict__ outJ,
-                   typename V<DIM>::T* __restrict__ zero_next) {
+ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
+                   typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
-  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = p < g.S;
   const i64 nb = (i64)n * g.S;
   const T* src = phi_prev + nb;
-  T* dst = outS + nb;
+  T* dst = out + nb;
   T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
   if (live) {
-    f = src[p];
-    go = gS[nb + p];
-    if (gJ) { T j = gJ[nb + p]; go.x += j.x; go.y += j.y; if (DIM == 3) go = V<DIM>::make(go.x, go.y, V<DIM>::z(go) + V<DIM>::z(j)); }
-    if (zero_next) zero_next[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
+    f = __ldg(src + p);
+    go = up[nb + p];
+    if (ZSTORE == 1) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
   }
   Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
@@ -283,38 +309,58 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
       const bool row = live && vy && vz;
       const bool v0 = row && ax.v0, v1 = row && ax.v1;
       const int a0 = (az.i0 + dz) * HW + (ay.i0 + dy) * g.W + ax.i0;      // S < 2^31 (host-checked)
-      const float wyz = wy * wz;
       // Jacobian: sum over corners of (+-) <phi(corner), g> * (other-axis weights)
       if (v0) {
         T s0 = __ldg(src + a0);
         float dot = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
-        jx -= dot * wyz;
+        jx -= dot * (wy * wz);
         jy += (dy ? dot : -dot) * (ax.w0 * wz);
         if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w0 * wy);
       }
       if (v1) {
         T s1 = __ldg(src + a0 + 1);
         float dot = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
-        jx += dot * wyz;
+        jx += dot * (wy * wz);
         jy += (dy ? dot : -dot) * (ax.w1 * wz);
         if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w1 * wy);
       }
-      // scatter, with the x1 contribution handed to lane+1 when it lands on that lane's x0 corner
-      const float w0 = ax.w0 * wyz, w1 = ax.w1 * wyz;
-      float c0x = gx * w0, c0y = gy * w0, c0z = gz * w0;
-      const float c1x = gx * w1, c1y = gy * w1, c1z = gz * w1;
-      const int a0_next = __shfl_down_sync(FULL, v0 ? a0 : -1, 1);
-      const bool hand = v1 && lane < 31 && a0_next == a0 + 1;
-      const float rx = __shfl_up_sync(FULL, hand ? c1x : 0.f, 1);
-      const float ry = __shfl_up_sync(FULL, hand ? c1y : 0.f, 1);
-      float rz = 0.f;
-      if (DIM == 3) rz = __shfl_up_sync(FULL, hand ? c1z : 0.f, 1);
-      if (lane > 0) { c0x += rx; c0y += ry; c0z += rz; }
-      if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
-      if (v1 && !hand) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
+      const float w0 = ax.w0 * wy * wz, w1 = ax.w1 * wy * wz;
+      ssb_emit_row<DIM, LANE>(dst, lane, v0, v1, a0, gx * w0, gy * w0, gz * w0, gx * w1, gy * w1, gz * w1);
     }
   }
-  if (live) outJ[nb + p] = V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult);
+  if (live) {
+    atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+    if (ZSTORE == 2) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
+  }
+}
+
+// bit 0: LANE; bits 2-3: ZSTORE (0 memset nodes, 1 zero before the REDs -- slow, kept as the
+// measured counter-example --, 2 zero after the REDs).  Default: LANE + zero after.
+static int g_ssb_mode = -1;
+static int ssb_mode() {
+  if (g_ssb_mode < 0) {
+    const char* e = getenv("ADVK_SSB_MODE");
+    g_ssb_mode = e ? (atoi(e) & 13) : 9;
+  }
+  return g_ssb_mode;
+}
+
+template <int DIM, bool LANE>
+static void launch_ss_step_bwd_z(int zs, const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
+                                 typename V<DIM>::T* out, cudaStream_t st) {
+  dim3 grid(blocks_for(g.S, 256), g.N);
+  if (zs == 1) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 1><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+  else if (zs == 2) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 2><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+  else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 0><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+}
+
+template <int DIM>
+static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
+                               typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
+  const int mode = ssb_mode();
+  const int zs = may_zero_up ? ((mode >> 2) & 3) : 0;
+  if (mode & 1) launch_ss_step_bwd_z<DIM, true>(zs, g, phi_prev, up, out, st);
+  else launch_ss_step_bwd_z<DIM, false>(zs, g, phi_prev, up, out, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -616,22 +662,22 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   const T* L = (const T*)levels;
   i64 F = (i64)g.N * g.S;
   T* g_off = (T*)scratch;
-  T* bufS[2] = {g_off + F, g_off + 3 * F};
-  T* bufJ[2] = {g_off + 2 * F, g_off + 4 * F};
+  T* buf[2] = {g_off + F, g_off + 2 * F};
   // (9)+(8)+(7): clamp mask, Gaussian (self-adjoint), compose-with-base border mask -> g_off = dL/d(off)
   launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, st);
-  // dL/dphi_n = g_off ; walk the squaring steps back.  dL/dphi_{k-1} = S + J (two buffers).
-  dim3 grid(blocks_for(g.S, 256), g.N);
-  const T* curS = g_off;
-  const T* curJ = nullptr;
-  cudaMemsetAsync(bufS[0], 0, sizeof(T) * F, st);
+  // dL/dphi_n = g_off ; walk the squaring steps back, ping-ponging between two buffers that are
+  // zeroed by memset nodes (g_off is kept for the Q1 subtraction below)
+  const bool self_zero = ((ssb_mode() >> 2) & 3) != 0;
+  if (self_zero) cudaMemsetAsync(buf[0], 0, sizeof(T) * F * (nb > 1 ? 2 : 1), st);
+  T* cur = g_off;
   for (int k = nb; k >= 1; --k) {
-    const int i = (nb - k) & 1;
-    T* zero_next = (k > 1) ? bufS[i ^ 1] : nullptr;
-    ADVK_LAUNCH(K_ss_step_bwd, st, ss_step_bwd_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, curS, curJ, bufS[i], bufJ[i], zero_next));
-    curS = bufS[i];
-    curJ = bufJ[i];
+    T* nxt = buf[(nb - k) & 1];
+    if (!self_zero) cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
+    launch_ss_step_bwd<DIM>(g, L + (k - 1) * F, cur, nxt, cur != g_off, st);
+    cur = nxt;
   }
+  const T* curS = cur;
+  const T* curJ = nullptr;
   // dL/dphi_0 = S + J - g_off (quirk Q1);  dL/du = that / 2^n;  then the upsample adjoint per axis
   float inv2n = 1.0f / (float)(1u << nb);
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
@@ -658,6 +704,12 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
 }  // namespace advk
 
 using namespace advk;
+
+extern "C" int advk_morph_tune(int ssb_mode_mask) {
+  int prev = ssb_mode();
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 13;
+  return prev;
+}
 
 extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg, const float* v,
                                  float scale, float* u_lr, float* out_norm2, void* stream) {

@@ -145,12 +145,18 @@ int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float
 int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const float* v,
                          float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
                          void* stream);
-/* scratch: 5 fields of N*S elements; lr_scratch: advk_morph_lr_scratch_floats() floats.
+/* scratch: 5 fields of N*S elements (3 are used); lr_scratch: advk_morph_lr_scratch_floats() floats.
  * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
 size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
 int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
                          const void* levels, const void* field_out, const void* g_field,
                          void* scratch, float* lr_scratch, float* g_v, void* stream);
+/* Kernel variant of the squaring-step backward (A/B timing and tests): bit 0 = neighbouring lanes
+ * combine contributions before the RED; bits 2-3 = who zeroes the ping-pong buffers: 0 memset nodes,
+ * 2 (value 8) the kernel, after its REDs, 1 (value 4) the kernel, before its REDs (slow; measured
+ * counter-example).  Default 9; environment ADVK_SSB_MODE.  Results agree up to fp32 summation
+ * order.  A negative mask only queries; returns the previous mask. */
+int advk_morph_tune(int ssb_mode_mask);
 
 /* ---- AdvNoise / AdvBias: intensity stage ------------------------------------------------
  * advk_bias_lowfield_*: conv_transposeNd + crop (adv_bias.py:293-307) folded into per-axis

@@ -140,10 +140,23 @@ MORPH_TIE_TOL = 1e-2
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
 @pytest.mark.parametrize("support", ["interior", "full"])
-def test_morph_field(d, size, vsize, scale, vnorm, support):
-    """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp."""
+@pytest.mark.parametrize("tile", [9, 0, 1, 4])
+def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
+    """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp.
+    `tile` is the advk_morph_tune mask of the squaring-step backward: 0 plain + memsets, 1 lane-combined REDs,
+    9 lane-combined + in-kernel zeroing after the REDs (default), 4 zeroing before the REDs."""
+    from advchain_b200 import _lib
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()
+    prev = _lib.load().advk_morph_tune(tile)
+    try:
+        _morph_field_case(d, size, vsize, scale, vnorm, support)
+    finally:
+        _lib.load().advk_morph_tune(prev)
+
+
+def _morph_field_case(d, size, vsize, scale, vnorm, support):
+    from advchain_b200.augmentor import AdvMorph
     torch.manual_seed(4)
     n = size[0]
     cfg = stage_cfgs(d, size, vector=vsize)["morph"]
