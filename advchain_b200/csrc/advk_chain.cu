@@ -51,6 +51,7 @@ struct Program {
   Dims g; int C; int n; int first_bwd;
   int do_clamp; float lo, hi; int want_mask;
   int tps;          // tiles per sample
+  FastDiv ftps;
   int interleave;   // 0: block owns a contiguous tile range; 1: tiles dealt round-robin
   i64 n_tiles;
   Stage st[MAX_STAGES];
@@ -68,50 +69,53 @@ __device__ __forceinline__ Stencil<DIM> make_stencil(float cx, float cy, float c
   return s;
 }
 
-// f(q, wx, wy, wz, dx, dy, dz) for every in-bounds corner; q = linear voxel index in the sample.
-template <int DIM, class F>
-__device__ __forceinline__ void for_corners(const Stencil<DIM>& s, const Dims& g, F f) {
-  const i64 HW = (i64)g.H * g.W;
+// The 2^d corners of one sampling stencil, resolved ONCE per voxel and reused by every channel:
+// 32-bit voxel offsets inside the sample (S < 2^31, host-checked), interpolation weights in ATen's
+// multiplication order (wx*wy)*wz, and a validity bit per corner.  Corner k: dx = k&1, dy = (k>>1)&1,
+// dz = k>>2 -- the order the gathers are summed in (z outer, x inner, like grid_sample).
+template <int DIM> struct Corners {
+  static constexpr int NC = (DIM == 3) ? 8 : 4;
+  int off[NC];
+  float w[NC];
+  unsigned mask;
+};
+
+template <int DIM>
+__device__ __forceinline__ void make_corners(const Stencil<DIM>& s, const Dims& g, bool ok, Corners<DIM>& t) {
+  const int HW = g.H * g.W;
+  const int base = s.z.i0 * HW + s.y.i0 * g.W + s.x.i0;
+  t.mask = 0u;
 #pragma unroll
-  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-    const bool vz = dz ? s.z.v1 : s.z.v0;
-    const float wz = dz ? s.z.w1 : s.z.w0;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const bool vy = dy ? s.y.v1 : s.y.v0;
-      const float wy = dy ? s.y.w1 : s.y.w0;
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const bool vx = dx ? s.x.v1 : s.x.v0;
-        const float wx = dx ? s.x.w1 : s.x.w0;
-        if (vx && vy && vz)
-          f((i64)(s.z.i0 + dz) * HW + (i64)(s.y.i0 + dy) * g.W + (s.x.i0 + dx), wx, wy, wz, dx, dy, dz);
-      }
-    }
+  for (int k = 0; k < Corners<DIM>::NC; ++k) {
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+    const bool v = ok && (dx ? s.x.v1 : s.x.v0) && (dy ? s.y.v1 : s.y.v0) && (dz ? s.z.v1 : s.z.v0);
+    t.off[k] = base + dx + dy * g.W + dz * HW;
+    t.w[k] = ((dx ? s.x.w1 : s.x.w0) * (dy ? s.y.w1 : s.y.w0)) * (dz ? s.z.w1 : s.z.w0);
+    t.mask |= (v ? 1u : 0u) << k;
   }
 }
 
-struct Vox { int n, x, y, z; i64 p; bool ok; };
+struct Vox { int n, x, y, z; int p; bool ok; };
 
-__device__ __forceinline__ Vox tile_voxel(const Program& P, i64 t) {
+__device__ __forceinline__ Vox tile_voxel(const Program& P, unsigned t) {
   Vox v;
-  v.n = (int)(t / P.tps);
-  v.p = (t % P.tps) * CT + threadIdx.x;
+  const unsigned n = fast_div(t, P.ftps);
+  v.n = (int)n;
+  v.p = (int)((t - n * (unsigned)P.tps) * CT + threadIdx.x);
   v.ok = v.p < P.g.S;
-  v.x = (int)(v.p % P.g.W);
-  v.y = (int)((v.p / P.g.W) % P.g.H);
-  v.z = (int)(v.p / ((i64)P.g.W * P.g.H));
+  voxel_xyz(P.g, (unsigned)v.p, v.x, v.y, v.z);
   return v;
 }
 
 // tile loop: for (t = t0; t < t1; t += dt)
-__device__ __forceinline__ void tile_range(const Program& P, i64& t0, i64& t1, i64& dt) {
+__device__ __forceinline__ void tile_range(const Program& P, unsigned& t0, unsigned& t1, unsigned& dt) {
+  const unsigned nt = (unsigned)P.n_tiles;
   if (P.interleave) {
-    t0 = blockIdx.x; t1 = P.n_tiles; dt = gridDim.x;
+    t0 = blockIdx.x; t1 = nt; dt = gridDim.x;
   } else {
-    i64 per = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-    t0 = (i64)blockIdx.x * per;
-    t1 = t0 + per < P.n_tiles ? t0 + per : P.n_tiles;
+    const unsigned per = (nt + gridDim.x - 1) / gridDim.x;
+    t0 = blockIdx.x * per;
+    t1 = t0 + per < nt ? t0 + per : nt;
     dt = 1;
   }
 }
@@ -124,24 +128,27 @@ __device__ __forceinline__ void stage_coords(const Program& P, const Stage& s, c
                                              float& bz) {
   const Dims& g = P.g;
   if (FIELD) {
-    if (DIM == 2) {
-      float2 f = reinterpret_cast<const float2*>(s.phi)[(i64)v.n * g.S + v.p];
-      rx = f.x; ry = f.y; rz = 0.f;
-    } else {
-      float4 f = reinterpret_cast<const float4*>(s.phi)[(i64)v.n * g.S + v.p];
-      rx = f.x; ry = f.y; rz = f.z;
+    rx = ry = rz = 0.f;
+    if (v.ok) {
+      if (DIM == 2) {
+        float2 f = __ldg(reinterpret_cast<const float2*>(s.phi) + ((i64)v.n * g.S + v.p));
+        rx = f.x; ry = f.y;
+      } else {
+        float4 f = __ldg(reinterpret_cast<const float4*>(s.phi) + ((i64)v.n * g.S + v.p));
+        rx = f.x; ry = f.y; rz = f.z;
+      }
     }
     cx = clampf(rx, -1.f, 1.f); cy = clampf(ry, -1.f, 1.f); cz = clampf(rz, -1.f, 1.f);
     bx = by = bz = 0.f;
   } else {
-    bx = base_coord(v.x, g.W, 0.f); by = base_coord(v.y, g.H, 0.f);
+    bx = base_coord_s(v.x, g.W, g.stW, 0.f); by = base_coord_s(v.y, g.H, g.stH, 0.f);
     if (DIM == 2) {
       const float* t = s.theta + v.n * 6;
       cx = t[0] * bx + t[1] * by + t[2];
       cy = t[3] * bx + t[4] * by + t[5];
       cz = 0.f; bz = 0.f;
     } else {
-      bz = base_coord(v.z, g.D, 0.f);
+      bz = base_coord_s(v.z, g.D, g.stD, 0.f);
       const float* t = s.theta + v.n * 12;
       cx = t[0] * bx + t[1] * by + t[2] * bz + t[3];
       cy = t[4] * bx + t[5] * by + t[6] * bz + t[7];
@@ -156,10 +163,10 @@ __device__ __forceinline__ void stage_coords(const Program& P, const Stage& s, c
 template <int DIM>
 __device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1, dt;
+  unsigned t0, t1, dt;
   tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; t += dt) {
+  for (unsigned t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float bv = 1.f;
@@ -167,8 +174,8 @@ __device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last)
       float braw; bool pass;
       bv = bias_value(s.b, bias_up<DIM>(s.b, s.low + (i64)v.n * s.b.lD * s.b.lH * s.b.lW, v.z, v.y, v.x, g, v.p), braw, pass);
     }
-    for (int c = 0; c < P.C; ++c) {
-      i64 q = ((i64)v.n * P.C + c) * g.S + v.p;
+    i64 q = (i64)v.n * P.C * g.S + v.p;
+    for (int c = 0; c < P.C; ++c, q += g.S) {
       float val = intensity_point(s.order, s.src[q], s.order != 1 ? s.delta[q] : 0.f, s.ns, bv, s.use_ig, s.ig);
       if (clamp) val = clampf(val, P.lo, P.hi);
       s.dst[q] = val;
@@ -176,37 +183,47 @@ __device__ void stage_intensity_fwd(const Program& P, const Stage& s, bool last)
   }
 }
 
+template <int DIM>
+__device__ __forceinline__ float gather_corners(const Corners<DIM>& ct, const float* __restrict__ src, float pv) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < Corners<DIM>::NC; ++k)
+    if (ct.mask & (1u << k)) acc += (__ldg(src + ct.off[k]) - pv) * ct.w[k];
+  return acc + pv;
+}
+
 template <int DIM, bool FIELD>
 __device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1, dt;
+  unsigned t0, t1, dt;
   tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; t += dt) {
+  for (unsigned t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
     Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Corners<DIM> ct;
+    make_corners<DIM>(st, g, true, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
-    for (int c = 0; c < P.C; ++c) {
-      const i64 cb = ((i64)v.n * P.C + c) * g.S;
-      const float* src = s.src + cb;
-      float acc = 0.f;
-      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
-        acc += (__ldg(src + q) - pv) * (wx * wy * wz);
-      });
-      float val = acc + pv;
+    const float* src = s.src + (i64)v.n * P.C * g.S;
+    float* dst = s.dst + (i64)v.n * P.C * g.S + v.p;
+    for (int c = 0; c < P.C; ++c, src += g.S, dst += g.S) {
+      float val = gather_corners<DIM>(ct, src, pv);
       if (clamp) val = clampf(val, P.lo, P.hi);
-      s.dst[cb + v.p] = val;
+      *dst = val;
     }
     if (s.mdst) {
-      const float* ms = s.msrc ? s.msrc + (i64)v.n * g.S : nullptr;
-      float acc = 0.f;
-      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
-        acc += ((ms ? __ldg(ms + q) : 1.f) - pv) * (wx * wy * wz);
-      });
-      float m = acc + pv;
+      float m;
+      if (s.msrc) m = gather_corners<DIM>(ct, s.msrc + (i64)v.n * g.S, pv);
+      else {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < Corners<DIM>::NC; ++k)
+          if (ct.mask & (1u << k)) acc += (1.f - pv) * ct.w[k];
+        m = acc + pv;
+      }
       if (s.binarize) m = (m != 0.f) ? 1.f : 0.f;
       s.mdst[(i64)v.n * g.S + v.p] = m;
     }
@@ -258,10 +275,10 @@ __device__ void zero_buffers(const Program& P) {
 template <int DIM>
 __device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
-  i64 t0, t1, dt;
+  unsigned t0, t1, dt;
   tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
-  for (i64 t = t0; t < t1; t += dt) {
+  for (unsigned t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (!v.ok) continue;
     float bv = 1.f, braw = 1.f;
@@ -269,8 +286,8 @@ __device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last)
     if (s.order != 0)
       bv = bias_value(s.b, bias_up<DIM>(s.b, s.low + (i64)v.n * s.b.lD * s.b.lH * s.b.lW, v.z, v.y, v.x, g, v.p), braw, pass);
     float gb = 0.f;
-    for (int c = 0; c < P.C; ++c) {
-      i64 q = ((i64)v.n * P.C + c) * g.S + v.p;
+    i64 q = (i64)v.n * P.C * g.S + v.p;
+    for (int c = 0; c < P.C; ++c, q += g.S) {
       float go = s.g_dst[q];
       const float x0 = s.src[q];
       const float dl = (s.order != 1) ? s.delta[q] : 0.f;
@@ -287,11 +304,22 @@ __device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last)
   }
 }
 
+// Adjoint of a warp stage.  Per voxel the corner table is built once; per channel the kernel loads the
+// 2^d source values (needed for the coordinate gradient and the clamp mask) and scatters go*w.  The
+// scatter is lane-combined like the squaring-step backward: along a corner row the x1 corner of lane i
+// is the x0 corner of lane i+1 for (near-)unit x spacing, so one shuffle per (row, channel) hands that
+// contribution over and the RED count halves; the hand-off pattern is decided once per voxel and shared
+// by all channels.  The coordinate gradient sum_c (src_c - pv) * go_c is accumulated per corner and
+// turned into d/dx, d/dy, d/dz after the channel loop.
 template <int DIM, bool FIELD>
 __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, float* red) {
   constexpr int NG = DIM * (DIM + 1);
+  constexpr int NC = Corners<DIM>::NC;
+  constexpr int NR = NC / 2;
+  const unsigned FULL = 0xffffffffu;
   const Dims& g = P.g;
-  i64 t0, t1, dt;
+  const int lane = threadIdx.x & 31;
+  unsigned t0, t1, dt;
   tile_range(P, t0, t1, dt);
   const bool clamp = last && P.do_clamp;
   const bool want_theta = !FIELD && s.g_theta != nullptr;
@@ -299,7 +327,7 @@ __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, floa
 #pragma unroll
   for (int i = 0; i < NG; ++i) acc[i] = 0.f;
   int cur_n = -1;
-  for (i64 t = t0; t < t1; t += dt) {
+  for (unsigned t = t0; t < t1; t += dt) {
     Vox v = tile_voxel(P, t);
     if (want_theta && v.n != cur_n) {            // block-uniform
       if (cur_n >= 0) {
@@ -313,32 +341,67 @@ __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, floa
       }
       cur_n = v.n;
     }
-    if (!v.ok) continue;
+    // no early exit for !v.ok: the whole warp takes part in the shuffles below
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
     Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Corners<DIM> ct;
+    make_corners<DIM>(st, g, v.ok, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
-    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
-    for (int c = 0; c < P.C; ++c) {
-      const i64 cb = ((i64)v.n * P.C + c) * g.S;
-      const float* src = s.src + cb;
-      float go = s.g_dst[cb + v.p];
+    const bool scatter = s.g_src != nullptr;
+    unsigned hand = 0u;                            // bit r: row r's x1 contribution goes to lane+1
+    if (scatter) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int k0 = 2 * r, k1 = k0 + 1;
+        const int a0_next = __shfl_down_sync(FULL, (ct.mask & (1u << k0)) ? ct.off[k0] : -1, 1);
+        if ((ct.mask & (1u << k1)) && lane < 31 && a0_next == ct.off[k1]) hand |= 1u << r;
+      }
+    }
+    float tk[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) tk[k] = 0.f;
+    const float* src = s.src + (i64)v.n * P.C * g.S;
+    const float* gd = s.g_dst + (i64)v.n * P.C * g.S + v.p;
+    float* gs = scatter ? s.g_src + (i64)v.n * P.C * g.S : nullptr;
+    for (int c = 0; c < P.C; ++c, src += g.S, gd += g.S) {
+      float go = v.ok ? *gd : 0.f;
+      float val[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) val[k] = (ct.mask & (1u << k)) ? __ldg(src + ct.off[k]) - pv : 0.f;
       if (clamp) {
         float a = 0.f;
-        for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int, int, int) {
-          a += (__ldg(src + q) - pv) * (wx * wy * wz);
-        });
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a += val[k] * ct.w[k];
         a += pv;
         if (!(a >= P.lo && a <= P.hi)) go = 0.f;
       }
-      float* gs = s.g_src ? s.g_src + cb : nullptr;
-      for_corners<DIM>(st, g, [&](i64 q, float wx, float wy, float wz, int dx, int dy, int dz) {
-        if (gs) atomicAdd(gs + q, go * (wx * wy * wz));
-        float val = (__ldg(src + q) - pv) * go;
-        ggx += (dx ? val : -val) * (wy * wz);
-        ggy += (dy ? val : -val) * (wx * wz);
-        if (DIM == 3) ggz += (dz ? val : -val) * (wx * wy);
-      });
+#pragma unroll
+      for (int k = 0; k < NC; ++k) tk[k] += val[k] * go;
+      if (scatter) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int k0 = 2 * r, k1 = k0 + 1;
+          const bool h = (hand >> r) & 1u;
+          float c0 = go * ct.w[k0];
+          const float c1 = go * ct.w[k1];
+          const float rcv = __shfl_up_sync(FULL, h ? c1 : 0.f, 1);
+          if (lane > 0) c0 += rcv;
+          if (ct.mask & (1u << k0)) atomicAdd(gs + ct.off[k0], c0);
+          if ((ct.mask & (1u << k1)) && !h) atomicAdd(gs + ct.off[k1], c1);
+        }
+        gs += g.S;
+      }
+    }
+    if (!v.ok) continue;
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const float wx = dx ? st.x.w1 : st.x.w0, wy = dy ? st.y.w1 : st.y.w0, wz = dz ? st.z.w1 : st.z.w0;
+      ggx += (dx ? tk[k] : -tk[k]) * (wy * wz);
+      ggy += (dy ? tk[k] : -tk[k]) * (wx * wz);
+      if (DIM == 3) ggz += (dz ? tk[k] : -tk[k]) * (wx * wy);
     }
     ggx *= st.x.mult; ggy *= st.y.mult; ggz *= st.z.mult;
     if (FIELD) {
@@ -438,8 +501,11 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
   if (!d || !make_dims(&d->g, P.g) || d->C < 1 || d->n_stages < 1 || d->n_stages > MAX_STAGES) return false;
   P.C = d->C; P.n = d->n_stages; P.first_bwd = 0;
   P.do_clamp = d->do_clamp; P.lo = d->clamp_lo; P.hi = d->clamp_hi; P.want_mask = d->want_mask;
+  if (P.g.S >= 0x7fffffffLL) return false;               // 32-bit voxel offsets inside a sample
   P.tps = (int)((P.g.S + CT - 1) / CT);
+  P.ftps = make_fastdiv((unsigned)P.tps);
   P.n_tiles = (i64)P.tps * P.g.N;
+  if (P.n_tiles >= 0x7fffffffLL) return false;
   const i64 ncs = slot_floats((i64)P.g.N * P.C * P.g.S), ns = slot_floats((i64)P.g.N * P.g.S);
   int last_warp = -1;
   for (int k = 0; k < P.n; ++k)
@@ -491,12 +557,20 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
 
 // Tuning knobs (environment, read once; advk_chain_tune() overrides): resident blocks per SM the
 // kernels are compiled for (register cap) and the tile-to-block assignment.
-static int g_minb = -1, g_interleave = -1;
+static int g_minb = -1, g_minb_bwd = -1, g_interleave = -1;
+static bool minb_ok(int v) { return v == 2 || v == 3 || v == 4 || v == 6; }
 static void tune_defaults() {
   if (g_minb < 0) {
     const char* e = getenv("ADVK_CHAIN_MINB");
     g_minb = e ? atoi(e) : 4;
-    if (g_minb != 2 && g_minb != 3 && g_minb != 4 && g_minb != 6) g_minb = 4;
+    if (!minb_ok(g_minb)) g_minb = 4;
+  }
+  if (g_minb_bwd < 0) {
+    // the adjoint keeps the corner table, per-corner partial sums and the theta accumulators live:
+    // ~110 registers without spills, so it is compiled for 3 resident CTAs (80 regs, 80 B spilled)
+    const char* e = getenv("ADVK_CHAIN_MINB_BWD");
+    g_minb_bwd = e ? atoi(e) : 3;
+    if (!minb_ok(g_minb_bwd)) g_minb_bwd = 3;
   }
   if (g_interleave < 0) {
     const char* e = getenv("ADVK_CHAIN_INTERLEAVE");
@@ -553,11 +627,12 @@ template <int DIM>
 static int launch_bwd(Program& P, cudaStream_t st) {
   tune_defaults();
   P.interleave = g_interleave;
-  switch (g_minb) {
+  switch (g_minb_bwd) {
     case 2: return launch_bwd_t<DIM, 2>(P, st);
     case 3: return launch_bwd_t<DIM, 3>(P, st);
     case 6: return launch_bwd_t<DIM, 6>(P, st);
-    default: return launch_bwd_t<DIM, 4>(P, st);
+    case 4: return launch_bwd_t<DIM, 4>(P, st);
+    default: return launch_bwd_t<DIM, 3>(P, st);
   }
 }
 
@@ -567,10 +642,15 @@ using namespace advk;
 
 extern "C" int advk_chain_tune(int min_blocks_per_sm, int interleave) {
   tune_defaults();
-  if (min_blocks_per_sm == 2 || min_blocks_per_sm == 3 || min_blocks_per_sm == 4 || min_blocks_per_sm == 6)
-    g_minb = min_blocks_per_sm;
+  // one digit: both directions; two digits "FB": forward F, backward B
+  if (min_blocks_per_sm >= 10) {
+    if (minb_ok(min_blocks_per_sm / 10)) g_minb = min_blocks_per_sm / 10;
+    if (minb_ok(min_blocks_per_sm % 10)) g_minb_bwd = min_blocks_per_sm % 10;
+  } else if (minb_ok(min_blocks_per_sm)) {
+    g_minb = g_minb_bwd = min_blocks_per_sm;
+  }
   if (interleave == 0 || interleave == 1) g_interleave = interleave;
-  return g_minb * 10 + g_interleave;
+  return (g_minb * 10 + g_minb_bwd) * 10 + g_interleave;
 }
 
 extern "C" int advk_chain_set_cooperative(int enable) {

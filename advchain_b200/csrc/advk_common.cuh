@@ -52,9 +52,34 @@ struct Prof {
     }                                           \
   } while (0)
 
+// Division by a run-time constant without the (emulated, ~100-instruction) 64-bit divide: the
+// multiply-high form used by CUTLASS' FastDivmod; exact for dividends below 2^31.
+struct FastDiv {
+  unsigned d, mul, shr;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+  FastDiv f;
+  f.d = d ? d : 1; f.mul = 0; f.shr = 0;
+  if (f.d != 1) {
+    unsigned lg = 0;
+    while ((1ull << lg) < f.d) ++lg;                    // ceil(log2 d)
+    unsigned p = 31 + lg;
+    f.mul = (unsigned)(((1ull << p) + f.d - 1) / f.d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+#endif
+
 struct Dims {
   int N, D, H, W;
   i64 S;  // D*H*W
+  FastDiv fW, fHW;            // voxel index -> (z, y, x), valid while S < 2^31
+  float stD, stH, stW;        // linspace step 2/(size-1) per axis (0 when size == 1)
 };
 
 inline bool make_dims(const advk_geom* g, Dims& o) {
@@ -62,8 +87,23 @@ inline bool make_dims(const advk_geom* g, Dims& o) {
   if (g->d == 2 && g->D != 1) return false;
   o.N = g->N; o.D = g->D; o.H = g->H; o.W = g->W;
   o.S = (i64)g->D * g->H * g->W;
+  o.fW = make_fastdiv((unsigned)g->W);
+  o.fHW = make_fastdiv((unsigned)((i64)g->H * g->W < 0x7fffffffLL ? (i64)g->H * g->W : 1));
+  o.stD = g->D > 1 ? 2.0f / (float)(g->D - 1) : 0.f;
+  o.stH = g->H > 1 ? 2.0f / (float)(g->H - 1) : 0.f;
+  o.stW = g->W > 1 ? 2.0f / (float)(g->W - 1) : 0.f;
   return true;
 }
+
+#ifdef __CUDACC__
+// p (voxel index within one sample, < 2^31) -> coordinates
+__device__ __forceinline__ void voxel_xyz(const Dims& g, unsigned p, int& x, int& y, int& z) {
+  const unsigned zz = fast_div(p, g.fHW);
+  const unsigned r = p - zz * (unsigned)(g.H * g.W);
+  const unsigned yy = fast_div(r, g.fW);
+  x = (int)(r - yy * (unsigned)g.W); y = (int)yy; z = (int)zz;
+}
+#endif
 
 template <int DIM> struct FieldT;
 template <> struct FieldT<2> { typedef float2 type; };
@@ -77,6 +117,11 @@ template <> struct FieldT<3> { typedef float4 type; };
 __device__ __forceinline__ float base_coord(int i, int size, float single = -1.f) {
   if (size <= 1) return single;
   float step = 2.0f / (float)(size - 1);
+  return (i < size / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(size - 1 - i));
+}
+// same value with the step precomputed on the host (Dims::stW/stH/stD: the identical fp32 quotient)
+__device__ __forceinline__ float base_coord_s(int i, int size, float step, float single = -1.f) {
+  if (size <= 1) return single;
   return (i < size / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(size - 1 - i));
 }
 

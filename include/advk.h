@@ -278,8 +278,10 @@ typedef struct advk_chain_desc {
  * previous setting.  Results are identical; exists for A/B timing. */
 int advk_chain_set_cooperative(int enable);
 /* Tuning (A/B timing): resident blocks per SM the chain kernels are compiled for (2, 3, 4 or 6 =
- * register cap 128/80/64/40; other values keep the current one) and tile assignment (0 contiguous
- * ranges per block, 1 round-robin; other values keep).  Returns 10*min_blocks + interleave. */
+ * register cap 128/80/64/40; one digit sets forward and backward, two digits "FB" set them
+ * separately, e.g. 43; other values keep the current ones; defaults 4 / 3) and tile assignment
+ * (0 contiguous ranges per block, 1 round-robin; other values keep).
+ * Returns 100*fwd + 10*bwd + interleave. */
 int advk_chain_tune(int min_blocks_per_sm, int interleave);
 int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* stash_floats, size_t* scratch_floats);
 int advk_chain_apply_fwd(const advk_chain_desc* d, const float* src, const float* mask_src,

@@ -47,7 +47,7 @@ def measure(tag):
 
 for coop in (1, 0):
     lib.advk_chain_set_cooperative(coop)
-    for minb in (2, 3, 4, 6):
-        for il in (0, 1):
+    for minb in ((43, 42, 44, 33, 32, 63) if coop else (43,)):
+        for il in (1,):
             lib.advk_chain_tune(minb, il)
-            measure("coop=%d minb=%d interleave=%d" % (coop, minb, il))
+            measure("coop=%d minb(fwd,bwd)=%d interleave=%d" % (coop, minb, il))
