@@ -23,7 +23,7 @@ int check_launch(const char* what);
   X(intensity_bwd) X(adjoint_axis_f) X(sumsq) X(update) X(clamp) X(clamp_bwd) X(nonzero)         \
   X(smooth_fwd) X(smooth_bwd) X(adjoint_axis) X(lowres_smooth) X(init_phi0) X(ss_step)           \
   X(ss_step_bwd) X(aos_to_planar) X(unorm2) X(warp_fwd) X(warp_bwd) X(loss_softmax)               \
-  X(loss_contour) X(loss_finalize) X(loss_grad) X(chain_fwd) X(chain_fwd_stage) X(chain_bwd)         \
+  X(loss_contour) X(loss_contour_adj) X(loss_finalize) X(loss_grad) X(chain_fwd) X(chain_fwd_stage) X(chain_bwd)         \
   X(chain_bwd_stage) X(steps_check)
 enum KernelId {
 #define ADVK_X(n) K_##n,
@@ -151,11 +151,11 @@ __device__ __forceinline__ float gs_index(float coord, int size, int pad, float&
     mult *= m;
   }
   if (pad != ADVK_PAD_ZEROS) {
-    if (x <= 0.f) { x = 0.f; mult = 0.f; }
-    else {
-      float mx = (float)(size - 1);
-      if (x >= mx) { x = mx; mult = 0.f; }
-    }
+    // clip_coordinates: min(size-1, max(x, 0)) (NaN -> 0 like ATen's ::max), gradient 0 on the clipped side
+    const float mx = (float)(size - 1);
+    const bool inside = (x > 0.f) && (x < mx);
+    x = fminf(mx, fmaxf(x, 0.f));
+    mult = inside ? mult : 0.f;
   }
   // safe_downgrade_to_int_range: anything non-finite or huge is "far outside"
   if (!(x <= 2147483646.f && x >= -2147483648.f)) x = -100.f;

@@ -69,7 +69,8 @@ intensity_fwd_kernel(Dims g, int C, int order, const float* __restrict__ x, cons
   if (p >= g.S) return;
   float bv = 1.f;
   if (order != 0) {
-    const int xx = (int)(p % g.W), yy = (int)((p / g.W) % g.H), zz = (int)(p / ((i64)g.W * g.H));
+    int xx, yy, zz;
+    voxel_xyz(g, (unsigned)p, xx, yy, zz);
     float braw; bool pass;
     bv = bias_value(b, bias_up<DIM>(b, low + (i64)n * b.lD * b.lH * b.lW, zz, yy, xx, g, p), braw, pass);
     if (bias_out) bias_out[(i64)n * g.S + p] = bv;
@@ -92,7 +93,8 @@ intensity_bwd_kernel(Dims g, int C, int order, const float* __restrict__ g_out, 
   if (p >= g.S) return;
   float bv = 1.f, braw = 1.f; bool pass = true;
   if (order != 0) {
-    const int xx = (int)(p % g.W), yy = (int)((p / g.W) % g.H), zz = (int)(p / ((i64)g.W * g.H));
+    int xx, yy, zz;
+    voxel_xyz(g, (unsigned)p, xx, yy, zz);
     bv = bias_value(b, bias_up<DIM>(b, low + (i64)n * b.lD * b.lH * b.lW, zz, yy, xx, g, p), braw, pass);
   }
   float gb = 0.f;
@@ -172,6 +174,7 @@ extern "C" int advk_intensity_fwd(const advk_geom* gg, int C, int order, const f
   Dims g; BiasCfg b = {};
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(order >= 0 && order <= 3 && C >= 1 && x && out, "bad order / null pointer");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   if (order != 1) ADVK_REQUIRE(delta != nullptr, "delta is NULL");
   if (order != 0) {
     ADVK_REQUIRE(make_bias(bias, gg->d, b) && low, "bad bias config / low is NULL");
@@ -193,6 +196,7 @@ extern "C" int advk_intensity_bwd(const advk_geom* gg, int C, int order, const f
   Dims g; BiasCfg b = {};
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(order >= 0 && order <= 3 && C >= 1 && x && g_out, "bad order / null pointer");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   if (order == 2 || order == 3) ADVK_REQUIRE(delta != nullptr, "delta is NULL");
   if (order != 0) {
     ADVK_REQUIRE(make_bias(bias, gg->d, b) && low, "bad bias config / low is NULL");

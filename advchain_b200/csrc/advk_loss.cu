@@ -13,7 +13,8 @@
 //
 //   K1 loss_softmax : E, pred  <- output, reference ; mse partial sums
 //   K2 loss_contour : R_k = mult_k m^2 (k * E_c)    ; contour partial sums      (c >= 1)
-//   K3 loss_grad    : g_pred_c = 2 A_mse m^2 E_c + 2 A_cont sum_k k^T * R_k ; softmax backward
+//   K3 loss_contour_adj : s_c = sum_k k^T * R_k (c >= 1)
+//   K4 loss_grad    : g_pred_c = 2 A_mse m^2 E_c + 2 A_cont s_c ; softmax backward
 #include "advk_common.cuh"
 
 namespace advk {
@@ -55,54 +56,141 @@ loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const fl
   if (threadIdx.x == 0) atomicAdd(acc, (double)v[0]);
 }
 
-// One thread per voxel per object class; R has 2 planes per class: [0] = sobel along the "x
-// filter" direction (2-D kx | 3-D gx, weight 2), [1] = the other (2-D ky | 3-D gz).
+// Sobel stencils through shared memory.  The 3x3(x3) kernels are products of the 1-D factors
+// h = [1,2,1] and hp = [1,0,-1] (common/loss.py:148-203):
+//     2-D  kx = h(H) hp(W),  ky = hp(H) h(W)
+//     3-D  gx = h(D) hp(H) h(W),  gz = h(D) h(H) hp(W)        (quirk Q10: gy := gx)
+// A CTA owns a 32 x 8 (x,y) tile and marches along z: each plane is staged once (tile + 1-voxel
+// halo, zero outside the volume like the reference's padding=1 convolutions), every thread
+// evaluates the two in-plane factors from 6 shared reads and keeps a 3-plane register window for the
+// h(D) factor -- 1.06 global reads per voxel instead of 27 L1 gathers.
+constexpr int LT_X = 32, LT_Y = 8, LT_Z = 32;
+
+// in-plane factors at (tx,ty) of a staged (LT_Y+2) x (LT_X+2) tile:
+//   a = hp(H) h(W) t,  b = h(H) hp(W) t
+__device__ __forceinline__ void sobel_plane(const float (*t)[LT_X + 2], int tx, int ty, float& a, float& b) {
+  const float r00 = t[ty][tx], r01 = t[ty][tx + 1], r02 = t[ty][tx + 2];
+  const float r10 = t[ty + 1][tx], r12 = t[ty + 1][tx + 2];
+  const float r20 = t[ty + 2][tx], r21 = t[ty + 2][tx + 1], r22 = t[ty + 2][tx + 2];
+  // hp = [1,0,-1] over offsets (-1,0,+1); h = [1,2,1]
+  a = (r00 + 2.f * r01 + r02) - (r20 + 2.f * r21 + r22);
+  b = (r00 + 2.f * r10 + r20) - (r02 + 2.f * r12 + r22);
+}
+
+__device__ __forceinline__ void stage_plane(float (*t)[LT_X + 2], const float* __restrict__ src, const Dims& g,
+                                            int pz, int x0, int y0) {
+  const bool zin = pz >= 0 && pz < g.D;
+  for (int i = threadIdx.x; i < (LT_Y + 2) * (LT_X + 2); i += LT_X * LT_Y) {
+    const int ly = i / (LT_X + 2), lx = i - ly * (LT_X + 2);
+    const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+    float v = 0.f;
+    if (zin && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) v = __ldg(src + ((i64)pz * g.H + gy) * g.W + gx);
+    t[ly][lx] = v;
+  }
+}
+
+// R has 2 planes per object class: [0] = the "x filter" response (2-D kx | 3-D gx, weight 2),
+// [1] = the other (2-D ky | 3-D gz); both already multiplied by mult * m^2 for the backward.
 template <int DIM>
-__global__ void __launch_bounds__(256)
-loss_contour_kernel(Dims g, int K, const float* __restrict__ E, const float* __restrict__ mask,
+__global__ void __launch_bounds__(LT_X * LT_Y)
+loss_contour_kernel(Dims g, int K, int nzc, const float* __restrict__ E, const float* __restrict__ mask,
                     float* __restrict__ R, double* __restrict__ acc) {
+  __shared__ float tile[2][LT_Y + 2][LT_X + 2];
   __shared__ float red[32];
-  const int n = blockIdx.z / (K - 1);
-  const int c = 1 + blockIdx.z % (K - 1);
-  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x % LT_X, ty = threadIdx.x / LT_X;
+  const int zc = blockIdx.z % nzc;
+  const int nc = blockIdx.z / nzc;
+  const int n = nc / (K - 1), c = 1 + nc % (K - 1);
+  const int x0 = blockIdx.x * LT_X, y0 = blockIdx.y * LT_Y;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool inxy = x < g.W && y < g.H;
+  const float* e = E + ((i64)n * K + c) * g.S;
+  const float* mk = mask ? mask + (i64)n * g.S : nullptr;
+  float* r0 = R + (((i64)n * (K - 1) + (c - 1)) * 2) * g.S;
+  float* r1 = r0 + g.S;
+  const float mult0 = (DIM == 3) ? 2.f : 1.f;               // quirk Q10: gx is used for x and y
   float v[1] = {0.f};
-  if (p < g.S) {
-    const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
-    const float* e = E + ((i64)n * K + c) * g.S;
-    float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-    for (int a = (DIM == 3 ? -1 : 0); a <= (DIM == 3 ? 1 : 0); ++a) {
-      int zz = z + a;
-      if (zz < 0 || zz >= g.D) continue;
-#pragma unroll
-      for (int b = -1; b <= 1; ++b) {
-        int yy = y + b;
-        if (yy < 0 || yy >= g.H) continue;
-#pragma unroll
-        for (int cc = -1; cc <= 1; ++cc) {
-          int xx = x + cc;
-          if (xx < 0 || xx >= g.W) continue;
-          float val = __ldg(e + ((i64)zz * g.H + yy) * g.W + xx);
-          if (DIM == 2) {
-            g0 += sob_h(b) * sob_hp(cc) * val;      // kx[b][cc] = h[b] hp[cc]
-            g1 += sob_hp(b) * sob_h(cc) * val;      // ky[b][cc] = hp[b] h[cc]
-          } else {
-            g0 += sob_h(a) * sob_hp(b) * sob_h(cc) * val;   // gx = h(D) hp(H) h(W)
-            g1 += sob_h(a) * sob_h(b) * sob_hp(cc) * val;   // gz = h(D) h(H) hp(W)
-          }
-        }
+  if (DIM == 2) {
+    stage_plane(tile[0], e, g, 0, x0, y0);
+    __syncthreads();
+    float a, b;
+    sobel_plane(tile[0], tx, ty, a, b);
+    if (inxy) {
+      const i64 p = (i64)y * g.W + x;
+      const float m = mk ? mk[p] : 1.f;
+      const float a0 = m * b, a1 = m * a;                   // kx = h(H) hp(W) = b,  ky = hp(H) h(W) = a
+      v[0] = a0 * a0 + a1 * a1;
+      r0[p] = m * a0;
+      r1[p] = m * a1;
+    }
+  } else {
+    const int zb = zc * LT_Z, ze = min(g.D, zb + LT_Z);
+    float wa[3] = {0.f, 0.f, 0.f}, wb[3] = {0.f, 0.f, 0.f};
+    for (int pz = zb - 1; pz <= ze; ++pz) {
+      float (*t)[LT_X + 2] = tile[(pz - zb + 1) & 1];
+      stage_plane(t, e, g, pz, x0, y0);
+      __syncthreads();
+      wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
+      sobel_plane(t, tx, ty, wa[2], wb[2]);
+      const int zo = pz - 1;
+      if (zo >= zb && inxy) {
+        const float g0 = wa[0] + 2.f * wa[1] + wa[2];        // gx = h(D) hp(H) h(W)
+        const float g1 = wb[0] + 2.f * wb[1] + wb[2];        // gz = h(D) h(H) hp(W)
+        const i64 p = ((i64)zo * g.H + y) * g.W + x;
+        const float m = mk ? mk[p] : 1.f;
+        const float a0 = m * g0, a1 = m * g1;
+        v[0] += mult0 * a0 * a0 + a1 * a1;
+        r0[p] = mult0 * m * a0;
+        r1[p] = m * a1;
       }
     }
-    const float m = mask ? mask[(i64)n * g.S + p] : 1.f;
-    const float mult0 = (DIM == 3) ? 2.f : 1.f;             // quirk Q10: gx is used for x and y
-    float a0 = m * g0, a1 = m * g1;
-    v[0] = mult0 * a0 * a0 + a1 * a1;
-    i64 rb = (((i64)n * (K - 1) + (c - 1)) * 2) * g.S + p;
-    R[rb] = mult0 * m * a0;
-    R[rb + g.S] = m * a1;
   }
   block_sum<1>(v, red);
   if (threadIdx.x == 0) atomicAdd(acc + 1, (double)v[0]);
+}
+
+// Adjoint of the Sobel correlations: dL/dE_c(q) = sum_k sum_o k[o] R_k(q - o).  h is symmetric and hp
+// antisymmetric, so this is MINUS the same correlation applied to R:  -(gx-stencil(R0) + gz-stencil(R1)).
+// Written to `out` (class c's plane of g_output, finished by loss_grad_kernel).
+template <int DIM>
+__global__ void __launch_bounds__(LT_X * LT_Y)
+loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, float* __restrict__ out) {
+  __shared__ float tile[2][2][LT_Y + 2][LT_X + 2];
+  const int tx = threadIdx.x % LT_X, ty = threadIdx.x / LT_X;
+  const int zc = blockIdx.z % nzc;
+  const int nc = blockIdx.z / nzc;
+  const int n = nc / (K - 1), c = 1 + nc % (K - 1);
+  const int x0 = blockIdx.x * LT_X, y0 = blockIdx.y * LT_Y;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool inxy = x < g.W && y < g.H;
+  const float* r0 = R + (((i64)n * (K - 1) + (c - 1)) * 2) * g.S;
+  const float* r1 = r0 + g.S;
+  float* o = out + ((i64)n * K + c) * g.S;
+  if (DIM == 2) {
+    stage_plane(tile[0][0], r0, g, 0, x0, y0);
+    stage_plane(tile[0][1], r1, g, 0, x0, y0);
+    __syncthreads();
+    float a0, b0, a1, b1;
+    sobel_plane(tile[0][0], tx, ty, a0, b0);
+    sobel_plane(tile[0][1], tx, ty, a1, b1);
+    if (inxy) o[(i64)y * g.W + x] = -(b0 + a1);             // kx-stencil(R0) + ky-stencil(R1)
+  } else {
+    const int zb = zc * LT_Z, ze = min(g.D, zb + LT_Z);
+    float wa[3] = {0.f, 0.f, 0.f}, wb[3] = {0.f, 0.f, 0.f};
+    for (int pz = zb - 1; pz <= ze; ++pz) {
+      const int buf = (pz - zb + 1) & 1;
+      stage_plane(tile[buf][0], r0, g, pz, x0, y0);
+      stage_plane(tile[buf][1], r1, g, pz, x0, y0);
+      __syncthreads();
+      wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
+      float dummy;
+      sobel_plane(tile[buf][0], tx, ty, wa[2], dummy);       // hp(H) h(W) R0
+      sobel_plane(tile[buf][1], tx, ty, dummy, wb[2]);       // h(H) hp(W) R1
+      const int zo = pz - 1;
+      if (zo >= zb && inxy)
+        o[((i64)zo * g.H + y) * g.W + x] = -((wa[0] + 2.f * wa[1] + wa[2]) + (wb[0] + 2.f * wb[1] + wb[2]));
+    }
+  }
 }
 
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont,
@@ -110,58 +198,28 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse
   loss[0] = (float)((double)a_mse * acc[0] + (double)a_cont * acc[1]);
 }
 
+// g_pred_c = 2 A_mse m^2 E_c + 2 A_cont s_c  (s_c = contour adjoint, already in g_out for c >= 1);
 // g_out_c = pred_c (g_pred_c - sum_j g_pred_j pred_j) * upstream
-template <int DIM>
 __global__ void __launch_bounds__(256)
-loss_grad_kernel(Dims g, int K, const float* __restrict__ E, const float* __restrict__ pred,
-                 const float* __restrict__ R, const float* __restrict__ mask, float a_mse, float a_cont,
-                 const float* __restrict__ upstream, float* __restrict__ g_out) {
+loss_grad_kernel(i64 S, int K, const float* __restrict__ E, const float* __restrict__ pred,
+                 const float* __restrict__ mask, float a_mse, float a_cont, const float* __restrict__ upstream,
+                 float* __restrict__ g_out) {
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= g.S) return;
-  const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
-  const float m = mask ? mask[(i64)n * g.S + p] : 1.f;
+  if (p >= S) return;
+  const float m = mask ? mask[(i64)n * S + p] : 1.f;
   const float up = upstream ? upstream[0] : 1.f;
+  const float cm = 2.f * a_mse * m * m, cc = 2.f * a_cont;
   float dot = 0.f;
-  // pass 1: g_pred_c, kept in g_out; pass 2: softmax backward
-  for (int c = 0; c < K; ++c) {
-    i64 q = ((i64)n * K + c) * g.S + p;
-    float gp = 2.f * a_mse * m * m * E[q];
-    if (c >= 1 && a_cont != 0.f) {
-      const float* r0 = R + (((i64)n * (K - 1) + (c - 1)) * 2) * g.S;
-      const float* r1 = r0 + g.S;
-      float s = 0.f;
-      // dL/dE(q) = sum_k sum_o k[o] R_k(q - o): visit source voxel s = q - o
-#pragma unroll
-      for (int a = (DIM == 3 ? -1 : 0); a <= (DIM == 3 ? 1 : 0); ++a) {
-        int zz = z - a;
-        if (zz < 0 || zz >= g.D) continue;
-#pragma unroll
-        for (int b = -1; b <= 1; ++b) {
-          int yy = y - b;
-          if (yy < 0 || yy >= g.H) continue;
-#pragma unroll
-          for (int cc = -1; cc <= 1; ++cc) {
-            int xx = x - cc;
-            if (xx < 0 || xx >= g.W) continue;
-            i64 sidx = ((i64)zz * g.H + yy) * g.W + xx;
-            if (DIM == 2)
-              s += sob_h(b) * sob_hp(cc) * __ldg(r0 + sidx) + sob_hp(b) * sob_h(cc) * __ldg(r1 + sidx);
-            else
-              s += sob_h(a) * sob_hp(b) * sob_h(cc) * __ldg(r0 + sidx) +
-                   sob_h(a) * sob_h(b) * sob_hp(cc) * __ldg(r1 + sidx);
-          }
-        }
-      }
-      gp += 2.f * a_cont * s;
-    }
+  i64 q = (i64)n * K * S + p;
+  for (int c = 0; c < K; ++c, q += S) {
+    float gp = cm * E[q];
+    if (c >= 1 && a_cont != 0.f) gp += cc * g_out[q];
     g_out[q] = gp;
     dot += gp * pred[q];
   }
-  for (int c = 0; c < K; ++c) {
-    i64 q = ((i64)n * K + c) * g.S + p;
-    g_out[q] = up * pred[q] * (g_out[q] - dot);
-  }
+  q = (i64)n * K * S + p;
+  for (int c = 0; c < K; ++c, q += S) g_out[q] = up * pred[q] * (g_out[q] - dot);
 }
 
 }  // namespace advk
@@ -188,6 +246,7 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(K >= 1 && output && reference && scratch && loss, "null pointer / bad K");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 NKS = (i64)g.N * K * g.S;
   double* acc = reinterpret_cast<double*>(scratch);          // scratch must be 8-byte aligned
@@ -200,9 +259,10 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   dim3 grid(blocks_for(g.S, 256), g.N);
   ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, E, pred, acc));
   if (K > 1 && w_contour != 0.f) {
-    dim3 grid2(blocks_for(g.S, 256), 1, g.N * (K - 1));
-    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<2><<<grid2, 256, 0, st>>>(g, K, E, mask, R, acc));
-    else ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<3><<<grid2, 256, 0, st>>>(g, K, E, mask, R, acc));
+    const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
+    dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
+    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<2><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
+    else ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
   }
   ADVK_LAUNCH(K_loss_finalize, st, loss_finalize_kernel<<<1, 1, 0, st>>>(acc, a_mse, a_cont, loss));
   return check_launch("consistency_loss_fwd");
@@ -214,6 +274,7 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(K >= 1 && scratch && g_output, "null pointer / bad K");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   cudaStream_t st = (cudaStream_t)stream;
   const i64 NKS = (i64)g.N * K * g.S;
   const float* E = scratch + 8;
@@ -222,8 +283,13 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   float a_mse, a_cont;
   loss_scales(g, K, gg->d, w_mse, w_contour, a_mse, a_cont);
   if (K <= 1) a_cont = 0.f;
+  if (a_cont != 0.f) {
+    const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
+    dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
+    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<2><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
+    else ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
+  }
   dim3 grid(blocks_for(g.S, 256), g.N);
-  if (gg->d == 2) ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<2><<<grid, 256, 0, st>>>(g, K, E, pred, R, mask, a_mse, a_cont, upstream, g_output));
-  else ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<3><<<grid, 256, 0, st>>>(g, K, E, pred, R, mask, a_mse, a_cont, upstream, g_output));
+  ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, upstream, g_output));
   return check_launch("consistency_loss_bwd");
 }

@@ -164,12 +164,13 @@ init_phi0_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
-  const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
+  int x, y, z;
+  voxel_xyz(g, (unsigned)p, x, y, z);
   float u[3];
   upsample_u<DIM>(c, g, u_lr, n, z, y, x, u);
-  phi0[(i64)n * g.S + p] = V<DIM>::make(base_coord(x, g.W) + u[0] * inv2n,
-                                         base_coord(y, g.H) + u[1] * inv2n,
-                                         (DIM == 3 ? base_coord(z, g.D) + u[2] * inv2n : 0.f));
+  phi0[(i64)n * g.S + p] = V<DIM>::make(base_coord_s(x, g.W, g.stW) + u[0] * inv2n,
+                                         base_coord_s(y, g.H, g.stH) + u[1] * inv2n,
+                                         (DIM == 3 ? base_coord_s(z, g.D, g.stD) + u[2] * inv2n : 0.f));
 }
 
 template <int DIM>
@@ -180,7 +181,8 @@ unorm2_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float* __restr
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   float v[1] = {0.f};
   if (p < g.S) {
-    const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((i64)g.W * g.H));
+    int x, y, z;
+    voxel_xyz(g, (unsigned)p, x, y, z);
     float u[3];
     upsample_u<DIM>(c, g, u_lr, n, z, y, x, u);
     v[0] = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
@@ -196,33 +198,33 @@ __global__ void __launch_bounds__(256)
 ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
   const int n = blockIdx.y;
-  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
   if (p >= g.S) return;
   const T* src = in + (i64)n * g.S;
-  const T f = src[p];
+  const T f = __ldg(src + p);
   Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   Axis az;
   if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
   else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
-  const i64 HW = (i64)g.H * g.W;
+  const int HW = g.H * g.W;
+  const T* c000 = src + (az.i0 * HW + ay.i0 * g.W + ax.i0);     // only dereferenced at in-bounds corners
   float ox = 0.f, oy = 0.f, oz = 0.f;
 #pragma unroll
   for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-    bool vz = dz ? az.v1 : az.v0;
-    float wz = dz ? az.w1 : az.w0;
+    const bool vz = dz ? az.v1 : az.v0;
+    const float wz = dz ? az.w1 : az.w0;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      bool vy = dy ? ay.v1 : ay.v0;
-      float wy = dy ? ay.w1 : ay.w0;
+      const bool vy = dy ? ay.v1 : ay.v0;
+      const float wy = dy ? ay.w1 : ay.w0;
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        bool vx = dx ? ax.v1 : ax.v0;
-        float wx = dx ? ax.w1 : ax.w0;
+        const bool vx = dx ? ax.v1 : ax.v0;
+        const float wx = dx ? ax.w1 : ax.w0;
         if (vx && vy && vz) {
-          i64 q = (i64)(az.i0 + dz) * HW + (i64)(ay.i0 + dy) * g.W + (ax.i0 + dx);
-          T s = __ldg(src + q);
-          float w = wx * wy * wz;
+          const T s = __ldg(c000 + (dz * HW + dy * g.W + dx));
+          const float w = wx * wy * wz;
           ox += s.x * w; oy += s.y * w;
           if (DIM == 3) oz += V<DIM>::z(s) * w;
         }
@@ -279,7 +281,7 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
   typedef typename V<DIM>::T T;
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.y;
-  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
   const bool live = p < g.S;
   const i64 nb = (i64)n * g.S;
   const T* src = phi_prev + nb;
@@ -382,12 +384,12 @@ struct SmoothArgs {
 };
 
 // grid_sample(base, c, border) along one axis: linear interpolation of the linspace.
-__device__ __forceinline__ float compose_axis(float c, int size, float& mult) {
+__device__ __forceinline__ float compose_axis(float c, int size, float step, float& mult) {
   float i = gs_index(c, size, ADVK_PAD_BORDER, mult);
   float f = floorf(i);
   int i0 = (int)f;
-  float v = base_coord(i0, size) * ((f + 1.f) - i);
-  if (i0 + 1 < size) v += base_coord(i0 + 1, size) * (i - f);
+  float v = base_coord_s(i0, size, step) * ((f + 1.f) - i);
+  if (i0 + 1 < size) v += base_coord_s(i0 + 1, size, step) * (i - f);
   return v;
 }
 
@@ -398,12 +400,12 @@ __device__ __forceinline__ void smooth_in(const SmoothArgs<DIM>& a, const Dims& 
   T p = a.A[idx], q = a.B[idx];
   if (MODE == 0) {
     float m;
-    float bx = base_coord(x, g.W), by = base_coord(y, g.H);
-    r[0] = compose_axis((p.x - q.x) + bx, g.W, m) - bx;
-    r[1] = compose_axis((p.y - q.y) + by, g.H, m) - by;
+    float bx = base_coord_s(x, g.W, g.stW), by = base_coord_s(y, g.H, g.stH);
+    r[0] = compose_axis((p.x - q.x) + bx, g.W, g.stW, m) - bx;
+    r[1] = compose_axis((p.y - q.y) + by, g.H, g.stH, m) - by;
     if (DIM == 3) {
-      float bz = base_coord(z, g.D);
-      r[2] = compose_axis((V<DIM>::z(p) - V<DIM>::z(q)) + bz, g.D, m) - bz;
+      float bz = base_coord_s(z, g.D, g.stD);
+      r[2] = compose_axis((V<DIM>::z(p) - V<DIM>::z(q)) + bz, g.D, g.stD, m) - bz;
     } else r[2] = 0.f;
   } else {
     r[0] = (q.x >= -1.f && q.x <= 1.f) ? p.x : 0.f;
@@ -417,14 +419,14 @@ __device__ __forceinline__ void smooth_out(const SmoothArgs<DIM>& a, const Dims&
                                            int y, int x, const float (&s)[3]) {
   typedef typename V<DIM>::T T;
   if (MODE == 0) {
-    a.out[idx] = V<DIM>::make(s[0] + base_coord(x, g.W), s[1] + base_coord(y, g.H),
-                              DIM == 3 ? s[2] + base_coord(z, g.D) : 0.f);
+    a.out[idx] = V<DIM>::make(s[0] + base_coord_s(x, g.W, g.stW), s[1] + base_coord_s(y, g.H, g.stH),
+                              DIM == 3 ? s[2] + base_coord_s(z, g.D, g.stD) : 0.f);
   } else {
     T p = a.C[idx], q = a.D[idx];
     float mx, my, mz = 0.f;
-    gs_index((p.x - q.x) + base_coord(x, g.W), g.W, ADVK_PAD_BORDER, mx);
-    gs_index((p.y - q.y) + base_coord(y, g.H), g.H, ADVK_PAD_BORDER, my);
-    if (DIM == 3) gs_index((V<DIM>::z(p) - V<DIM>::z(q)) + base_coord(z, g.D), g.D, ADVK_PAD_BORDER, mz);
+    gs_index((p.x - q.x) + base_coord_s(x, g.W, g.stW), g.W, ADVK_PAD_BORDER, mx);
+    gs_index((p.y - q.y) + base_coord_s(y, g.H, g.stH), g.H, ADVK_PAD_BORDER, my);
+    if (DIM == 3) gs_index((V<DIM>::z(p) - V<DIM>::z(q)) + base_coord_s(z, g.D, g.stD), g.D, ADVK_PAD_BORDER, mz);
     a.out[idx] = V<DIM>::make(mx != 0.f ? s[0] : 0.f, my != 0.f ? s[1] : 0.f, mz != 0.f ? s[2] : 0.f);
   }
 }
@@ -717,6 +719,7 @@ extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg,
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
   ADVK_REQUIRE(v && u_lr && out_norm2, "null pointer");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   cudaStream_t st = (cudaStream_t)stream;
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   int NC = g.N * gg->d;
@@ -739,6 +742,7 @@ extern "C" int advk_morph_field_fwd(const advk_geom* gg, const advk_morph_cfg* c
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
   ADVK_REQUIRE(v && u_lr && levels && field_out, "null pointer");
+  ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
   cudaStream_t st = (cudaStream_t)stream;
   return gg->d == 2 ? field_fwd<2>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st)
