@@ -42,14 +42,17 @@ struct Stage {
   // data path
   const float* src; float* dst;
   const float* msrc; float* mdst; int binarize;
+  int src_pk, dst_pk;        // channel-packed (float4 per voxel per group of 4 channels) source / destination
   // adjoint
   const float* g_dst; float* g_src; int zero_g_src;
+  float* g_src_user;         // packed mode, first stage: planar user buffer the packed g_src is unpacked into
   float* g_delta; float* g_up; void* g_phi; float* g_theta;
 };
 
 struct Program {
   Dims g; int C; int n; int first_bwd;
   int do_clamp; float lo, hi; int want_mask;
+  int pack;         // 0 planar intermediates; 4: intermediates and scatter targets channel-packed
   int tps;          // tiles per sample
   FastDiv ftps;
   int interleave;   // 0: block owns a contiguous tile range; 1: tiles dealt round-robin
@@ -230,30 +233,100 @@ __device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
   }
 }
 
+// ---- channel-packed variants (C % 4 == 0, warp stages only: the K-class prediction path) -----------
+// Intermediates are stored as one float4 per voxel per group of 4 channels, so a corner is ONE 16-byte
+// gather / ONE vector RED for 4 channels instead of 4 scalar ones; only the user-facing tensors (chain
+// input, output, their gradients) stay planar N x C x S.
+__device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
+  return make_float4(acc.x + a.x * w, acc.y + a.y * w, acc.z + a.z * w, acc.w + a.w * w);
+}
+
 template <int DIM>
+__device__ __forceinline__ float4 load_corner4(const Stage& s, bool packed, const float* __restrict__ base, i64 S,
+                                               int off, float pv) {
+  float4 v;
+  if (packed) v = __ldg(reinterpret_cast<const float4*>(base) + off);
+  else v = make_float4(__ldg(base + off), __ldg(base + S + off), __ldg(base + 2 * S + off), __ldg(base + 3 * S + off));
+  return make_float4(v.x - pv, v.y - pv, v.z - pv, v.w - pv);
+}
+
+template <int DIM, bool FIELD>
+__device__ void stage_warp_fwd_pk(const Program& P, const Stage& s, bool last) {
+  const Dims& g = P.g;
+  unsigned t0, t1, dt;
+  tile_range(P, t0, t1, dt);
+  const bool clamp = last && P.do_clamp;
+  const int CG = P.C >> 2;
+  for (unsigned t = t0; t < t1; t += dt) {
+    Vox v = tile_voxel(P, t);
+    if (!v.ok) continue;
+    float cx, cy, cz, rx, ry, rz, bx, by, bz;
+    stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Corners<DIM> ct;
+    make_corners<DIM>(st, g, true, ct);
+    const float pv = s.pv ? s.pv[v.n] : 0.f;
+    for (int cg = 0; cg < CG; ++cg) {
+      // group base: packed = float4 index (n*CG+cg)*S, planar = channel (n*C + 4cg)
+      const float* base = s.src_pk ? s.src + 4 * ((i64)v.n * CG + cg) * g.S : s.src + ((i64)v.n * P.C + 4 * cg) * g.S;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < Corners<DIM>::NC; ++k)
+        if (ct.mask & (1u << k)) acc = f4_fma(load_corner4<DIM>(s, s.src_pk, base, g.S, ct.off[k], pv), ct.w[k], acc);
+      float4 val = make_float4(acc.x + pv, acc.y + pv, acc.z + pv, acc.w + pv);
+      if (clamp) val = make_float4(clampf(val.x, P.lo, P.hi), clampf(val.y, P.lo, P.hi), clampf(val.z, P.lo, P.hi), clampf(val.w, P.lo, P.hi));
+      if (s.dst_pk) {
+        reinterpret_cast<float4*>(s.dst)[((i64)v.n * CG + cg) * g.S + v.p] = val;
+      } else {
+        float* d = s.dst + ((i64)v.n * P.C + 4 * cg) * g.S + v.p;
+        d[0] = val.x; d[g.S] = val.y; d[2 * g.S] = val.z; d[3 * g.S] = val.w;
+      }
+    }
+    if (s.mdst) {
+      float m;
+      if (s.msrc) m = gather_corners<DIM>(ct, s.msrc + (i64)v.n * g.S, pv);
+      else {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < Corners<DIM>::NC; ++k)
+          if (ct.mask & (1u << k)) acc += (1.f - pv) * ct.w[k];
+        m = acc + pv;
+      }
+      if (s.binarize) m = (m != 0.f) ? 1.f : 0.f;
+      s.mdst[(i64)v.n * g.S + v.p] = m;
+    }
+  }
+}
+
+template <int DIM, bool PK>
 __device__ __forceinline__ void run_stage_fwd(const Program& P, int k) {
   const Stage& s = P.st[k];
   const bool last = (k == P.n - 1);
+  if (PK) {
+    if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_fwd_pk<DIM, true>(P, s, last);
+    else stage_warp_fwd_pk<DIM, false>(P, s, last);
+    return;
+  }
   if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_fwd<DIM>(P, s, last);
   else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_fwd<DIM, true>(P, s, last);
   else stage_warp_fwd<DIM, false>(P, s, last);
 }
 
-template <int DIM, int MINB>
+template <int DIM, int MINB, bool PK>
 __global__ void __launch_bounds__(CT, MINB)
 chain_fwd_kernel(const __grid_constant__ Program P) {
   cg::grid_group grid = cg::this_grid();
   for (int k = 0; k < P.n; ++k) {
     if (k) grid.sync();
-    run_stage_fwd<DIM>(P, k);
+    run_stage_fwd<DIM, PK>(P, k);
   }
 }
 
 // one stage per launch (used when a cooperative launch is not possible / for A-B timing)
-template <int DIM, int MINB>
+template <int DIM, int MINB, bool PK>
 __global__ void __launch_bounds__(CT, MINB)
 chain_fwd_stage_kernel(const __grid_constant__ Program P, int k) {
-  run_stage_fwd<DIM>(P, k);
+  run_stage_fwd<DIM, PK>(P, k);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -436,16 +509,178 @@ __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, floa
   }
 }
 
-template <int DIM>
+template <int DIM, bool FIELD>
+__device__ void stage_warp_bwd_pk(const Program& P, const Stage& s, bool last, float* red) {
+  constexpr int NG = DIM * (DIM + 1);
+  constexpr int NC = Corners<DIM>::NC;
+  constexpr int NR = NC / 2;
+  const unsigned FULL = 0xffffffffu;
+  const Dims& g = P.g;
+  const int lane = threadIdx.x & 31;
+  const int CG = P.C >> 2;
+  unsigned t0, t1, dt;
+  tile_range(P, t0, t1, dt);
+  const bool clamp = last && P.do_clamp;
+  const bool want_theta = !FIELD && s.g_theta != nullptr;
+  const bool gd_pk = !last;                       // upstream of the last stage is the user's planar g_out
+  float acc[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) acc[i] = 0.f;
+  int cur_n = -1;
+  for (unsigned t = t0; t < t1; t += dt) {
+    Vox v = tile_voxel(P, t);
+    if (want_theta && v.n != cur_n) {            // block-uniform
+      if (cur_n >= 0) {
+        block_sum<NG>(acc, red);
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int i = 0; i < NG; ++i) atomicAdd(s.g_theta + cur_n * NG + i, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NG; ++i) acc[i] = 0.f;
+      }
+      cur_n = v.n;
+    }
+    float cx, cy, cz, rx, ry, rz, bx, by, bz;
+    stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Corners<DIM> ct;
+    make_corners<DIM>(st, g, v.ok, ct);
+    const float pv = s.pv ? s.pv[v.n] : 0.f;
+    const bool scatter = s.g_src != nullptr;
+    unsigned hand = 0u;
+    if (scatter) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int k0 = 2 * r, k1 = k0 + 1;
+        const int a0_next = __shfl_down_sync(FULL, (ct.mask & (1u << k0)) ? ct.off[k0] : -1, 1);
+        if ((ct.mask & (1u << k1)) && lane < 31 && a0_next == ct.off[k1]) hand |= 1u << r;
+      }
+    }
+    float tk[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) tk[k] = 0.f;
+    for (int cg = 0; cg < CG; ++cg) {
+      const float* base = s.src_pk ? s.src + 4 * ((i64)v.n * CG + cg) * g.S : s.src + ((i64)v.n * P.C + 4 * cg) * g.S;
+      float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v.ok) {
+        if (gd_pk) go = reinterpret_cast<const float4*>(s.g_dst)[((i64)v.n * CG + cg) * g.S + v.p];
+        else {
+          const float* gd = s.g_dst + ((i64)v.n * P.C + 4 * cg) * g.S + v.p;
+          go = make_float4(gd[0], gd[g.S], gd[2 * g.S], gd[3 * g.S]);
+        }
+      }
+      if (clamp) {                                 // last stage of an image chain with C % 4 == 0 (rare)
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+          if (ct.mask & (1u << k)) a = f4_fma(load_corner4<DIM>(s, s.src_pk, base, g.S, ct.off[k], pv), ct.w[k], a);
+        if (!(a.x + pv >= P.lo && a.x + pv <= P.hi)) go.x = 0.f;
+        if (!(a.y + pv >= P.lo && a.y + pv <= P.hi)) go.y = 0.f;
+        if (!(a.z + pv >= P.lo && a.z + pv <= P.hi)) go.z = 0.f;
+        if (!(a.w + pv >= P.lo && a.w + pv <= P.hi)) go.w = 0.f;
+      }
+      float4* gs = scatter ? reinterpret_cast<float4*>(s.g_src) + ((i64)v.n * CG + cg) * g.S : nullptr;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int k0 = 2 * r, k1 = k0 + 1;
+        const bool m0 = ct.mask & (1u << k0), m1 = ct.mask & (1u << k1);
+        if (m0) {
+          const float4 a = load_corner4<DIM>(s, s.src_pk, base, g.S, ct.off[k0], pv);
+          tk[k0] += a.x * go.x + a.y * go.y + a.z * go.z + a.w * go.w;
+        }
+        if (m1) {
+          const float4 a = load_corner4<DIM>(s, s.src_pk, base, g.S, ct.off[k1], pv);
+          tk[k1] += a.x * go.x + a.y * go.y + a.z * go.z + a.w * go.w;
+        }
+        if (scatter) {
+          const bool h = (hand >> r) & 1u;
+          const float w0 = ct.w[k0], w1 = ct.w[k1];
+          float4 c0 = make_float4(go.x * w0, go.y * w0, go.z * w0, go.w * w0);
+          const float4 c1 = make_float4(go.x * w1, go.y * w1, go.z * w1, go.w * w1);
+          const float r0 = __shfl_up_sync(FULL, h ? c1.x : 0.f, 1);
+          const float r1 = __shfl_up_sync(FULL, h ? c1.y : 0.f, 1);
+          const float r2 = __shfl_up_sync(FULL, h ? c1.z : 0.f, 1);
+          const float r3 = __shfl_up_sync(FULL, h ? c1.w : 0.f, 1);
+          if (lane > 0) { c0.x += r0; c0.y += r1; c0.z += r2; c0.w += r3; }
+          if (m0) atomicAdd(gs + ct.off[k0], c0);
+          if (m1 && !h) atomicAdd(gs + ct.off[k1], c1);
+        }
+      }
+    }
+    if (!v.ok) continue;
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const float wx = dx ? st.x.w1 : st.x.w0, wy = dy ? st.y.w1 : st.y.w0, wz = dz ? st.z.w1 : st.z.w0;
+      ggx += (dx ? tk[k] : -tk[k]) * (wy * wz);
+      ggy += (dy ? tk[k] : -tk[k]) * (wx * wz);
+      if (DIM == 3) ggz += (dz ? tk[k] : -tk[k]) * (wx * wy);
+    }
+    ggx *= st.x.mult; ggy *= st.y.mult; ggz *= st.z.mult;
+    if (FIELD) {
+      if (s.g_phi) {
+        if (!(rx >= -1.f && rx <= 1.f)) ggx = 0.f;
+        if (!(ry >= -1.f && ry <= 1.f)) ggy = 0.f;
+        if (DIM == 2) {
+          reinterpret_cast<float2*>(s.g_phi)[(i64)v.n * g.S + v.p] = make_float2(ggx, ggy);
+        } else {
+          if (!(rz >= -1.f && rz <= 1.f)) ggz = 0.f;
+          reinterpret_cast<float4*>(s.g_phi)[(i64)v.n * g.S + v.p] = make_float4(ggx, ggy, ggz, 0.f);
+        }
+      }
+    } else if (want_theta) {
+      if (DIM == 2) {
+        acc[0] += ggx * bx; acc[1] += ggx * by; acc[2] += ggx;
+        acc[3] += ggy * bx; acc[4] += ggy * by; acc[5] += ggy;
+      } else {
+        acc[0] += ggx * bx; acc[1] += ggx * by; acc[2] += ggx * bz; acc[3] += ggx;
+        acc[4] += ggy * bx; acc[5] += ggy * by; acc[6] += ggy * bz; acc[7] += ggy;
+        acc[8] += ggz * bx; acc[9] += ggz * by; acc[10] += ggz * bz; acc[11] += ggz;
+      }
+    }
+  }
+  if (want_theta && cur_n >= 0) {
+    block_sum<NG>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NG; ++i) atomicAdd(s.g_theta + cur_n * NG + i, acc[i]);
+    }
+  }
+}
+
+// packed g_src of the first stage -> the user's planar N x C x S gradient
+__device__ void unpack_g_src(const Program& P) {
+  const Stage& s = P.st[P.first_bwd];
+  if (!P.pack || !s.g_src_user || !s.g_src) return;
+  const Dims& g = P.g;
+  const int CG = P.C >> 2;
+  const i64 tot = (i64)g.N * CG * g.S;
+  const float4* src = reinterpret_cast<const float4*>(s.g_src);
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (i64)gridDim.x * blockDim.x) {
+    const i64 ng = i / g.S, p = i - ng * g.S;       // one 64-bit divide per element of a streaming pass
+    const float4 v = src[i];
+    float* d = s.g_src_user + (ng * 4) * g.S + p;    // channel (n*C + 4cg) = 4*(n*CG+cg)
+    d[0] = v.x; d[g.S] = v.y; d[2 * g.S] = v.z; d[3 * g.S] = v.w;
+  }
+}
+
+template <int DIM, bool PK>
 __device__ __forceinline__ void run_stage_bwd(const Program& P, int k, float* red) {
   const Stage& s = P.st[k];
   const bool last = (k == P.n - 1);
+  if (PK) {
+    if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_bwd_pk<DIM, true>(P, s, last, red);
+    else stage_warp_bwd_pk<DIM, false>(P, s, last, red);
+    return;
+  }
   if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_bwd<DIM>(P, s, last);
   else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_bwd<DIM, true>(P, s, last, red);
   else stage_warp_bwd<DIM, false>(P, s, last, red);
 }
 
-template <int DIM, int MINB>
+template <int DIM, int MINB, bool PK>
 __global__ void __launch_bounds__(CT, MINB)
 chain_bwd_kernel(const __grid_constant__ Program P) {
   __shared__ float red[12 * 32];
@@ -453,21 +688,35 @@ chain_bwd_kernel(const __grid_constant__ Program P) {
   zero_buffers(P);
   for (int k = P.n - 1; k >= P.first_bwd; --k) {
     grid.sync();
-    run_stage_bwd<DIM>(P, k, red);
+    run_stage_bwd<DIM, PK>(P, k, red);
+  }
+  if (PK && P.st[P.first_bwd].g_src_user) {
+    grid.sync();
+    unpack_g_src(P);
   }
 }
 
-template <int DIM, int MINB>
+template <int DIM, int MINB, bool PK>
 __global__ void __launch_bounds__(CT, MINB)
 chain_bwd_stage_kernel(const __grid_constant__ Program P, int k) {
   __shared__ float red[12 * 32];
-  if (k < 0) zero_buffers(P);
-  else run_stage_bwd<DIM>(P, k, red);
+  if (k == -1) zero_buffers(P);
+  else if (k == -2) unpack_g_src(P);
+  else run_stage_bwd<DIM, PK>(P, k, red);
 }
 
 // ------------------------------------------------------------------------------------ host
 
 static int g_coop = -1;   // -1: decide on first use
+static int g_pack = -1;
+
+static bool pack_enabled() {
+  if (g_pack < 0) {
+    const char* e = getenv("ADVK_CHAIN_PACK");
+    g_pack = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pack == 1;
+}
 
 static bool coop_enabled() {
   int& v = g_coop;
@@ -508,8 +757,12 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
   if (P.n_tiles >= 0x7fffffffLL) return false;
   const i64 ncs = slot_floats((i64)P.g.N * P.C * P.g.S), ns = slot_floats((i64)P.g.N * P.g.S);
   int last_warp = -1;
-  for (int k = 0; k < P.n; ++k)
+  bool all_warps = true;
+  for (int k = 0; k < P.n; ++k) {
     if (d->stages[k].kind != ADVK_STAGE_INTENSITY) last_warp = k;
+    else all_warps = false;
+  }
+  P.pack = (pack_enabled() && all_warps && P.n >= 2 && (P.C % 4) == 0) ? 4 : 0;
   float* mstash = stash ? stash + (i64)(P.n - 1) * ncs : nullptr;
   const float* cur = src;
   const float* mcur = mask_src;
@@ -539,6 +792,8 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
       s.pad = a.pad_mode; s.interp = a.interp; s.pv = a.pad_values;
     }
     s.src = cur;
+    s.src_pk = (P.pack && k > 0) ? 1 : 0;
+    s.dst_pk = (P.pack && k < P.n - 1) ? 1 : 0;
     if (k == P.n - 1) s.dst = out;
     else {
       if (!stash) return false;
@@ -578,37 +833,47 @@ static void tune_defaults() {
   }
 }
 
-template <int DIM, int MINB>
-static int launch_fwd_t(Program& P, cudaStream_t st) {
+template <int DIM, int MINB, bool PK>
+static int launch_fwd_p(Program& P, cudaStream_t st) {
   if (coop_enabled() && P.n > 1) {
-    static int gmax = coop_grid(chain_fwd_kernel<DIM, MINB>);
+    static int gmax = coop_grid(chain_fwd_kernel<DIM, MINB, PK>);
     int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
     void* args[] = {(void*)&P};
     ADVK_LAUNCH(K_chain_fwd, st,
-                cudaLaunchCooperativeKernel((void*)chain_fwd_kernel<DIM, MINB>, dim3(grid), dim3(CT), args, 0, st));
+                cudaLaunchCooperativeKernel((void*)chain_fwd_kernel<DIM, MINB, PK>, dim3(grid), dim3(CT), args, 0, st));
   } else {
     int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
     for (int k = 0; k < P.n; ++k)
-      ADVK_LAUNCH(K_chain_fwd_stage, st, chain_fwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, k));
+      ADVK_LAUNCH(K_chain_fwd_stage, st, (chain_fwd_stage_kernel<DIM, MINB, PK><<<grid, CT, 0, st>>>(P, k)));
   }
   return check_launch("chain_apply_fwd");
 }
-
 template <int DIM, int MINB>
-static int launch_bwd_t(Program& P, cudaStream_t st) {
+static int launch_fwd_t(Program& P, cudaStream_t st) {
+  return P.pack ? launch_fwd_p<DIM, MINB, true>(P, st) : launch_fwd_p<DIM, MINB, false>(P, st);
+}
+
+template <int DIM, int MINB, bool PK>
+static int launch_bwd_p(Program& P, cudaStream_t st) {
   if (coop_enabled()) {
-    static int gmax = coop_grid(chain_bwd_kernel<DIM, MINB>);
+    static int gmax = coop_grid(chain_bwd_kernel<DIM, MINB, PK>);
     int grid = (int)(P.n_tiles < gmax ? P.n_tiles : gmax);
     void* args[] = {(void*)&P};
     ADVK_LAUNCH(K_chain_bwd, st,
-                cudaLaunchCooperativeKernel((void*)chain_bwd_kernel<DIM, MINB>, dim3(grid), dim3(CT), args, 0, st));
+                cudaLaunchCooperativeKernel((void*)chain_bwd_kernel<DIM, MINB, PK>, dim3(grid), dim3(CT), args, 0, st));
   } else {
     int grid = (int)(P.n_tiles < 148 * 16 ? P.n_tiles : 148 * 16);
-    ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, -1));
+    ADVK_LAUNCH(K_chain_bwd_stage, st, (chain_bwd_stage_kernel<DIM, MINB, PK><<<grid, CT, 0, st>>>(P, -1)));
     for (int k = P.n - 1; k >= P.first_bwd; --k)
-      ADVK_LAUNCH(K_chain_bwd_stage, st, chain_bwd_stage_kernel<DIM, MINB><<<grid, CT, 0, st>>>(P, k));
+      ADVK_LAUNCH(K_chain_bwd_stage, st, (chain_bwd_stage_kernel<DIM, MINB, PK><<<grid, CT, 0, st>>>(P, k)));
+    if (PK && P.st[P.first_bwd].g_src_user)
+      ADVK_LAUNCH(K_chain_bwd_stage, st, (chain_bwd_stage_kernel<DIM, MINB, PK><<<grid, CT, 0, st>>>(P, -2)));
   }
   return check_launch("chain_apply_bwd");
+}
+template <int DIM, int MINB>
+static int launch_bwd_t(Program& P, cudaStream_t st) {
+  return P.pack ? launch_bwd_p<DIM, MINB, true>(P, st) : launch_bwd_p<DIM, MINB, false>(P, st);
 }
 
 template <int DIM>
@@ -653,6 +918,12 @@ extern "C" int advk_chain_tune(int min_blocks_per_sm, int interleave) {
   return (g_minb * 10 + g_minb_bwd) * 10 + g_interleave;
 }
 
+extern "C" int advk_chain_set_packed(int enable) {
+  int prev = pack_enabled() ? 1 : 0;
+  g_pack = enable ? 1 : 0;
+  return prev;
+}
+
 extern "C" int advk_chain_set_cooperative(int enable) {
   int prev = coop_enabled() ? 1 : 0;
   if (enable) {
@@ -675,7 +946,8 @@ extern "C" int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* sta
     if (d->stages[k].kind != ADVK_STAGE_INTENSITY) ++warps;
   if (stash_floats)
     *stash_floats = (size_t)((i64)(d->n_stages - 1) * ncs + ((d->want_mask && warps > 1) ? (i64)(warps - 1) * ns : 0));
-  if (scratch_floats) *scratch_floats = (size_t)((i64)(d->n_stages - 1) * ncs);
+  // one slot per stage boundary, plus one for the packed gradient of the chain input (packed mode)
+  if (scratch_floats) *scratch_floats = (size_t)((i64)d->n_stages * ncs);
   return ADVK_OK;
 }
 
@@ -710,11 +982,14 @@ extern "C" int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out
   if (g_src) first = 0;
   if (first == P.n) return ADVK_OK;       // nothing requested
   P.first_bwd = first;
-  if (first < P.n - 1 || (first > 0 && false)) ADVK_REQUIRE(scratch != nullptr, "scratch is NULL");
+  if (first < P.n - 1 || (P.pack && g_src)) ADVK_REQUIRE(scratch != nullptr, "scratch is NULL");
   for (int k = P.n - 1; k >= first; --k) {
     Stage& s = P.st[k];
     s.g_dst = (k == P.n - 1) ? g_out : scratch + (i64)k * slot;
-    if (k == 0) s.g_src = g_src;                  // may be NULL: gradient w.r.t. the chain input not wanted
+    if (k == 0) {                                 // g_src may be NULL: gradient w.r.t. the chain input not wanted
+      if (P.pack && g_src) { s.g_src = scratch + (i64)(P.n - 1) * slot; s.g_src_user = g_src; }
+      else s.g_src = g_src;
+    }
     else if (k == first) s.g_src = nullptr;       // nobody consumes it
     else s.g_src = scratch + (i64)(k - 1) * slot;
     s.zero_g_src = (s.kind != ADVK_STAGE_INTENSITY && s.g_src != nullptr) ? 1 : 0;

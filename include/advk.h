@@ -277,6 +277,11 @@ typedef struct advk_chain_desc {
  * environment variable ADVK_CHAIN_COOP is not "0"); 0: one plain launch per stage.  Returns the
  * previous setting.  Results are identical; exists for A/B timing. */
 int advk_chain_set_cooperative(int enable);
+/* 1 (default; environment ADVK_CHAIN_PACK): chains made of warp stages only with C % 4 == 0 (the
+ * K-class prediction path) keep their intermediates and scatter targets channel-packed, one float4
+ * per voxel per 4 channels; 0: planar everywhere.  Returns the previous setting.  Results agree up
+ * to fp32 summation order. */
+int advk_chain_set_packed(int enable);
 /* Tuning (A/B timing): resident blocks per SM the chain kernels are compiled for (2, 3, 4 or 6 =
  * register cap 128/80/64/40; one digit sets forward and backward, two digits "FB" set them
  * separately, e.g. 43; other values keep the current ones; defaults 4 / 3) and tile assignment

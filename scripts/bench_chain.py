@@ -45,9 +45,10 @@ def measure(tag):
     print("%-28s %s" % (tag, " | ".join(out)), flush=True)
 
 
-for coop in (1, 0):
-    lib.advk_chain_set_cooperative(coop)
-    for minb in ((43, 42, 44, 33, 32, 63) if coop else (43,)):
-        for il in (1,):
-            lib.advk_chain_tune(minb, il)
-            measure("coop=%d minb(fwd,bwd)=%d interleave=%d" % (coop, minb, il))
+for pack in (1, 0):
+    lib.advk_chain_set_packed(pack)
+    for coop in (1, 0):
+        lib.advk_chain_set_cooperative(coop)
+        for minb in ((43, 42, 44, 33) if coop else (43,)):
+            lib.advk_chain_tune(minb, 1)
+            measure("pack=%d coop=%d minb(fwd,bwd)=%d" % (pack, coop, minb))

@@ -367,15 +367,16 @@ def _chain_solver(d, size, chain, pad, interp, fused):
 
 @pytest.mark.parametrize("d,size,chain,pad,interp", CHAINS)
 @pytest.mark.parametrize("coop", [1, 0])
-def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, coop):
+@pytest.mark.parametrize("k", [3, 4, 8])
+def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, coop, k):
     """The fused executor (advk_chain_apply_*) against the per-transform kernels on the same
     parameters: image chain + clamp, prediction warp-back, valid-region mask, and every parameter
-    gradient -- for arbitrary stage orders, paddings and interpolation modes."""
+    gradient -- for arbitrary stage orders, paddings and interpolation modes.  k = 4 and 8 classes
+    take the channel-packed prediction path (float4 intermediates), k = 3 the planar one."""
     from advchain_b200 import _lib
     lib = _lib.load()
     prev = lib.advk_chain_set_cooperative(coop)
     try:
-        k = 3
         torch.manual_seed(11)
         data = torch.rand(*size).to(_dev())
         gpred = torch.randn(size[0], k, *size[2:]).to(_dev())
