@@ -171,7 +171,7 @@ class MorphField(Function):
         spatial = tuple(size[2:])
         nvox = g.N * g.D * g.H * g.W
         u_lr = torch.empty_like(v)
-        levels = torch.empty((nb_steps + 1) * nvox * lanes, dtype=torch.float32, device=v.device)
+        levels = torch.empty((nb_steps + 2) * nvox * lanes, dtype=torch.float32, device=v.device)
         field = torch.empty((g.N,) + spatial + (lanes,), dtype=torch.float32, device=v.device)
         call("advk_morph_field_fwd", C.byref(g), C.byref(cfg), ptr(v), float(scale), nb_steps,
              ptr(u_lr), ptr(levels), ptr(field), stream())

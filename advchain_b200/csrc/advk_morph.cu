@@ -469,79 +469,118 @@ smooth2d_kernel(Dims g, SmoothArgs<2> a) {
   }
 }
 
-// 3-D: (x,y) tile per CTA, marching along z with a 9-plane register ring per thread.
-constexpr int S3_TX = 32, S3_TY = 16, S3_THREADS = S3_TX * S3_TY;
+// 3-D: two launches.
+//   smooth3d_xy: one CTA per 64 x 16 tile of ONE z-plane: input map (compose-with-base | clamp mask)
+//     on tile + 4-voxel halo into shared memory, x pass and y pass with register windows (every
+//     thread produces 4 consecutive outputs from 12 inputs: 3 LDS.128 per 36 FMA), result t -> `tmp`.
+//   smooth3d_z: one thread per (x,y) column and 16-plane chunk, 9-plane register ring (fully unrolled),
+//     output map (re-add base | border mask) fused.
+// The previous single kernel (xy tile marching in z) staged every plane 1.5 x 1.9 times through the
+// 90-instruction input map and issued 960 warp instructions per 32 voxels (profiles/r01p); this
+// split needs ~300 and exposes D times more CTAs.
+constexpr int SX_TX = 64, SX_TY = 16, SX_THREADS = 256;
+constexpr int SX_IW = SX_TX + 2 * KR, SX_IH = SX_TY + 2 * KR;
+constexpr int SZ_CHUNK = 16;
 
 template <int MODE>
-__global__ void __launch_bounds__(S3_THREADS)
-smooth3d_kernel(Dims g, SmoothArgs<3> a, int zchunk, int nzc) {
-  constexpr int IW = S3_TX + 2 * KR, IH = S3_TY + 2 * KR;
-  __shared__ float s_in[3][IH][IW];
-  __shared__ float s_tmp[3][IH][S3_TX];
-  const int n = blockIdx.z / nzc;
-  const int zc = blockIdx.z % nzc;
-  const int x0 = blockIdx.x * S3_TX, y0 = blockIdx.y * S3_TY;
-  const int zb = zc * zchunk;
-  const int ze = min(g.D, zb + zchunk);
-  const int tx = threadIdx.x % S3_TX, ty = threadIdx.x / S3_TX;
+__global__ void __launch_bounds__(SX_THREADS)
+smooth3d_xy_kernel(Dims g, SmoothArgs<3> a, float4* __restrict__ tmp) {
+  __shared__ __align__(16) float s_in[3][SX_IH][SX_IW];
+  __shared__ __align__(16) float s_tmp[3][SX_IH][SX_TX];
+  const int z = blockIdx.z % g.D, n = blockIdx.z / g.D;
+  const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
+  const i64 pb = (i64)n * g.S + (i64)z * g.H * g.W;
+  for (int i = threadIdx.x; i < SX_IW * SX_IH; i += SX_THREADS) {
+    const int ly = i / SX_IW, lx = i - ly * SX_IW;
+    const int gy = y0 + ly - KR, gx = x0 + lx - KR;
+    float r[3] = {0.f, 0.f, 0.f};
+    if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) smooth_in<3, MODE>(a, g, pb + (i64)gy * g.W + gx, z, gy, gx, r);
+    s_in[0][ly][lx] = r[0]; s_in[1][ly][lx] = r[1]; s_in[2][ly][lx] = r[2];
+  }
+  __syncthreads();
+  float w[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) w[k] = a.w[k];
+  // x pass: task = (component, row, run of 4 outputs)
+  constexpr int RUNS = SX_TX / 4;
+  for (int task = threadIdx.x; task < 3 * SX_IH * RUNS; task += SX_THREADS) {
+    const int c = task / (SX_IH * RUNS);
+    const int rem = task - c * (SX_IH * RUNS);
+    const int ly = rem / RUNS, xs = (rem - ly * RUNS) * 4;
+    const float4 i0 = *reinterpret_cast<const float4*>(&s_in[c][ly][xs]);
+    const float4 i1 = *reinterpret_cast<const float4*>(&s_in[c][ly][xs + 4]);
+    const float4 i2 = *reinterpret_cast<const float4*>(&s_in[c][ly][xs + 8]);
+    const float in[12] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += w[k] * in[j + k];
+    }
+    *reinterpret_cast<float4*>(&s_tmp[c][ly][xs]) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  // y pass: thread = (x, group of 4 rows), all three components
+  const int tx = threadIdx.x % SX_TX, yg = threadIdx.x / SX_TX;
+  float o[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float in[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) in[i] = s_tmp[c][yg * 4 + i][tx];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) acc += w[k] * in[j + k];
+      o[c][j] = acc;
+    }
+  }
+  const int gx = x0 + tx;
+  if (gx < g.W) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gy = y0 + yg * 4 + j;
+      if (gy < g.H) tmp[pb + (i64)gy * g.W + gx] = make_float4(o[0][j], o[1][j], o[2][j], 0.f);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+smooth3d_z_kernel(Dims g, SmoothArgs<3> a, const float4* __restrict__ tmp, int nzc) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z / nzc, zb = (blockIdx.z % nzc) * SZ_CHUNK;
+  if (x >= g.W || y >= g.H) return;
   const i64 HW = (i64)g.H * g.W;
-  float ring[3][KT];
+  const i64 col = (i64)n * g.S + (i64)y * g.W + x;
+  float w[KT];
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+  for (int k = 0; k < KT; ++k) w[k] = a.w[k];
+  float rx[KT], ry[KT], rz[KT];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) ring[c][k] = 0.f;
-  for (int pz = zb - KR; pz < ze + KR; ++pz) {
-    float v[3] = {0.f, 0.f, 0.f};
-    if (pz >= 0 && pz < g.D) {   // block-uniform
-      for (int i = threadIdx.x; i < IW * IH; i += S3_THREADS) {
-        int ly = i / IW, lx = i % IW;
-        int gy = y0 + ly - KR, gx = x0 + lx - KR;
-        float r[3] = {0.f, 0.f, 0.f};
-        if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
-          smooth_in<3, MODE>(a, g, (i64)n * g.S + (i64)pz * HW + (i64)gy * g.W + gx, pz, gy, gx, r);
-        s_in[0][ly][lx] = r[0]; s_in[1][ly][lx] = r[1]; s_in[2][ly][lx] = r[2];
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < S3_TX * IH; i += S3_THREADS) {
-        int ly = i / S3_TX, lx = i % S3_TX;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = 0; k < KT; ++k) rx[k] = ry[k] = rz[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          float w = a.w[k];
-          a0 += w * s_in[0][ly][lx + k]; a1 += w * s_in[1][ly][lx + k]; a2 += w * s_in[2][ly][lx + k];
-        }
-        s_tmp[0][ly][lx] = a0; s_tmp[1][ly][lx] = a1; s_tmp[2][ly][lx] = a2;
-      }
-      __syncthreads();
+  for (int i = 0; i < SZ_CHUNK + 2 * KR; ++i) {
+    const int pz = zb - KR + i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pz >= 0 && pz < g.D) v = __ldg(tmp + col + (i64)pz * HW);
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        float w = a.w[k];
-        v[0] += w * s_tmp[0][ty + k][tx]; v[1] += w * s_tmp[1][ty + k][tx]; v[2] += w * s_tmp[2][ty + k][tx];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-#pragma unroll
-      for (int k = 0; k < KT - 1; ++k) ring[c][k] = ring[c][k + 1];
-      ring[c][KT - 1] = v[c];
-    }
+    for (int k = 0; k < KT - 1; ++k) { rx[k] = rx[k + 1]; ry[k] = ry[k + 1]; rz[k] = rz[k + 1]; }
+    rx[KT - 1] = v.x; ry[KT - 1] = v.y; rz[KT - 1] = v.z;
     const int zo = pz - KR;
-    const int gy = y0 + ty, gx = x0 + tx;
-    if (zo >= zb && zo < ze && gy < g.H && gx < g.W) {
+    if (i >= 2 * KR && zo < g.D) {
       float s[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        float w = a.w[k];
-        s[0] += w * ring[0][k]; s[1] += w * ring[1][k]; s[2] += w * ring[2][k];
-      }
-      smooth_out<3, MODE>(a, g, (i64)n * g.S + (i64)zo * HW + (i64)gy * g.W + gx, zo, gy, gx, s);
+      for (int k = 0; k < KT; ++k) { s[0] += w[k] * rx[k]; s[1] += w[k] * ry[k]; s[2] += w[k] * rz[k]; }
+      smooth_out<3, MODE>(a, g, col + (i64)zo * HW, zo, y, x, s);
     }
   }
 }
 
 template <int DIM, int MODE>
 static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const void* B, const void* C,
-                          const void* D, void* out, cudaStream_t st) {
+                          const void* D, void* out, void* tmp, cudaStream_t st) {
   typedef typename V<DIM>::T T;
   SmoothArgs<DIM> a;
   a.A = (const T*)A; a.B = (const T*)B; a.C = (const T*)C; a.D = (const T*)D; a.out = (T*)out;
@@ -550,10 +589,12 @@ static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const
     dim3 grid((g.W + S2_TX - 1) / S2_TX, (g.H + S2_TY - 1) / S2_TY, g.N);
     ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth2d_kernel<MODE><<<grid, S2_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<2>*>(&a)));
   } else {
-    int zchunk = 16;
-    int nzc = (g.D + zchunk - 1) / zchunk;
-    dim3 grid((g.W + S3_TX - 1) / S3_TX, (g.H + S3_TY - 1) / S3_TY, g.N * nzc);
-    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_kernel<MODE><<<grid, S3_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<3>*>(&a), zchunk, nzc));
+    SmoothArgs<3>& a3 = *reinterpret_cast<SmoothArgs<3>*>(&a);
+    dim3 gxy((g.W + SX_TX - 1) / SX_TX, (g.H + SX_TY - 1) / SX_TY, (unsigned)(g.N * g.D));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_xy_kernel<MODE><<<gxy, SX_THREADS, 0, st>>>(g, a3, (float4*)tmp));
+    const int nzc = (g.D + SZ_CHUNK - 1) / SZ_CHUNK;
+    dim3 gz((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)(g.N * nzc));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_z_kernel<MODE><<<gz, 256, 0, st>>>(g, a3, (const float4*)tmp, nzc));
   }
 }
 
@@ -642,7 +683,7 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   float inv2n = 1.0f / (float)(1u << nb);
   ADVK_LAUNCH(K_init_phi0, st, init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, L));
   for (int k = 1; k <= nb; ++k) ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
-  launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, st);
+  launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
   return check_launch("morph_field_fwd");
 }
 
@@ -666,7 +707,7 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   T* g_off = (T*)scratch;
   T* buf[2] = {g_off + F, g_off + 2 * F};
   // (9)+(8)+(7): clamp mask, Gaussian (self-adjoint), compose-with-base border mask -> g_off = dL/d(off)
-  launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, st);
+  launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, g_off + 3 * F, st);
   // dL/dphi_n = g_off ; walk the squaring steps back, ping-ponging between two buffers that are
   // zeroed by memset nodes (g_off is kept for the Q1 subtraction below)
   const bool self_zero = ((ssb_mode() >> 2) & 3) != 0;
@@ -744,6 +785,7 @@ extern "C" int advk_morph_field_fwd(const advk_geom* gg, const advk_morph_cfg* c
   ADVK_REQUIRE(v && u_lr && levels && field_out, "null pointer");
   ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
+  ADVK_REQUIRE((i64)g.N * g.D <= 65535, "batch x depth too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
   return gg->d == 2 ? field_fwd<2>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st)
                     : field_fwd<3>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st);
@@ -765,6 +807,7 @@ extern "C" int advk_morph_field_bwd(const advk_geom* gg, const advk_morph_cfg* c
   ADVK_REQUIRE(levels && field_out && g_field && scratch && lr_scratch && g_v, "null pointer");
   ADVK_REQUIRE(g.S < 2147483647LL, "more than 2^31 voxels per sample");
   ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
+  ADVK_REQUIRE((i64)g.N * g.D <= 65535, "batch x depth too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
   return gg->d == 2 ? field_bwd<2>(g, c, scale, nb_steps, levels, field_out, g_field, scratch, lr_scratch, g_v, st)
                     : field_bwd<3>(g, c, scale, nb_steps, levels, field_out, g_field, scratch, lr_scratch, g_v, st);

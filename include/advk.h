@@ -137,7 +137,8 @@ int advk_warp_field_bwd(const advk_geom* g, int C, const float* g_out, const flo
  *
  * advk_morph_unorm2: sum over the whole batch of |upsampled smoothed velocity|^2, for the 3-D
  *   step-count rule of adv_morph.py:159-162 (the host picks nb_steps). out: 1 float, overwritten.
- * levels: (nb_steps+1) fields of N*S elements each, phi_0 .. phi_n, kept for the backward.
+ * levels: (nb_steps+2) fields of N*S elements each: phi_0 .. phi_n, kept for the backward, plus one
+ *   scratch field used by the forward.
  * field_out: the UNCLAMPED composed field (consumers clamp on load); N*S elements.
  * u_lr: scratch N x d x lr floats. */
 int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float* v, float scale,
@@ -145,7 +146,7 @@ int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float
 int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const float* v,
                          float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
                          void* stream);
-/* scratch: 5 fields of N*S elements (3 are used); lr_scratch: advk_morph_lr_scratch_floats() floats.
+/* scratch: 5 fields of N*S elements (4 are used); lr_scratch: advk_morph_lr_scratch_floats() floats.
  * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
 size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
 int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
