@@ -190,6 +190,25 @@ __device__ __forceinline__ Axis make_axis(float coord, int size, int pad, int in
   return a;
 }
 
+// Border padding + linear interpolation (the squaring steps and the compose-with-base of the field
+// build): the clipped pixel coordinate lies in [0, size-1], so the int-range guard is dead code, corner
+// i0 is always in bounds and corner i0+1 is in bounds unless the coordinate sits on the last voxel.
+__device__ __forceinline__ Axis make_axis_border(float coord, int size) {
+  Axis a;
+  const float mx = (float)(size - 1);
+  float x = ((coord + 1.f) / 2.f) * mx;
+  const bool inside = (x > 0.f) && (x < mx);
+  x = fminf(mx, fmaxf(x, 0.f));
+  a.mult = inside ? mx / 2.f : 0.f;
+  const float f = floorf(x);
+  a.i0 = (int)f;
+  a.w0 = (f + 1.f) - x;
+  a.w1 = x - f;
+  a.v0 = true;
+  a.v1 = a.i0 + 1 < size;
+  return a;
+}
+
 // ---------------------------------------------------------------------------------------
 // F.interpolate(mode=linear, align_corners=False) source index (UpSample.cuh:96-131).
 struct UpAxis { int i0, i1; float l0, l1; };

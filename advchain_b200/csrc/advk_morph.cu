@@ -191,6 +191,74 @@ unorm2_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float* __restr
   if (threadIdx.x == 0) atomicAdd(out, v[0]);
 }
 
+// Row-wise version of the two kernels above: a CTA owns 8 rows x 32 voxels of one z-plane.  The z and
+// y interpolation weights are shared by a whole row, so the CTA first reduces the lattice to one line
+// of Wl values per (channel, row) in shared memory and every voxel only interpolates along x
+// (2 shared reads per channel instead of 2^d global ones; ~35 instead of ~150 instructions per voxel).
+// phi0 == nullptr: only the sum of |u|^2 is produced (unorm2).
+constexpr int LRW_MAX = 64;
+template <int DIM>
+__global__ void __launch_bounds__(256)
+init_phi0_rows_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n,
+                      typename V<DIM>::T* __restrict__ phi0, float* __restrict__ norm2) {
+  __shared__ float rowbuf[DIM][8][LRW_MAX];
+  __shared__ float red[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int z = (DIM == 3) ? blockIdx.z % g.D : 0;
+  const int n = (DIM == 3) ? blockIdx.z / g.D : blockIdx.z;
+  const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
+  const int lr = c.Dl * c.Hl * c.Wl;
+  UpAxis uz;
+  if (DIM == 3) uz = up_axis(z, c.Dl, c.sD);
+  else { uz.i0 = uz.i1 = 0; uz.l0 = 1.f; uz.l1 = 0.f; }
+  for (int i = threadIdx.x; i < DIM * 8 * c.Wl; i += 256) {
+    const int xl = i % c.Wl, r = (i / c.Wl) & 7, ch = i / (8 * c.Wl);
+    const int yy = min(blockIdx.y * 8 + r, g.H - 1);
+    const UpAxis uy = up_axis(yy, c.Hl, c.sH);
+    const float* s = u_lr + ((i64)n * DIM + ch) * lr + xl;
+    float acc = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+      const int zi = dz ? uz.i1 : uz.i0;
+      const float lz = dz ? uz.l1 : uz.l0;
+      acc += lz * (uy.l0 * __ldg(s + (zi * c.Hl + uy.i0) * c.Wl) + uy.l1 * __ldg(s + (zi * c.Hl + uy.i1) * c.Wl));
+    }
+    rowbuf[ch][r][xl] = acc;
+  }
+  __syncthreads();
+  float v[1] = {0.f};
+  if (x < g.W && y < g.H) {
+    const UpAxis ux = up_axis(x, c.Wl, c.sW);
+    float u[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < DIM; ++ch) u[ch] = ux.l0 * rowbuf[ch][ty][ux.i0] + ux.l1 * rowbuf[ch][ty][ux.i1];
+    v[0] = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+    if (phi0)
+      phi0[(i64)n * g.S + ((i64)z * g.H + y) * g.W + x] =
+          V<DIM>::make(base_coord_s(x, g.W, g.stW) + u[0] * inv2n, base_coord_s(y, g.H, g.stH) + u[1] * inv2n,
+                       (DIM == 3 ? base_coord_s(z, g.D, g.stD) + u[2] * inv2n : 0.f));
+  }
+  if (norm2) {
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) atomicAdd(norm2, v[0]);
+  }
+}
+
+template <int DIM>
+static void launch_init_phi0(const MorphCfg& c, const Dims& g, const float* u_lr, float inv2n, void* phi0,
+                             float* norm2, cudaStream_t st) {
+  typedef typename V<DIM>::T T;
+  const i64 gz = (DIM == 3) ? (i64)g.N * g.D : g.N;
+  if (c.Wl <= LRW_MAX && gz <= 65535) {
+    dim3 grid((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)gz);
+    ADVK_LAUNCH(phi0 ? K_init_phi0 : K_unorm2, st, init_phi0_rows_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, (T*)phi0, norm2));
+  } else {
+    dim3 grid(blocks_for(g.S, 256), g.N);
+    if (phi0) ADVK_LAUNCH(K_init_phi0, st, init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, (T*)phi0));
+    else ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, norm2));
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // One squaring step: out(p) = sample(in, at in(p)), border padding, align_corners=True.
 template <int DIM>
@@ -202,10 +270,10 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
   if (p >= g.S) return;
   const T* src = in + (i64)n * g.S;
   const T f = __ldg(src + p);
-  Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
-  Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
   Axis az;
-  if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
   else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
   const int HW = g.H * g.W;
   const T* c000 = src + (az.i0 * HW + ay.i0 * g.W + ax.i0);     // only dereferenced at in-bounds corners
@@ -292,10 +360,10 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
     go = up[nb + p];
     if (ZSTORE == 1) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
   }
-  Axis ax = make_axis(f.x, g.W, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
-  Axis ay = make_axis(f.y, g.H, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
   Axis az;
-  if (DIM == 3) az = make_axis(V<DIM>::z(f), g.D, ADVK_PAD_BORDER, ADVK_INTERP_LINEAR);
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
   else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
   const int HW = g.H * g.W;
   const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
@@ -650,10 +718,65 @@ adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ a2, const T* 
   out[idx] = t_scale(acc, vs);
 }
 
+// Same adjoint for the FIRST (largest) axis, where `inner` is a whole plane / row: a CTA owns 32
+// consecutive inner positions and all of the axis; its 8 warps split the axis, every thread streams its
+// slice once (no window overlap: each input is read exactly once), keeps the running pair of output
+// nodes in registers and flushes to a shared accumulator when the pair changes.
+constexpr int ADJ_NOUT_MAX = 64;
+__device__ __forceinline__ void sm_add(float4* d, float4 v) {
+  atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y); atomicAdd(&d->z, v.z);
+}
+__device__ __forceinline__ void sm_add(float2* d, float2 v) { atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y); }
+__device__ __forceinline__ void sm_add(float* d, float v) { atomicAdd(d, v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+adjoint_axis_big_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out,
+                        int n_in, int n_out, i64 inner, float scale) {
+  extern __shared__ float4 adj_smem4[];
+  T* acc = reinterpret_cast<T*>(adj_smem4);                 // [n_out][32]
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const i64 o = blockIdx.y;
+  const i64 i = (i64)blockIdx.x * 32 + lane;
+  for (int k = threadIdx.x; k < n_out * 32; k += 256) acc[k] = t_zero<T>();
+  __syncthreads();
+  if (i < inner) {
+    const int chunk = (n_in + 7) / 8;
+    const int p0 = wrp * chunk, p1 = min(n_in, p0 + chunk);
+    const bool hb = (b != nullptr);
+    int c0 = -1, c1 = -1;
+    T s0 = t_zero<T>(), s1 = t_zero<T>();
+    for (int p = p0; p < p1; ++p) {
+      const UpAxis u = up_axis(p, n_out, scale);
+      if (u.i0 != c0 || u.i1 != c1) {
+        if (c0 >= 0) { sm_add(acc + c0 * 32 + lane, s0); sm_add(acc + c1 * 32 + lane, s1); }
+        c0 = u.i0; c1 = u.i1; s0 = t_zero<T>(); s1 = t_zero<T>();
+      }
+      const i64 q = (o * n_in + p) * inner + i;
+      const T av = a[q];
+      const T bv = hb ? b[q] : av;
+      t_fma(s0, u.l0, av, bv, hb);
+      t_fma(s1, u.l1, av, bv, hb);
+    }
+    if (c0 >= 0) { sm_add(acc + c0 * 32 + lane, s0); sm_add(acc + c1 * 32 + lane, s1); }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_out * 32; k += 256) {
+    const int j = k >> 5, l = k & 31;
+    const i64 ii = (i64)blockIdx.x * 32 + l;
+    if (ii < inner) out[(o * n_out + j) * inner + ii] = t_scale(acc[k], vs);
+  }
+}
+
 template <typename T>
 static void launch_adjoint_axis(const T* a, const T* a2, const T* b, float vs, T* out, i64 outer, int n_in,
                                 int n_out, i64 inner, float scale, cudaStream_t st) {
   i64 tot = outer * n_out * inner;
+  if (!a2 && inner >= 32 && n_out <= ADJ_NOUT_MAX && outer <= 65535) {
+    dim3 grid((unsigned)((inner + 31) / 32), (unsigned)outer);
+    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(a, b, vs, out, n_in, n_out, inner, scale));
+    return;
+  }
   ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, a2, b, vs, out, outer, n_in, n_out, inner, scale));
 }
 
@@ -681,7 +804,7 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   i64 F = (i64)g.N * g.S;
   dim3 grid(blocks_for(g.S, 256), g.N);
   float inv2n = 1.0f / (float)(1u << nb);
-  ADVK_LAUNCH(K_init_phi0, st, init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, L));
+  launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, nullptr, st);
   for (int k = 1; k <= nb; ++k) ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
   launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
   return check_launch("morph_field_fwd");
@@ -768,10 +891,10 @@ extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg,
   dim3 grid(blocks_for(g.S, 256), g.N);
   if (gg->d == 2) {
     launch_lowres_smooth<2>(c, NC, v, scale, u_lr, st);
-    ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<2><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
+    launch_init_phi0<2>(c, g, u_lr, 0.f, nullptr, out_norm2, st);
   } else {
     launch_lowres_smooth<3>(c, NC, v, scale, u_lr, st);
-    ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<3><<<grid, 256, 0, st>>>(c, g, u_lr, out_norm2));
+    launch_init_phi0<3>(c, g, u_lr, 0.f, nullptr, out_norm2, st);
   }
   return check_launch("morph_unorm2");
 }
