@@ -62,7 +62,7 @@ ALGO_WORDS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="m128", choices=sorted(WORKLOADS))
@@ -81,7 +81,7 @@ def make_cfgs(d, size):
 
 class ClockSampler(object):
     """nvidia-smi clock / throttle-reason sampler running beside the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -96,7 +96,18 @@ class ClockSampler(object):
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts):
+        """nvidia-smi timestamp 'YYYY/MM/DD HH:MM:SS.mmm' (local time) -> epoch seconds."""
+        try:
+            base, _, ms = ts.partition(".")
+            return time.mktime(time.strptime(base, "%Y/%m/%d %H:%M:%S")) + (float("0." + ms) if ms else 0.0)
+        except Exception:
+            return None
+
+    def stop(self, window=None):
+        """window = (t0, t1) wall-clock bounds of the timed region: only samples taken inside it (the
+        samples 'under load') enter the median; without any, every sample is used and `in_window` is 0."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -107,20 +118,25 @@ class ClockSampler(object):
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                rows.append((self._epoch(c[0]), float(c[1]), float(c[2]),
+                             [nm for nm, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+        inside = []
+        if window is not None:
+            inside = [r for r in rows if r[0] is not None and window[0] - 0.05 <= r[0] <= window[1] + 0.05]
+        use = inside or rows
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use]
+        reasons = set(nm for r in use for nm in r[3])
+        out["in_window"] = len(inside)
         self.f.close()
         try:
             os.unlink(self.f.name)
@@ -133,6 +149,19 @@ class ClockSampler(object):
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
+
+
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by scripts/summarize_ncu.py), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        return None if e is None else float(e["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -175,24 +204,48 @@ def cpu_port_step_time(d, size, chain, steps=1, warmup=0, threads=None):
     return times
 
 
-def sample_size(d, size):
-    """The bounded CPU sample: the same workload with every spatial axis halved (1/2^d of the
-    voxels); throughput is scaled by the voxel ratio."""
-    sp = [max(16, s // 2) for s in size[2:]]
+def sample_size(d, size, div=2):
+    """The bounded CPU sample: the same workload with every spatial axis divided by `div` (1/div^d of
+    the voxels); throughput is scaled by the voxel ratio."""
+    sp = [max(16, s // div) for s in size[2:]]
     return [size[0], size[1]] + sp
 
 
+def _nvox(size):
+    n = size[0]
+    for s in size[2:]:
+        n *= s
+    return n
+
+
+REF_BUDGET_S = 180.0     # wall-clock bound of the reference arm's timed region
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path, restated in oracle/ (kind "port"), on all host
+    cores.  Each step is one PGD inner-loop iteration on a BOUNDED sample of the workload: the same
+    chain on a sub-volume with every spatial axis divided by 2, 4, ... -- the largest one for which the
+    K timed steps are projected (from the warm-up) to finish within REF_BUDGET_S -- and the measured
+    iterations/s are scaled by the voxel ratio (CPU cost is linear in the voxel count at these sizes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     d, size, chain = WORKLOADS[args.workload]
-    ssz = sample_size(d, size)
-    ratio = 1.0
-    for a, b in zip(ssz[2:], size[2:]):
-        ratio *= float(a) / float(b)
     cores = os.cpu_count() or 1
-    times = cpu_port_step_time(d, ssz, chain, steps=args.steps, warmup=args.warmup, threads=cores)
+    div = 2
+    ssz = sample_size(d, size, div)
+    warm = cpu_port_step_time(d, ssz, chain, steps=max(1, args.warmup), warmup=0, threads=cores)
+    per_step = min(warm)
+    while per_step * args.steps > REF_BUDGET_S and min(ssz[2:]) > 16:
+        div *= 2
+        nxt = sample_size(d, size, div)
+        if nxt == ssz:
+            break
+        per_step *= float(_nvox(nxt)) / float(_nvox(ssz))
+        ssz = nxt
+    ratio = float(_nvox(ssz)) / float(_nvox(size))
+    times = cpu_port_step_time(d, ssz, chain, steps=args.steps, warmup=(0 if div == 2 else max(1, args.warmup)),
+                               threads=cores)
     total = sum(times)
     value = args.steps / total * ratio
     sample = ("each step = 1 PGD inner-loop iteration of the CPU port on %s (%.4g of the voxels of %s); "
@@ -295,6 +348,7 @@ def run_b200(args):
 
     # ---- eager warm-up; two steps run with every kernel bracketed by CUDA events -> per-kernel
     # breakdown and the dominant kernel
+    eager_steps = min(args.steps, 50)          # the eager legs (breakdown / live roofline) are bounded
     sol.use_cuda_graph = False
     for _ in range(max(args.warmup, 3)):
         step(True)
@@ -314,8 +368,8 @@ def run_b200(args):
     _lib.launch_count(reset=True)
     if dom is not None:
         _lib.prof_configure(dom, 16384)
-    ms_eager = timed(args.steps, True)
-    eager_launches = _lib.launch_count(reset=True)
+    ms_eager = timed(eager_steps, True)
+    eager_launches = _lib.launch_count(reset=True) * args.steps // eager_steps
     dom_ms = _lib.prof_collect(16384).get(dom, []) if dom is not None else []
     _lib.prof_configure(None)
 
@@ -326,8 +380,12 @@ def run_b200(args):
         step(True)
     sol.graph_replays = 0
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)                       # let nvidia-smi come up before the timed region starts
+    w0 = time.time()
     ms = timed(args.steps, True)
-    clocks = sampler.stop() if sampler else None
+    w1 = time.time()
+    clocks = sampler.stop((w0, w1)) if sampler else None
     graph_used = use_graph and getattr(sol, "graph_replays", 0) == args.steps
     launches = (sol.graph_launches_per_replay * args.steps) if graph_used else eager_launches
 
@@ -352,12 +410,12 @@ def run_b200(args):
         algo_bytes = ALGO_WORDS[dom](d) * 4.0 * nvox
         achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom), "peak_source": peak_src,
                 "algo_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms,
                 "launches_timed": len(dom_ms),
                 "kernel_share_of_step": sum(dom_ms) / ms_eager if ms_eager > 0 else None,
-                "measured_in": "eager timed region of the same %d steps (CUDA events on the launching "
-                               "stream; graph nodes cannot be bracketed)" % args.steps}
+                "measured_in": "eager timed region of %d steps (CUDA events on the launching "
+                               "stream; graph nodes cannot be bracketed)" % eager_steps}
     # whole-step algorithmic bytes: full chain 102d+10C+5K+1 words / voxel
     C = size[1]
     if chain == ["noise", "bias", "morph", "affine"]:
@@ -376,7 +434,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": host_data.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "cuda_graph": bool(graph_used),
-        "ms_per_step_eager": ms_eager / args.steps,
+        "ms_per_step_eager": ms_eager / eager_steps,
         "clocks": clocks,
         "roofline": roof,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in ranked},
