@@ -63,6 +63,7 @@ class AdvMorph(AdvTransformBase):
         self._steps_cache = None
         self._cfg = None
         self._fixed_steps = None    # (n, int32 device counter): graph mode, rule verified on the device
+        self._last_nb_steps = None  # count the last graph-mode loop ran with (and verified)
         self.shard = None           # sharding.ShardContext: whole-batch norm for the 3-D step rule (quirk Q2)
 
     def init_config(self, config_dict):

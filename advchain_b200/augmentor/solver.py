@@ -463,7 +463,12 @@ class ComposeAdversarialTransformSolver(object):
         for t in morph3d:
             t._fixed_steps = None
             t._steps_cache = None
-        nsteps = tuple(t._nb_steps() for t in morph3d)
+        # The step count of the 3-D squaring rule needs a device reduction + a scalar read.  A loop that was
+        # already captured re-uses the count it last ran with (no host round trip before the replays);
+        # the device-side check of every replay (advk_morph_steps_check) reports if the rule now gives a
+        # different count, in which case the loop is redone eagerly below.
+        nsteps = tuple(t._last_nb_steps if getattr(t, "_last_nb_steps", None) is not None else t._nb_steps()
+                       for t in morph3d)
         rng = self._intensity_range(data) if self.if_norm_image else None
         key = (id(model), model.training, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
                float(step), tuple(id(t) for t in chain), tuple(t.power_iteration for t in chain),
@@ -517,7 +522,12 @@ class ComposeAdversarialTransformSolver(object):
         elif st is False:
             return False
         st["data"].copy_(data.detach())
-        st["init_output"].copy_(init_output.detach())
+        # the clean prediction usually is the same tensor for every call of a training step: skip the
+        # device-to-device refresh when neither its storage nor its version counter moved
+        tag = (init_output.data_ptr(), init_output._version, tuple(init_output.shape))
+        if st.get("init_tag") != tag:
+            st["init_output"].copy_(init_output.detach())
+            st["init_tag"] = tag
         for buf, p in zip(st["params"], start):
             buf.copy_(p)
         st["viol"].zero_()
@@ -527,11 +537,15 @@ class ComposeAdversarialTransformSolver(object):
         self.graph_launches_per_replay = st["advk_launches"]
         self.last_dist = st["dist"][0]
         if morph3d and int(st["viol"].item()) != 0:
-            # the 3-D step count grew during the loop: redo it eagerly from the start parameters
+            # the 3-D step count changed during the loop: redo it eagerly from the start parameters
             for t, p in zip(chain, start):
                 t.param = p
                 t.is_training = False
+            for t in morph3d:
+                t._last_nb_steps = None
             return False
+        for t, n in zip(morph3d, nsteps):
+            t._last_nb_steps = n
         for t, buf in zip(chain, st["params"]):
             t.param = buf.clone()
         for flag, t in zip(optimize_flags, chain):
