@@ -16,10 +16,10 @@ __version__ = "0.1.0"
 
 def install_as_advchain():
     """Registers this package under the reference's import names (`advchain.augmentor`,
-    `advchain.common.loss`, `advchain.common.utils`)."""
+    `advchain.common.loss`, `advchain.common.utils`, `advchain.common.layers`)."""
     import types
     from . import augmentor, common
-    from .common import loss, utils
+    from .common import layers, loss, utils
     root = types.ModuleType("advchain")
     root.augmentor, root.common = augmentor, common
     sys.modules["advchain"] = root
@@ -27,4 +27,5 @@ def install_as_advchain():
     sys.modules["advchain.common"] = common
     sys.modules["advchain.common.loss"] = loss
     sys.modules["advchain.common.utils"] = utils
+    sys.modules["advchain.common.layers"] = layers
     return root

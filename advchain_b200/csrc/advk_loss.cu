@@ -64,7 +64,7 @@ loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const fl
 // halo, zero outside the volume like the reference's padding=1 convolutions), every thread
 // evaluates the two in-plane factors from 6 shared reads and keeps a 3-plane register window for the
 // h(D) factor -- 1.06 global reads per voxel instead of 27 L1 gathers.
-constexpr int LT_X = 32, LT_Y = 8, LT_Z = 32;
+constexpr int LT_X = 32, LT_Y = 8, LT_Z = 16;
 
 // in-plane factors at (tx,ty) of a staged (LT_Y+2) x (LT_X+2) tile:
 //   a = hp(H) h(W) t,  b = h(H) hp(W) t

@@ -262,7 +262,7 @@ static void launch_init_phi0(const MorphCfg& c, const Dims& g, const float* u_lr
 // ---------------------------------------------------------------------------------------
 // One squaring step: out(p) = sample(in, at in(p)), border padding, align_corners=True.
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
   const int n = blockIdx.y;

