@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libadvchain_b200.so")
 ABI_VERSION = 1
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
-INTERP_LINEAR, INTERP_NEAREST = 0, 1
+INTERP_LINEAR, INTERP_NEAREST, INTERP_BICUBIC = 0, 1, 2
 UPD_L2_ASCENT, UPD_SIGN_ASCENT, UPD_L2_POWER, UPD_SIGN_POWER = 0, 1, 2, 3
 
 

@@ -16,13 +16,13 @@ from .._lib import call, ptr, stream
 
 _PAD = {"zeros": _lib.PAD_ZEROS, "border": _lib.PAD_BORDER, "reflection": _lib.PAD_REFLECTION}
 _INTERP = {"bilinear": _lib.INTERP_LINEAR, "trilinear": _lib.INTERP_LINEAR,
-           "linear": _lib.INTERP_LINEAR, "nearest": _lib.INTERP_NEAREST}
+           "linear": _lib.INTERP_LINEAR, "nearest": _lib.INTERP_NEAREST, "bicubic": _lib.INTERP_BICUBIC}
 
 
 def parse_interp(interp):
     if interp not in _INTERP:
         raise NotImplementedError("interpolation mode %r is not supported by the CUDA path "
-                                  "(bilinear/trilinear/nearest are)" % (interp,))
+                                  "(bilinear/trilinear/nearest/bicubic are)" % (interp,))
     return _INTERP[interp]
 
 

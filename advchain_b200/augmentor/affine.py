@@ -152,6 +152,8 @@ class AdvAffine(AdvTransformBase):
         fwd = mode in ("fwd", "pfwd")
         if interp is None:
             interp = self.forward_interp if fwd else self.backward_interp
+        if _ops.parse_interp(interp) == _ops._lib.INTERP_BICUBIC:
+            return NotImplemented                                     # bicubic: per-transform kernels
         pp = _ops.fused_padding(self.image_padding_mode, data)      # quirk Q5
         if pp is None:
             return NotImplemented

@@ -190,6 +190,151 @@ warp_bwd_kernel(Dims g, int C, const float* __restrict__ g_out, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Bicubic (2-D only, like F.grid_sample): GridSampler.cuh grid_sampler_2d_kernel /
+// grid_sampler_2d_backward_kernel, mode == Bicubic.  The grid coordinate is only un-normalised (no
+// clipping); every one of the 4 x 4 taps runs its INTEGER coordinate through the padding rule
+// (clip / reflect) and a bounds test, forward and backward alike; the grid gradient uses the
+// derivative of the cubic-convolution coefficients (A = -0.75) and treats the tap positions as
+// constants, exactly as ATen does.
+constexpr float CUBIC_A = -0.75f;
+__device__ __forceinline__ float cubic_conv1(float x) { return ((CUBIC_A + 2.f) * x - (CUBIC_A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic_conv2(float x) {
+  return ((CUBIC_A * x - 5.f * CUBIC_A) * x + 8.f * CUBIC_A) * x - 4.f * CUBIC_A;
+}
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  c[0] = cubic_conv2(t + 1.f);
+  c[1] = cubic_conv1(t);
+  const float u = 1.f - t;
+  c[2] = cubic_conv1(u);
+  c[3] = cubic_conv2(u + 1.f);
+}
+__device__ __forceinline__ void cubic_coeffs_grad(float t, float (&c)[4]) {
+  float x = -1.f - t;
+  c[0] = (-3.f * CUBIC_A * x - 10.f * CUBIC_A) * x - 8.f * CUBIC_A;
+  x = -t;
+  c[1] = (-3.f * (CUBIC_A + 2.f) * x - 2.f * (CUBIC_A + 3.f)) * x;
+  x = 1.f - t;
+  c[2] = (3.f * (CUBIC_A + 2.f) * x - 2.f * (CUBIC_A + 3.f)) * x;
+  x = 2.f - t;
+  c[3] = (3.f * CUBIC_A * x - 10.f * CUBIC_A) * x + 8.f * CUBIC_A;
+}
+// compute_coordinates on a tap index (align_corners=True) + bounds test; returns -1 when outside
+__device__ __forceinline__ int cubic_tap(float c, int size, int pad) {
+  if (pad == ADVK_PAD_REFLECTION) {
+    float m;
+    c = gs_reflect(c, 0, 2 * (size - 1), m);
+  }
+  if (pad != ADVK_PAD_ZEROS) c = fminf((float)(size - 1), fmaxf(c, 0.f));
+  if (!(c <= 2147483646.f && c >= -2147483648.f)) c = -100.f;
+  const int i = (int)c;
+  return (i >= 0 && i < size) ? i : -1;
+}
+
+struct CubicTaps {
+  int ix[4], iy[4];
+  float cx[4], cy[4], gx[4], gy[4];
+  float mx, my;
+};
+__device__ __forceinline__ CubicTaps make_cubic(float coordx, float coordy, const Dims& g, int pad) {
+  CubicTaps t;
+  t.mx = (float)(g.W - 1) / 2.f; t.my = (float)(g.H - 1) / 2.f;
+  const float fx = ((coordx + 1.f) / 2.f) * (float)(g.W - 1), fy = ((coordy + 1.f) / 2.f) * (float)(g.H - 1);
+  const float nx = floorf(fx), ny = floorf(fy);
+  cubic_coeffs(fx - nx, t.cx); cubic_coeffs(fy - ny, t.cy);
+  cubic_coeffs_grad(fx - nx, t.gx); cubic_coeffs_grad(fy - ny, t.gy);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    t.ix[i] = cubic_tap(nx - 1.f + (float)i, g.W, pad);
+    t.iy[i] = cubic_tap(ny - 1.f + (float)i, g.H, pad);
+  }
+  return t;
+}
+
+template <bool FIELD>
+__global__ void __launch_bounds__(WARP_THREADS)
+warp_bicubic_fwd_kernel(Dims g, int C, const float* __restrict__ src, const float* __restrict__ theta,
+                        const void* __restrict__ field, int pad, const float* __restrict__ padv,
+                        float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.S) return;
+  const int x = (int)(p % g.W), y = (int)(p / g.W);
+  float cx, cy, cz, rx, ry, rz;
+  sample_coords<2, FIELD>(g, n, 0, y, x, p, theta, field, cx, cy, cz, rx, ry, rz);
+  const CubicTaps t = make_cubic(cx, cy, g, pad);
+  const float pv = padv ? padv[n] : 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* s = src + ((i64)n * C + c) * g.S;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float row = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v = (t.ix[i] >= 0 && t.iy[j] >= 0) ? __ldg(s + (i64)t.iy[j] * g.W + t.ix[i]) - pv : 0.f;
+        row += v * t.cx[i];
+      }
+      acc += row * t.cy[j];
+    }
+    out[((i64)n * C + c) * g.S + p] = acc + pv;
+  }
+}
+
+template <bool FIELD>
+__global__ void __launch_bounds__(WARP_THREADS)
+warp_bicubic_bwd_kernel(Dims g, int C, const float* __restrict__ g_out, const float* __restrict__ src,
+                        const float* __restrict__ theta, const void* __restrict__ field, int pad,
+                        const float* __restrict__ padv, float* __restrict__ g_src,
+                        float* __restrict__ g_theta, void* __restrict__ g_field) {
+  __shared__ float red[6 * 32];
+  const int n = blockIdx.y;
+  const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < g.S;
+  float ggx = 0.f, ggy = 0.f, bx = 0.f, by = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;
+  if (live) {
+    const int x = (int)(p % g.W), y = (int)(p / g.W);
+    float cx, cy, cz;
+    sample_coords<2, FIELD>(g, n, 0, y, x, p, theta, field, cx, cy, cz, rx, ry, rz);
+    if (!FIELD) { bx = base_coord(x, g.W, 0.f); by = base_coord(y, g.H, 0.f); }
+    const CubicTaps t = make_cubic(cx, cy, g, pad);
+    const float pv = padv ? padv[n] : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const i64 cb = ((i64)n * C + c) * g.S;
+      const float go = g_out[cb + p];
+      const float* s = src + cb;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (t.ix[i] >= 0 && t.iy[j] >= 0) {
+            const i64 q = (i64)t.iy[j] * g.W + t.ix[i];
+            if (g_src) atomicAdd(g_src + cb + q, go * t.cx[i] * t.cy[j]);
+            const float v = __ldg(s + q) - pv;
+            ggx -= v * t.gx[i] * t.cy[j] * go;
+            ggy -= v * t.gy[j] * t.cx[i] * go;
+          }
+        }
+      }
+    }
+    ggx *= t.mx; ggy *= t.my;
+  }
+  if (FIELD) {
+    if (!live || !g_field) return;
+    if (!(rx >= -1.f && rx <= 1.f)) ggx = 0.f;
+    if (!(ry >= -1.f && ry <= 1.f)) ggy = 0.f;
+    reinterpret_cast<float2*>(g_field)[(i64)n * g.S + p] = make_float2(ggx, ggy);
+  } else {
+    if (!g_theta) return;
+    float v[6] = {ggx * bx, ggx * by, ggx, ggy * bx, ggy * by, ggy};
+    block_sum<6>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) atomicAdd(g_theta + n * 6 + k, v[k]);
+    }
+  }
+}
+
 template <bool FIELD>
 static int launch_fwd(const advk_geom* gg, int C, const float* src, const float* theta,
                       const void* field, int pad, int interp, const float* padv, float* out,
@@ -197,10 +342,13 @@ static int launch_fwd(const advk_geom* gg, int C, const float* src, const float*
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(C >= 1 && src && out && (FIELD ? field != nullptr : theta != nullptr), "null pointer");
-  ADVK_REQUIRE(pad >= 0 && pad <= 2 && interp >= 0 && interp <= 1, "bad pad/interp mode");
+  ADVK_REQUIRE(pad >= 0 && pad <= 2 && interp >= 0 && interp <= 2, "bad pad/interp mode");
+  ADVK_REQUIRE(interp != ADVK_INTERP_BICUBIC || gg->d == 2, "bicubic interpolation is 2-D only (like F.grid_sample)");
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
-  if (gg->d == 2)
+  if (interp == ADVK_INTERP_BICUBIC)
+    ADVK_LAUNCH(K_warp_fwd, st, warp_bicubic_fwd_kernel<FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, padv, out));
+  else if (gg->d == 2)
     ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
   else
     ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
@@ -215,10 +363,13 @@ static int launch_bwd(const advk_geom* gg, int C, const float* g_out, const floa
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(C >= 1 && src && g_out && (FIELD ? field != nullptr : theta != nullptr), "null pointer");
-  ADVK_REQUIRE(pad >= 0 && pad <= 2 && interp >= 0 && interp <= 1, "bad pad/interp mode");
+  ADVK_REQUIRE(pad >= 0 && pad <= 2 && interp >= 0 && interp <= 2, "bad pad/interp mode");
+  ADVK_REQUIRE(interp != ADVK_INTERP_BICUBIC || gg->d == 2, "bicubic interpolation is 2-D only (like F.grid_sample)");
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
-  if (gg->d == 2)
+  if (interp == ADVK_INTERP_BICUBIC)
+    ADVK_LAUNCH(K_warp_bwd, st, warp_bicubic_bwd_kernel<FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, padv, g_src, g_theta, g_field));
+  else if (gg->d == 2)
     ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
   else
     ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));

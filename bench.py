@@ -91,10 +91,25 @@ class ClockSampler(object):
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                 stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def wait_ready(self, timeout_s=15.0):
+        """Blocks until the first sample has been written (the first nvidia-smi call on a fresh box can
+        take seconds to come up)."""
+        if self.p is None:
+            return False
+        t0 = time.time()
+        while time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return True
+            except OSError:
+                return False
+            time.sleep(0.05)
+        return False
 
     @staticmethod
     def _epoch(ts):
@@ -131,7 +146,11 @@ class ClockSampler(object):
                 continue
         inside = []
         if window is not None:
-            inside = [r for r in rows if r[0] is not None and window[0] - 0.05 <= r[0] <= window[1] + 0.05]
+            inside = [r for r in rows if r[0] is not None and window[0] - 0.03 <= r[0] <= window[1] + 0.03]
+            if not inside:                      # a timed region shorter than the sampling period
+                mid = 0.5 * (window[0] + window[1])
+                near = sorted((abs(r[0] - mid), i) for i, r in enumerate(rows) if r[0] is not None)
+                inside = [rows[i] for dist_, i in near[:1] if dist_ < 0.5]
         use = inside or rows
         sm = [r[1] for r in use]
         mx = [r[2] for r in use]
@@ -301,6 +320,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     d, size, chain = WORKLOADS[args.workload]
+    sampler = ClockSampler(local) if rank == 0 else None     # runs beside everything; filtered to the timed window
     torch.manual_seed(1234 + rank)
     host_data = torch.rand(*size).pin_memory()
     conv = torch.nn.Conv2d if d == 2 else torch.nn.Conv3d
@@ -427,9 +447,8 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step(True)
     sol.graph_replays = 0
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        time.sleep(1.0)                       # let nvidia-smi come up before the timed region starts
+        sampler.wait_ready()                  # started before the warm-up; make sure it is producing
     w0 = time.time()
     ms = timed(args.steps, True)
     w1 = time.time()

@@ -32,7 +32,8 @@ extern "C" {
 
 enum { ADVK_OK = 0, ADVK_ERR_ARG = -1, ADVK_ERR_UNSUPPORTED = -2, ADVK_ERR_CUDA = -3 };
 enum { ADVK_PAD_ZEROS = 0, ADVK_PAD_BORDER = 1, ADVK_PAD_REFLECTION = 2 };
-enum { ADVK_INTERP_LINEAR = 0, ADVK_INTERP_NEAREST = 1 };
+enum { ADVK_INTERP_LINEAR = 0, ADVK_INTERP_NEAREST = 1,
+       ADVK_INTERP_BICUBIC = 2 /* single-stage 2-D warps only (F.grid_sample mode="bicubic") */ };
 
 /* PGD update modes (advk_pgd_update) */
 enum {

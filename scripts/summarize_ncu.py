@@ -61,22 +61,38 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full():
-    rep = os.path.join(G, tag + "_prof.ncu-rep")
-    if not os.path.exists(rep):
+    import glob
+    reps = sorted(glob.glob(os.path.join(G, tag + "_full_*.ncu-rep")))
+    legacy = os.path.join(G, tag + "_prof.ncu-rep")
+    if os.path.exists(legacy):
+        reps.append(legacy)
+    if not reps:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
-    kn = hdr.index("Kernel Name")
     with open(os.path.join(P, prefix + "_ncu_full.md"), "w") as f:
-        f.write("# ncu --set full --clock-control none (per launch; cold cache) -- %s\n\n" % tag)
-        for r in rows[2:]:
-            f.write("## `%s`\n\n| metric | value | unit |\n|---|---:|---|\n" % r[kn][:100])
-            for w, i in idx:
-                f.write("| %s | %s | %s |\n" % (w, r[i], units[i]))
-            f.write("\n")
+        f.write("# ncu --set full --clock-control none --import-source on (per launch; cold cache, serialised) -- %s\n\n" % tag)
+        f.write("Workload m128 (1x1x128^3, full chain), `scripts/one_step.py`; one block per captured launch.\n\n")
+        for rep in reps:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            rows = list(csv.reader(raw.splitlines()))
+            if len(rows) < 3:
+                continue
+            hdr, units = rows[0], rows[1]
+            idx = [(w, hdr.index(w)) for w in WANT + EXTRA if w in hdr]
+            kn = hdr.index("Kernel Name")
+            for r in rows[2:]:
+                f.write("## `%s`\n\n| metric | value | unit |\n|---|---:|---|\n" % r[kn][:100])
+                for w, i in idx:
+                    f.write("| %s | %s | %s |\n" % (w, r[i], units[i]))
+                f.write("\n")
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_traffic.py"), tag] + reps)
 
+
+EXTRA = ["l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
+         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+         "smsp__warps_eligible.avg.per_cycle_active"]
 
 launches()
 full()

@@ -99,6 +99,73 @@ def test_warp_field(d, size, pad):
     assert rel_err(_field_to_cf(f1.grad, d), g0.grad) < GRAD_TOL
 
 
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection", -0.5])
+@pytest.mark.parametrize("kind", ["affine", "field"])
+def test_warp_bicubic_2d(pad, kind):
+    """interp='bicubic' (2-D only, F.grid_sample mode='bicubic'): 4 x 4 cubic-convolution taps, every tap
+    index run through the padding rule; gradients w.r.t. the source, theta and the field."""
+    ops = _ops()
+    torch.manual_seed(7)
+    size = [2, 3, 37, 53]
+    n = size[0]
+    src = torch.rand(*size)
+    gout = torch.randn(*size)
+    s0 = src.clone().requires_grad_(True)
+    s1 = src.to(_dev()).requires_grad_(True)
+    pm, pv = ops.parse_padding(pad, s1)
+    code = ops.parse_interp("bicubic")
+    if kind == "affine":
+        theta = torch.eye(2, 3).unsqueeze(0).repeat(n, 1, 1) + 0.25 * torch.randn(n, 2, 3)
+        t0 = theta.clone().requires_grad_(True)
+        ref = orc.warp(s0, theta=t0, interp="bicubic", padding=pad)
+        ref.backward(gout)
+        t1 = theta.to(_dev()).requires_grad_(True)
+        out = ops.WarpAffine.apply(s1, t1, pm, code, pv)
+        out.backward(gout.to(_dev()))
+        assert rel_err(t1.grad, t0.grad) < GRAD_TOL
+    else:
+        base = orc.base_grid(n, size[2:])
+        grid = base + 0.3 * torch.randn_like(base)
+        g0 = grid.clone().requires_grad_(True)
+        ref = orc.warp(s0, grid_cf=torch.clamp(g0, -1, 1), interp="bicubic", padding=pad)
+        ref.backward(gout)
+        f1 = _cf_to_field(grid).to(_dev()).requires_grad_(True)
+        out = ops.WarpField.apply(s1, f1, pm, code, pv)
+        out.backward(gout.to(_dev()))
+        assert rel_err(_field_to_cf(f1.grad, 2), g0.grad) < GRAD_TOL
+    assert rel_err(out, ref) < 2 * OUT_TOL
+    assert rel_err(s1.grad, s0.grad) < GRAD_TOL
+
+
+def test_bicubic_transform_end_to_end_and_3d_refusal():
+    """AdvAffine / AdvMorph configured with bicubic interpolators run through the solver (per-transform
+    kernels; the fused executor hands bicubic chains over) and match the oracle; 3-D bicubic is refused
+    like F.grid_sample refuses it."""
+    from advchain_b200.augmentor import AdvAffine, AdvMorph, ComposeAdversarialTransformSolver
+    size = [2, 1, 40, 56]
+    cfgs = stage_cfgs(2, size)
+    for k in ("morph", "affine"):
+        cfgs[k]["forward_interp"] = cfgs[k]["backward_interp"] = "bicubic"
+    ts = [AdvMorph(2, cfgs["morph"], device=_dev()), AdvAffine(2, cfgs["affine"], device=_dev())]
+    sol = ComposeAdversarialTransformSolver(ts, if_norm_image=False)
+    torch.manual_seed(9)
+    for t in ts:
+        t.init_parameters()
+        t.eval()
+    x = torch.rand(*size)
+    out = sol.forward(x.to(_dev()))
+    field = torch.clamp(orc.morph_field(ts[0].param.detach().cpu(), 1.5, size[2:]), -1, 1)
+    ref = orc.warp(x, grid_cf=field, interp="bicubic")
+    theta = ts[1].affine_matrix.detach().cpu()
+    ref = orc.warp(ref, theta=theta, interp="bicubic")
+    assert rel_err(out, ref) < 5e-5
+    ops = _ops()
+    s3 = torch.rand(1, 1, 8, 8, 8, device=_dev())
+    th3 = torch.eye(3, 4, device=_dev()).unsqueeze(0)
+    with pytest.raises(RuntimeError):
+        ops.WarpAffine.apply(s3, th3, 0, ops.parse_interp("bicubic"), None)
+
+
 @pytest.mark.parametrize("d", [2, 3])
 @pytest.mark.parametrize("pscale", [1.0, 0.5])
 def test_affine_theta(d, pscale):
