@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadvchain_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
 INTERP_LINEAR, INTERP_NEAREST, INTERP_BICUBIC = 0, 1, 2
@@ -96,8 +96,8 @@ SIGNATURES = {
     "advk_chain_apply_fwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_chain_apply_bwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_loss_scratch_floats": (_Z, [_G, _I]),
-    "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _I, _P, _P, _P]),
-    "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _P, _P, _P, _P]),
+    "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _F, _I, _P, _P, _P]),
+    "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _F, _I, _P, _P, _P, _P]),
     "advk_pgd_update": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P]),
     "advk_pgd_update_guarded": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P, _P]),
     "advk_morph_tune": (_I, [_I]),

@@ -463,10 +463,10 @@ def run_chain(src, stages, clamp=None, mask_src=None, want_mask=False, binarize=
 
 
 class ConsistencyLoss(Function):
-    """calc_segmentation_consistency (common/loss.py:8-87) for scales=[0], types mse/contour."""
+    """calc_segmentation_consistency (common/loss.py:8-87) for scales=[0], types mse/contour/kl."""
 
     @staticmethod
-    def forward(ctx, output, reference, mask, w_mse, w_contour, is_gt):
+    def forward(ctx, output, reference, mask, w_mse, w_contour, is_gt, w_kl=0.0):
         output, reference = _f32c(output), _f32c(reference.detach())
         g = _lib.geom(output.shape)
         k = output.shape[1]
@@ -476,20 +476,20 @@ class ConsistencyLoss(Function):
         scratch = torch.empty(int(n), dtype=torch.float32, device=output.device)
         loss = torch.empty((), dtype=torch.float32, device=output.device)
         call("advk_consistency_loss_fwd", C.byref(g), k, ptr(output), ptr(reference), ptr(mask),
-             float(w_mse), float(w_contour), 1 if is_gt else 0, ptr(scratch), ptr(loss), stream())
+             float(w_mse), float(w_contour), float(w_kl), 1 if is_gt else 0, ptr(scratch), ptr(loss), stream())
         ctx.save_for_backward(scratch, mask)
-        ctx.meta = (g, k, float(w_mse), float(w_contour), output.shape)
+        ctx.meta = (g, k, float(w_mse), float(w_contour), float(w_kl), 1 if is_gt else 0, output.shape)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_loss):
         scratch, mask = ctx.saved_tensors
-        g, k, w_mse, w_contour, shape = ctx.meta
+        g, k, w_mse, w_contour, w_kl, is_gt, shape = ctx.meta
         g_out = torch.empty(shape, dtype=torch.float32, device=scratch.device)
-        call("advk_consistency_loss_bwd", C.byref(g), k, ptr(mask), w_mse, w_contour, ptr(scratch),
+        call("advk_consistency_loss_bwd", C.byref(g), k, ptr(mask), w_mse, w_contour, w_kl, is_gt, ptr(scratch),
              ptr(_f32c(g_loss).reshape(1)), ptr(g_out), stream())
-        return g_out, None, None, None, None, None
+        return g_out, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- glue

@@ -1,8 +1,8 @@
 """Consistency loss the solver calls every inner step (reference: advchain/common/loss.py:8-249).
 
-On CUDA tensors the default configuration of the solver -- scales=[0], divergence types 'mse'
-and/or 'contour', a channel-uniform mask -- runs in the fused advk_consistency_loss_* kernels
-(SURVEY.md section 8f rank f1).  Everything else ('kl', multi-scale, per-channel masks, CPU tensors)
+On CUDA tensors the single-scale configurations of the solver -- scales=[0], divergence types 'mse',
+'contour' and/or 'kl', a channel-uniform mask -- run in the fused advk_consistency_loss_* kernels
+(SURVEY.md section 8f rank f1).  Everything else (multi-scale, per-channel masks, CPU tensors)
 takes the plain PyTorch formulation below, written to reproduce the reference's numbers
 including its quirks -- Q9 (the 'mse' term is divided a second time by N*S) and Q10 (3-D contour
 loss uses the x-kernel for y and the last-assigned kernel for z).
@@ -66,7 +66,7 @@ def _fusable(output, reference, divergence_types, divergence_weights, scales, ma
         return False
     if len(divergence_types) != len(divergence_weights) or not divergence_types:
         return False
-    if any(t not in ('mse', 'contour') for t in divergence_types):
+    if any(t not in ('mse', 'contour', 'kl') for t in divergence_types):
         return False
     if reference.requires_grad and torch.is_grad_enabled():
         return False                      # the fused backward only produces dL/d(output)
@@ -86,10 +86,10 @@ def calc_segmentation_consistency(output, reference, divergence_types=['kl', 'co
         raise NotImplementedError
     if _fusable(output, reference, divergence_types, divergence_weights, scales, mask):
         from ..augmentor import _ops
-        w = {'mse': 0.0, 'contour': 0.0}
+        w = {'mse': 0.0, 'contour': 0.0, 'kl': 0.0}
         for name, weight in zip(divergence_types, divergence_weights):
             w[name] += float(weight)
-        return _ops.ConsistencyLoss.apply(output, reference, mask, w['mse'], w['contour'], bool(is_gt))
+        return _ops.ConsistencyLoss.apply(output, reference, mask, w['mse'], w['contour'], bool(is_gt), w['kl'])
     num_classes = reference.size(1)
     spatial_dims = output.dim() - 2
     assert spatial_dims in (2, 3), 'only support 2d or 3d segmentation'

@@ -7,6 +7,8 @@
 //   pred = softmax(output), tgt = softmax(reference) (or reference itself when is_gt)
 //   E_c  = pred_c - tgt_c
 //   mse      = sum_c sum_p (m E_c)^2 / (N K S) / (N S)                       (quirk Q9)
+//   kl       = sum_p m sum_c p_c (log p_c - log_softmax(output)_c) / (N S)   (common/loss.py:223-249;
+//              p = softmax(reference), or where(reference == 0, 1e-8, 1 - 1e-8) when is_gt)
 //   contour  = 1/(K-1) sum_{c>=1} 1/nk sum_k  sum_p (m (k * E_c))^2 / (N S)
 //              k in {sobel_x, sobel_y} (2-D) | {gx, gx, gz} (3-D, quirk Q10: gy := gx)
 // The Sobel correlation is linear, so conv(pred) - conv(tgt) = conv(E): one stencil per class.
@@ -25,12 +27,12 @@ __device__ __forceinline__ float sob_hp(int o) { return (float)(-o); }          
 
 __global__ void __launch_bounds__(256)
 loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const float* __restrict__ ref,
-                    const float* __restrict__ mask, int is_gt, float* __restrict__ E,
+                    const float* __restrict__ mask, int is_gt, int want_kl, float* __restrict__ E,
                     float* __restrict__ pred, double* __restrict__ acc) {
-  __shared__ float red[32];
+  __shared__ float red[64];
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  float v[1] = {0.f};
+  float v[2] = {0.f, 0.f};
   if (p < S) {
     const float* o = out + (i64)n * K * S + p;
     const float* r = ref + (i64)n * K * S + p;
@@ -39,7 +41,8 @@ loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const fl
     float so = 0.f, sr = 0.f;
     for (int c = 0; c < K; ++c) { so += expf(o[c * S] - mo); sr += expf(r[c * S] - mr); }
     const float m = mask ? mask[(i64)n * S + p] : 1.f;
-    float s = 0.f;
+    const float lso = logf(so), lsr = logf(sr);
+    float s = 0.f, plogp = 0.f, plogq = 0.f;
     for (int c = 0; c < K; ++c) {
       float pc = expf(o[c * S] - mo) / so;
       float tc = is_gt ? r[c * S] : expf(r[c * S] - mr) / sr;
@@ -49,11 +52,22 @@ loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const fl
       pred[q] = pc;
       float me = pc * m - tc * m;      // the reference masks both operands, then subtracts
       s += me * me;
+      if (want_kl) {                    // kl_divergence, common/loss.py:223-249
+        float pk, lpk;
+        if (is_gt) { pk = (r[c * S] == 0.f) ? 1e-8f : 1.f - 1e-8f; lpk = logf(pk); }
+        else { pk = tc; lpk = (r[c * S] - mr) - lsr; }
+        plogp += m * (pk * lpk);
+        plogq += m * (pk * ((o[c * S] - mo) - lso));
+      }
     }
     v[0] = s;
+    v[1] = plogp - plogq;
   }
-  block_sum<1>(v, red);
-  if (threadIdx.x == 0) atomicAdd(acc, (double)v[0]);
+  block_sum<2>(v, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc, (double)v[0]);
+    if (want_kl) atomicAdd(acc + 2, (double)v[1]);
+  }
 }
 
 // Sobel stencils through shared memory.  The 3x3(x3) kernels are products of the 1-D factors
@@ -193,17 +207,17 @@ loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, flo
   }
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont,
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont, float a_kl,
                                      float* __restrict__ loss) {
-  loss[0] = (float)((double)a_mse * acc[0] + (double)a_cont * acc[1]);
+  loss[0] = (float)((double)a_mse * acc[0] + (double)a_cont * acc[1] + (double)a_kl * acc[2]);
 }
 
 // g_pred_c = 2 A_mse m^2 E_c + 2 A_cont s_c  (s_c = contour adjoint, already in g_out for c >= 1);
 // g_out_c = pred_c (g_pred_c - sum_j g_pred_j pred_j) * upstream
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(i64 S, int K, const float* __restrict__ E, const float* __restrict__ pred,
-                 const float* __restrict__ mask, float a_mse, float a_cont, const float* __restrict__ upstream,
-                 float* __restrict__ g_out) {
+                 const float* __restrict__ mask, float a_mse, float a_cont, float a_kl, int is_gt,
+                 const float* __restrict__ upstream, float* __restrict__ g_out) {
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
@@ -218,30 +232,49 @@ loss_grad_kernel(i64 S, int K, const float* __restrict__ E, const float* __restr
     g_out[q] = gp;
     dot += gp * pred[q];
   }
+  // 'kl' differentiates straight to the logits: d/do_c = A_kl m (softmax(o)_c sum_j p_j - p_c)
+  float psum = 0.f;
+  if (a_kl != 0.f) {
+    q = (i64)n * K * S + p;
+    for (int c = 0; c < K; ++c, q += S) {
+      const float t = pred[q] - E[q];
+      psum += is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
+    }
+  }
   q = (i64)n * K * S + p;
-  for (int c = 0; c < K; ++c, q += S) g_out[q] = up * pred[q] * (g_out[q] - dot);
+  for (int c = 0; c < K; ++c, q += S) {
+    float go = pred[q] * (g_out[q] - dot);
+    if (a_kl != 0.f) {
+      const float t = pred[q] - E[q];
+      const float pk = is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
+      go += a_kl * m * (pred[q] * psum - pk);
+    }
+    g_out[q] = up * go;
+  }
 }
 
 }  // namespace advk
 
 using namespace advk;
 
-static void loss_scales(const Dims& g, int K, int d, float w_mse, float w_contour, float& a_mse, float& a_cont) {
+static void loss_scales(const Dims& g, int K, int d, float w_mse, float w_contour, float w_kl, float& a_mse,
+                        float& a_cont, float& a_kl) {
   double NS = (double)g.N * (double)g.S;
   a_mse = (float)((double)w_mse / (NS * K) / NS);
   a_cont = (K > 1) ? (float)((double)w_contour / (double)(K - 1) / (double)(d == 2 ? 2 : 3) / NS) : 0.f;
+  a_kl = (float)((double)w_kl / NS);
 }
 
 extern "C" size_t advk_loss_scratch_floats(const advk_geom* gg, int K) {
   Dims g;
   if (!make_dims(gg, g) || K < 1) return 0;
-  // E, pred: N*K*S each; R: N*(K-1)*2*S; 2 doubles (= 4 floats) of accumulators, 16-byte aligned slot
+  // E, pred: N*K*S each; R: N*(K-1)*2*S; 3 doubles (= 6 floats) of accumulators in a 32-byte slot
   return (size_t)((i64)g.N * g.S * (2 * K + 2 * (K - 1)) + 8);
 }
 
 extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float* output,
                                          const float* reference, const float* mask, float w_mse,
-                                         float w_contour, int is_gt, float* scratch, float* loss,
+                                         float w_contour, float w_kl, int is_gt, float* scratch, float* loss,
                                          void* stream) {
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
@@ -253,24 +286,24 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   float* E = scratch + 8;
   float* pred = E + NKS;
   float* R = pred + NKS;
-  float a_mse, a_cont;
-  loss_scales(g, K, gg->d, w_mse, w_contour, a_mse, a_cont);
-  cudaMemsetAsync(acc, 0, 2 * sizeof(double), st);
+  float a_mse, a_cont, a_kl;
+  loss_scales(g, K, gg->d, w_mse, w_contour, w_kl, a_mse, a_cont, a_kl);
+  cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
   dim3 grid(blocks_for(g.S, 256), g.N);
-  ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, E, pred, acc));
+  ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, w_kl != 0.f ? 1 : 0, E, pred, acc));
   if (K > 1 && w_contour != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
     if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<2><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
     else ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
   }
-  ADVK_LAUNCH(K_loss_finalize, st, loss_finalize_kernel<<<1, 1, 0, st>>>(acc, a_mse, a_cont, loss));
+  ADVK_LAUNCH(K_loss_finalize, st, loss_finalize_kernel<<<1, 1, 0, st>>>(acc, a_mse, a_cont, a_kl, loss));
   return check_launch("consistency_loss_fwd");
 }
 
 extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float* mask, float w_mse,
-                                         float w_contour, const float* scratch, const float* upstream,
-                                         float* g_output, void* stream) {
+                                         float w_contour, float w_kl, int is_gt, const float* scratch,
+                                         const float* upstream, float* g_output, void* stream) {
   Dims g;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(K >= 1 && scratch && g_output, "null pointer / bad K");
@@ -280,8 +313,8 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   const float* E = scratch + 8;
   const float* pred = E + NKS;
   const float* R = pred + NKS;
-  float a_mse, a_cont;
-  loss_scales(g, K, gg->d, w_mse, w_contour, a_mse, a_cont);
+  float a_mse, a_cont, a_kl;
+  loss_scales(g, K, gg->d, w_mse, w_contour, w_kl, a_mse, a_cont, a_kl);
   if (K <= 1) a_cont = 0.f;
   if (a_cont != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
@@ -290,6 +323,6 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
     else ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
   }
   dim3 grid(blocks_for(g.S, 256), g.N);
-  ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, upstream, g_output));
+  ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output));
   return check_launch("consistency_loss_bwd");
 }

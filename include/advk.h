@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ADVK_ABI_VERSION 1
+#define ADVK_ABI_VERSION 2
 
 enum { ADVK_OK = 0, ADVK_ERR_ARG = -1, ADVK_ERR_UNSUPPORTED = -2, ADVK_ERR_CUDA = -3 };
 enum { ADVK_PAD_ZEROS = 0, ADVK_PAD_BORDER = 1, ADVK_PAD_REFLECTION = 2 };
@@ -298,19 +298,20 @@ int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out, const flo
 
 /* ---- consistency loss -------------------------------------------
  * replaces calc_segmentation_consistency (common/loss.py:8-87) for scales=[0] and divergence
- * types 'mse' (:55-64, incl. the second division by N*S) and 'contour' (:65-79 -> contour_loss
- * :102-220, incl. the 3-D gy := gx kernel re-use); a weight of 0 disables a term.
+ * types 'mse' (:55-64, incl. the second division by N*S), 'contour' (:65-79 -> contour_loss
+ * :102-220, incl. the 3-D gy := gx kernel re-use) and 'kl' (:49-54 -> kl_divergence :223-249); a
+ * weight of 0 disables a term.
  * output, reference: N x K x S logits (reference is used as probabilities when is_gt != 0);
  * mask: N x S (one channel, broadcast over K) or NULL.  scratch: advk_loss_scratch_floats()
  * floats, 8-byte aligned; it carries the softmax / edge maps from fwd to bwd.  loss: 1 float
  * (device).  bwd: upstream = device pointer to dL/dloss (NULL = 1); g_output N x K x S, written. */
 size_t advk_loss_scratch_floats(const advk_geom* g, int K);
 int advk_consistency_loss_fwd(const advk_geom* g, int K, const float* output, const float* reference,
-                              const float* mask, float w_mse, float w_contour, int is_gt,
+                              const float* mask, float w_mse, float w_contour, float w_kl, int is_gt,
                               float* scratch, float* loss, void* stream);
 int advk_consistency_loss_bwd(const advk_geom* g, int K, const float* mask, float w_mse,
-                              float w_contour, const float* scratch, const float* upstream,
-                              float* g_output, void* stream);
+                              float w_contour, float w_kl, int is_gt, const float* scratch,
+                              const float* upstream, float* g_output, void* stream);
 
 /* ---- solver glue ------------------------------------------------------------------------
  * advk_clamp: out = clamp(x, lo, hi)   (solver.forward if_norm_image, adv_compose_solver.py:167-175)

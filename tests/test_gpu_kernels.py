@@ -352,7 +352,8 @@ LOSS = [(2, [2, 4, 37, 53]), (3, [2, 4, 11, 19, 23]), (3, [1, 3, 16, 16, 16]), (
 
 @pytest.mark.parametrize("d,size", LOSS)
 @pytest.mark.parametrize("types,weights", [(["mse", "contour"], [1.0, 0.5]), (["mse"], [1.0]),
-                                           (["contour"], [0.7])])
+                                           (["contour"], [0.7]), (["kl", "contour"], [1.0, 0.5]),
+                                           (["kl"], [0.8]), (["mse", "kl", "contour"], [1.0, 0.3, 0.5])])
 @pytest.mark.parametrize("masked", [False, True])
 @pytest.mark.parametrize("is_gt", [False, True])
 def test_consistency_loss(d, size, types, weights, masked, is_gt):
@@ -363,6 +364,8 @@ def test_consistency_loss(d, size, types, weights, masked, is_gt):
     ref = torch.randn(*size) * 2
     if is_gt:
         ref = torch.softmax(ref * 4, 1)
+        if "kl" in types:      # one-hot targets: exercises the where(reference == 0, 1e-8, 1 - 1e-8) branch
+            ref = torch.nn.functional.one_hot(ref.argmax(1), size[1]).movedim(-1, 1).float()
     mask = None
     if masked:
         mask = (torch.rand(size[0], 1, *size[2:]) > 0.3).float()
@@ -381,14 +384,23 @@ def test_consistency_loss(d, size, types, weights, masked, is_gt):
 
 
 def test_consistency_loss_fallbacks():
-    """'kl' and multi-scale stay on the PyTorch formulation and still agree with the oracle."""
+    """A per-channel (non channel-uniform) mask is outside the fused kernels' contract: the PyTorch
+    formulation takes over and agrees with the oracle.  scales > 0 fail like the reference (its full-size
+    mask is multiplied with the pooled predictions, common/loss.py:36-60)."""
+    from advchain_b200 import _lib
     from advchain_b200.common.loss import calc_segmentation_consistency
     torch.manual_seed(10)
     out, ref = torch.randn(2, 3, 24, 24), torch.randn(2, 3, 24, 24)
-    l0 = orc.consistency_loss(out, ref, ("kl", "contour"), (1.0, 0.5))
+    mask = (torch.rand(2, 3, 24, 24) > 0.3).float()
+    l0 = orc.consistency_loss(out, ref, ("kl", "contour"), (1.0, 0.5), mask)
+    _lib.launch_count("loss_softmax", reset=True)
     l1 = calc_segmentation_consistency(out.to(_dev()), ref.to(_dev()), divergence_types=["kl", "contour"],
-                                       divergence_weights=[1.0, 0.5], scales=[0])
+                                       divergence_weights=[1.0, 0.5], scales=[0], mask=mask.to(_dev()))
+    assert _lib.launch_count("loss_softmax") == 0
     assert abs(l1.item() - l0.item()) <= 2e-5 * abs(l0.item())
+    with pytest.raises(RuntimeError):
+        calc_segmentation_consistency(out.to(_dev()), ref.to(_dev()), divergence_types=["mse"],
+                                      divergence_weights=[1.0], scales=[0, 1])
 
 
 def test_no_cpu_fallback():
