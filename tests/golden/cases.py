@@ -46,4 +46,8 @@ CASES = {
     "c3d_morph_affine": dict(d=3, size=[1, 1, 24, 16, 32], chain=["morph", "affine"], n_iter=2,
                              K=4, seed=22, vector=[3, 2, 4]),
     "c3d_affine": dict(d=3, size=[2, 1, 12, 20, 16], chain=["affine"], n_iter=1, K=2, seed=23),
+    # power-iteration (VAT-style) training mode of every transform: xi-scaled probes, g -> unit(g)
+    "c2d_power": dict(d=2, size=[2, 1, 40, 48], chain=FULL, n_iter=2, K=4, seed=31, power=True),
+    "c3d_power": dict(d=3, size=[1, 1, 16, 20, 24], chain=FULL, n_iter=2, K=3, seed=32, power=True,
+                      vector=[2, 2, 3]),
 }

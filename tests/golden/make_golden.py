@@ -36,7 +36,8 @@ def build_reference(aug, case):
     cpu = torch.device("cpu")
     out = []
     for name in case["chain"]:
-        kw = dict(spatial_dims=d, config_dict=cfgs[name], use_gpu=False, device=cpu)
+        kw = dict(spatial_dims=d, config_dict=cfgs[name], use_gpu=False, device=cpu,
+                  power_iteration=bool(case.get("power", False)))
         if name == "noise":
             out.append(aug.AdvNoise(**kw))
         elif name == "bias":

@@ -41,7 +41,9 @@ def oracle_solver(case, size=None):
     stages = []
     for n in case["chain"]:
         kw = {"padding": pad} if n in ("morph", "affine") else {}
-        stages.append(orc.make_stage(n, cfgs[n], **kw))
+        st = orc.make_stage(n, cfgs[n], **kw)
+        st.power_iteration = bool(case.get("power", False))
+        stages.append(st)
     return orc.Solver(stages, if_norm_image=True)
 
 
@@ -54,15 +56,16 @@ def cuda_solver(case, device, size=None, **solver_kw):
     cfgs = stage_cfgs(d, size, vector=case.get("vector"))
     pad = case.get("padding", "zeros")
     chain = []
+    pw = bool(case.get("power", False))
     for n in case["chain"]:
         if n == "noise":
-            chain.append(AdvNoise(d, cfgs[n], device=device))
+            chain.append(AdvNoise(d, cfgs[n], power_iteration=pw, device=device))
         elif n == "bias":
-            chain.append(AdvBias(d, cfgs[n], device=device))
+            chain.append(AdvBias(d, cfgs[n], power_iteration=pw, device=device))
         elif n == "morph":
-            chain.append(AdvMorph(d, cfgs[n], image_padding_mode=pad, device=device))
+            chain.append(AdvMorph(d, cfgs[n], power_iteration=pw, image_padding_mode=pad, device=device))
         else:
-            chain.append(AdvAffine(d, cfgs[n], image_padding_mode=pad, device=device))
+            chain.append(AdvAffine(d, cfgs[n], power_iteration=pw, image_padding_mode=pad, device=device))
     kw = dict(divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5], if_norm_image=True)
     kw.update(solver_kw)
     return ComposeAdversarialTransformSolver(chain, **kw)
