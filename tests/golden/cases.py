@@ -50,4 +50,8 @@ CASES = {
     "c2d_power": dict(d=2, size=[2, 1, 40, 48], chain=FULL, n_iter=2, K=4, seed=31, power=True),
     "c3d_power": dict(d=3, size=[1, 1, 16, 20, 24], chain=FULL, n_iter=2, K=3, seed=32, power=True,
                       vector=[2, 2, 3]),
+    # anatomy-preserving branch of optimizing_transform (adv_compose_solver.py:329-338, 376-400): the
+    # thresholded round-trip score enters dist and the stop test; tolerance 1.0 -> exactly n_iter steps
+    "c2d_anatomy": dict(d=2, size=[2, 1, 40, 48], chain=["morph", "affine"], n_iter=1, K=4, seed=41,
+                        anatomy=True),
 }

@@ -102,9 +102,25 @@ def run_case(aug, name, case):
     solver.loss_fn = patched_loss
 
     steps = [STEP[n] for n in case["chain"]]
+    extra = {}
+    if case.get("anatomy"):
+        amask = (data > 0.5).float()
+        rec["anatomy_mask"] = amask
+        orig_anat = solver.compute_anatomy_misoverlapping_loss
+        scores = []
+
+        def patched_anat(anatomy_mask_images):
+            v = orig_anat(anatomy_mask_images=anatomy_mask_images)
+            scores.append(float(v))
+            return v
+        solver.compute_anatomy_misoverlapping_loss = patched_anat
+        extra = dict(anatomy_mask_images=amask, anatomy_reg_weight=50, volume_preserve_tolerance=1.0)
     solver.optimizing_transform(model=model, data=data, init_output=init_output,
                                 optimize_flags=[True] * len(transforms), n_iter=case["n_iter"],
-                                step_sizes=steps)
+                                step_sizes=steps, **extra)
+    if case.get("anatomy"):
+        solver.compute_anatomy_misoverlapping_loss = orig_anat
+        rec["anatomy_scores"] = torch.tensor(scores)
     solver.loss_fn = orig_loss
     for i, t in enumerate(transforms):
         rec["final_param_%d" % i] = t.param.detach().clone()

@@ -155,3 +155,43 @@ def test_cuda_graph_loop_matches_eager_loop(name):
         tol = 1e-3 if t.get_name() != "affine" else 0.25
         assert rel_err(b, a) < tol, (t.get_name(), rel_err(b, a))
     assert abs(results[0][2] - results[1][2]) <= 2e-2 * abs(results[0][2])
+
+
+def test_anatomy_preserving_branch_matches_reference():
+    """optimizing_transform with anatomy_mask_images (adv_compose_solver.py:329-338, 376-400): the
+    thresholded round-trip score of the anatomy mask is added to `dist` and decides when the loop stops.
+    The fixture was recorded from the reference with a tolerance that stops after n_iter steps, so the
+    loop is deterministic: same scores (before the step and at the stop test), same final parameters."""
+    dev = torch.device("cuda:0")
+    meta, z = load_golden("c2d_anatomy")
+    case = meta["case"]
+    model = make_model(case, z, dev)
+    sol = cuda_solver(case, dev)
+    data, init_out = z["data"].to(dev), z["init_output"].to(dev)
+    chain = sol.chain_of_transforms
+    for i, t in enumerate(chain):
+        t.init_parameters()
+        t.param = z["p0_%d" % i].to(dev)
+    amask = z["anatomy_mask"].to(dev)
+    scores = []
+    orig = sol.compute_anatomy_misoverlapping_loss
+
+    def rec(anatomy_mask_images):
+        v = orig(anatomy_mask_images=anatomy_mask_images)
+        scores.append(float(v))
+        return v
+    sol.compute_anatomy_misoverlapping_loss = rec
+    out = sol.optimizing_transform(model=model, data=data, init_output=init_out, optimize_flags=[True] * len(chain),
+                                   n_iter=case["n_iter"], step_sizes=meta["steps"], anatomy_mask_images=amask,
+                                   anatomy_reg_weight=50, volume_preserve_tolerance=1.0)
+    assert len(out) >= len(chain)
+    want = z["anatomy_scores"].tolist()
+    assert len(scores) == len(want)
+    for a, b in zip(scores, want):
+        assert abs(a - b) <= 2e-3, (scores, want)      # a thresholded mask: a few voxels may flip
+    # dist of the step = consistency loss + 50 * score
+    assert abs(float(sol.last_dist) - (z["s0_dist"].item() + 50 * want[0])) <= 0.11
+    for i, t in enumerate(chain):
+        tol = 0.25 if t.get_name() == "affine" else 2e-3         # sign step of the affine parameters
+        p1, p0 = t.param.detach().cpu(), z["final_param_%d" % i]
+        assert float((p1 - p0).norm() / p0.norm()) < tol, t.get_name()
