@@ -147,15 +147,16 @@ __device__ __forceinline__ void stage_coords(const Program& P, const Stage& s, c
     bx = base_coord_s(v.x, g.W, g.stW, 0.f); by = base_coord_s(v.y, g.H, g.stH, 0.f);
     if (DIM == 2) {
       const float* t = s.theta + v.n * 6;
-      cx = t[0] * bx + t[1] * by + t[2];
-      cy = t[3] * bx + t[4] * by + t[5];
+      // the K = 3 dot product of affine_grid's bmm, accumulated in order with one rounding per step
+      cx = __fadd_rn(__fmaf_rn(t[1], by, __fmul_rn(t[0], bx)), t[2]);
+      cy = __fadd_rn(__fmaf_rn(t[4], by, __fmul_rn(t[3], bx)), t[5]);
       cz = 0.f; bz = 0.f;
     } else {
       bz = base_coord_s(v.z, g.D, g.stD, 0.f);
       const float* t = s.theta + v.n * 12;
-      cx = t[0] * bx + t[1] * by + t[2] * bz + t[3];
-      cy = t[4] * bx + t[5] * by + t[6] * bz + t[7];
-      cz = t[8] * bx + t[9] * by + t[10] * bz + t[11];
+      cx = __fadd_rn(__fmaf_rn(t[2], bz, __fmaf_rn(t[1], by, __fmul_rn(t[0], bx))), t[3]);
+      cy = __fadd_rn(__fmaf_rn(t[6], bz, __fmaf_rn(t[5], by, __fmul_rn(t[4], bx))), t[7]);
+      cz = __fadd_rn(__fmaf_rn(t[10], bz, __fmaf_rn(t[9], by, __fmul_rn(t[8], bx))), t[11]);
     }
     rx = cx; ry = cy; rz = cz;
   }

@@ -37,15 +37,16 @@ __device__ __forceinline__ void sample_coords(const Dims& g, int n, int z, int y
     float bx = base_coord(x, g.W, 0.f), by = base_coord(y, g.H, 0.f);
     if (DIM == 2) {
       const float* t = theta + n * 6;
-      cx = t[0] * bx + t[1] * by + t[2];
-      cy = t[3] * bx + t[4] * by + t[5];
+      // the K = 3 dot product of affine_grid's bmm, accumulated in order with one rounding per step
+      cx = __fadd_rn(__fmaf_rn(t[1], by, __fmul_rn(t[0], bx)), t[2]);
+      cy = __fadd_rn(__fmaf_rn(t[4], by, __fmul_rn(t[3], bx)), t[5]);
       cz = 0.f;
     } else {
       float bz = base_coord(z, g.D, 0.f);
       const float* t = theta + n * 12;
-      cx = t[0] * bx + t[1] * by + t[2] * bz + t[3];
-      cy = t[4] * bx + t[5] * by + t[6] * bz + t[7];
-      cz = t[8] * bx + t[9] * by + t[10] * bz + t[11];
+      cx = __fadd_rn(__fmaf_rn(t[2], bz, __fmaf_rn(t[1], by, __fmul_rn(t[0], bx))), t[3]);
+      cy = __fadd_rn(__fmaf_rn(t[6], bz, __fmaf_rn(t[5], by, __fmul_rn(t[4], bx))), t[7]);
+      cz = __fadd_rn(__fmaf_rn(t[10], bz, __fmaf_rn(t[9], by, __fmul_rn(t[8], bx))), t[11]);
     }
     rx = cx; ry = cy; rz = cz;
   }

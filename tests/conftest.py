@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    try:
+        # parity is stated in fp32: keep the toy models of the tests out of TF32 (PyTorch lets cuDNN use
+        # TF32 for convolutions by default, which alone moves the logits by ~1e-4)
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

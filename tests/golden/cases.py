@@ -46,6 +46,8 @@ CASES = {
     "c3d_morph_affine": dict(d=3, size=[1, 1, 24, 16, 32], chain=["morph", "affine"], n_iter=2,
                              K=4, seed=22, vector=[3, 2, 4]),
     "c3d_affine": dict(d=3, size=[2, 1, 12, 20, 16], chain=["affine"], n_iter=1, K=2, seed=23),
+    # BASELINE.json configs[0]: 2-D 1x1x192x192, AdvAffine only, 1 PGD step (the notebook path)
+    "c1_affine192": dict(d=2, size=[1, 1, 192, 192], chain=["affine"], n_iter=1, K=4, seed=51),
     # power-iteration (VAT-style) training mode of every transform: xi-scaled probes, g -> unit(g)
     "c2d_power": dict(d=2, size=[2, 1, 40, 48], chain=FULL, n_iter=2, K=4, seed=31, power=True),
     "c3d_power": dict(d=3, size=[1, 1, 16, 20, 24], chain=FULL, n_iter=2, K=3, seed=32, power=True,

@@ -18,10 +18,12 @@ GRAD_TOL = 1e-4     # raw parameter gradients (fp32 atomics; the reference's CUD
 # (fp64) value of its algorithm (measured: 8e-5..2.5e-4 on outputs, up to 8e-3 on the morph
 # gradient, DESIGN.md "Parity").  The bound used below is therefore
 #     err(cuda, fixture) <= max(TOL, FLOOR_MULT * err(fixture, oracle_fp64))
-# i.e. the CUDA path may not be further from the reference than the reference is from its own
-# exact arithmetic.  tests/test_gpu_kernels.py holds the strict per-kernel 1e-5 checks on
+# i.e. the CUDA path may not be further from the reference than two independent fp32 evaluations of the
+# algorithm are from each other: |cuda - fixture| <= |cuda - exact| + |fixture - exact| ~ 2 x floor (the
+# fixtures come from ATen's CPU kernels, whose interpolation weights are formed as 1 - frac, while the
+# CUDA path follows ATen's CUDA kernels, (floor + 1) - x: the same algorithm, different roundings).  tests/test_gpu_kernels.py holds the strict per-kernel 1e-5 checks on
 # identical inputs, and the smooth-image cases below hold the end-to-end 1e-5 check.
-FLOOR_MULT = 1.5
+FLOOR_MULT = 2.0
 # Raw parameter gradients additionally contain discrete ties of the reference algorithm (border
 # clip masks decided by 1-ulp differences at the volume faces, in-bounds tests of the zero
 # padding; see tests/test_gpu_kernels.py::test_morph_field).  One realisation of the fp64 floor
