@@ -287,7 +287,9 @@ def workload_config(args, d, size, chain):
                         "loss mse+contour" % (args.workload, d, "x".join(map(str, size)), "->".join(chain), d,
                                               K_CLASSES),
             "per_gpu_size": size, "chain": chain, "n_gpus": args.gpus,
-            "l2": "per-step working set (field levels 2 signs x 9 x 32 MB at 128^3) exceeds the 126 MB L2; no flush"}
+            "l2": "per-step working set (field levels 2 signs x 9 x 32 MB at 128^3) exceeds the 126 MB L2; no flush",
+            "model_precision": "the toy model runs under PyTorch defaults (cuDNN may pick TF32 convolution "
+                               "kernels); every advk kernel computes in fp32"}
 
 
 # ----------------------------------------------------------------------------------- GPU arm
