@@ -478,7 +478,9 @@ def run_b200(args):
         algo_bytes = ALGO_WORDS[dom](d) * 4.0 * nvox
         achieved = algo_bytes / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic_bytes(dom), "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": ncu_traffic_bytes(dom) if args.workload == "m128" else None,   # captured on m128 only
+                "peak_source": peak_src,
                 "algo_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms,
                 "launches_timed": len(dom_ms),
                 "kernel_share_of_step": sum(dom_ms) / ms_eager if ms_eager > 0 else None,
