@@ -543,6 +543,7 @@ class ComposeAdversarialTransformSolver(object):
                 t.is_training = False
             for t in morph3d:
                 t._last_nb_steps = None
+            self.graph_redos = getattr(self, "graph_redos", 0) + 1
             return False
         for t, n in zip(morph3d, nsteps):
             t._last_nb_steps = n

@@ -197,3 +197,44 @@ def test_anatomy_preserving_branch_matches_reference():
         tol = 0.25 if t.get_name() == "affine" else 2e-3         # sign step of the affine parameters
         p1, p0 = t.param.detach().cpu(), z["final_param_%d" % i]
         assert float((p1 - p0).norm() / p0.norm()) < tol, t.get_name()
+
+
+def test_graph_loop_redoes_eagerly_when_the_3d_step_count_changes():
+    """adv_morph.py:159-162: in 3-D the number of squaring steps follows the norm of the velocity field,
+    which grows during the PGD loop.  The captured loop runs with a fixed count and verifies the rule on
+    the device; when a replay violates it the whole loop is redone eagerly -- same result as the eager
+    loop, and the redo is counted."""
+    from advchain_b200.augmentor import AdvMorph, ComposeAdversarialTransformSolver
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [1, 1, 24, 24, 24]
+    cfg = stage_cfgs(3, size, vector=[3, 3, 3])["morph"]
+    torch.manual_seed(3)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv3d(1, 3, 3, 1, 1).eval().to(dev)
+    probe = AdvMorph(3, dict(cfg), device=dev)
+    probe.init_parameters()
+    v0 = probe.param.detach().clone()
+    # pick epsilon so that ||u|| / 2^8 sits just below the 0.5 threshold at the start of the loop
+    probe.epsilon = 1.0
+    from advchain_b200.augmentor import _ops
+    n2 = float(_ops.morph_unorm2(v0, size, probe._morph_cfg(), 1.0).item()) ** 0.5
+    eps = 0.47 * 256.0 / n2
+    outs, redos = [], []
+    for graph in (False, True):
+        c = dict(cfg)
+        c["epsilon"] = eps
+        t = AdvMorph(3, c, device=dev)
+        sol = ComposeAdversarialTransformSolver([t], divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = graph
+        init = sol.get_init_output(conv, x)
+        t.init_parameters()
+        t.param = v0.clone()
+        assert t._nb_steps() == 8
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True], n_iter=3,
+                                 step_sizes=[1.0])
+        outs.append(t.param.detach().clone())
+        redos.append(getattr(sol, "graph_redos", 0))
+    assert redos == [0, 1], redos
+    assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
