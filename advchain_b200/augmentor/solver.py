@@ -10,6 +10,7 @@ zero to every parameter gradient), and all transform arit
 CUDA kernels.
 """
 import logging
+import os
 
 import torch
 
@@ -49,6 +50,7 @@ class ComposeAdversarialTransformSolver(object):
         self.shard = None                 # sharding.ShardContext: "exact-global" multi-GPU semantics
         self._graphs = {}
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
+        self.overlap_field_builds = os.environ.get("ADVK_OVERLAP_FIELDS", "1") != "0"   # graph loop only
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
     # ------------------------------------------------------------------ public entry points
@@ -424,9 +426,27 @@ class ComposeAdversarialTransformSolver(object):
             t.param = buf
             t.is_training = False
         self.make_learnable_transformation(optimize_flags=st["flags"], chain_of_transforms=chain)
+        side = None
+        if self.overlap_field_builds:
+            # the inverse-direction field phi(-v) is only needed by predict_backward: build it on a side
+            # stream beside [phi(+v) -> image chain -> model]; autograd then runs its backward on that
+            # stream too, beside [model dgrad -> image-chain adjoint -> phi(+v) backward]
+            morphs = [t for t in chain if isinstance(t, AdvMorph)]
+            if morphs:
+                try:        # the two field backwards meet in AccumulateGrad on different streams, by design
+                    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+                except AttributeError:
+                    pass
+                side = st.setdefault("side_stream", torch.cuda.Stream())
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for t in morphs:
+                        t._field(-1)
         augmented = self.forward(st["data"])
         with _disable_tracking_bn_stats(model):
             out = self.get_net_output(model, augmented)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         if self.if_contains_geo_transform(chain):
             warped = self.predict_backward(out)
             mask = self.valid_region_mask(st["init_output"])
