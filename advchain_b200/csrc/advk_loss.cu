@@ -103,6 +103,36 @@ __device__ __forceinline__ void stage_plane(float (*t)[LT_X + 2], const float* _
   }
 }
 
+// Register-prefetched variant for the z-marching loops: the (LT_Y+2)(LT_X+2) = 340 cells of a plane are
+// two per thread; `fetch` issues the global loads of the NEXT plane while the current one is consumed
+// from shared memory, `commit` stores them.
+struct PlaneRegs { float a, b; };
+__device__ __forceinline__ PlaneRegs fetch_plane(const float* __restrict__ src, const Dims& g, int pz, int x0, int y0) {
+  PlaneRegs r; r.a = 0.f; r.b = 0.f;
+  if (pz < 0 || pz >= g.D) return r;
+  {
+    const int i = threadIdx.x;
+    const int ly = i / (LT_X + 2), lx = i - ly * (LT_X + 2);
+    const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+    if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) r.a = __ldg(src + ((i64)pz * g.H + gy) * g.W + gx);
+  }
+  {
+    const int i = threadIdx.x + LT_X * LT_Y;
+    if (i < (LT_Y + 2) * (LT_X + 2)) {
+      const int ly = i / (LT_X + 2), lx = i - ly * (LT_X + 2);
+      const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+      if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) r.b = __ldg(src + ((i64)pz * g.H + gy) * g.W + gx);
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ void commit_plane(float (*t)[LT_X + 2], const PlaneRegs& r) {
+  float* flat = &t[0][0];
+  flat[threadIdx.x] = r.a;
+  const int i = threadIdx.x + LT_X * LT_Y;
+  if (i < (LT_Y + 2) * (LT_X + 2)) flat[i] = r.b;
+}
+
 // R has 2 planes per object class: [0] = the "x filter" response (2-D kx | 3-D gx, weight 2),
 // [1] = the other (2-D ky | 3-D gz); both already multiplied by mult * m^2 for the backward.
 template <int DIM>
@@ -140,10 +170,12 @@ loss_contour_kernel(Dims g, int K, int nzc, const float* __restrict__ E, const f
   } else {
     const int zb = zc * LT_Z, ze = min(g.D, zb + LT_Z);
     float wa[3] = {0.f, 0.f, 0.f}, wb[3] = {0.f, 0.f, 0.f};
+    PlaneRegs nxt = fetch_plane(e, g, zb - 1, x0, y0);
     for (int pz = zb - 1; pz <= ze; ++pz) {
       float (*t)[LT_X + 2] = tile[(pz - zb + 1) & 1];
-      stage_plane(t, e, g, pz, x0, y0);
+      commit_plane(t, nxt);
       __syncthreads();
+      if (pz < ze) nxt = fetch_plane(e, g, pz + 1, x0, y0);
       wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
       sobel_plane(t, tx, ty, wa[2], wb[2]);
       const int zo = pz - 1;
@@ -191,11 +223,13 @@ loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, flo
   } else {
     const int zb = zc * LT_Z, ze = min(g.D, zb + LT_Z);
     float wa[3] = {0.f, 0.f, 0.f}, wb[3] = {0.f, 0.f, 0.f};
+    PlaneRegs n0 = fetch_plane(r0, g, zb - 1, x0, y0), n1 = fetch_plane(r1, g, zb - 1, x0, y0);
     for (int pz = zb - 1; pz <= ze; ++pz) {
       const int buf = (pz - zb + 1) & 1;
-      stage_plane(tile[buf][0], r0, g, pz, x0, y0);
-      stage_plane(tile[buf][1], r1, g, pz, x0, y0);
+      commit_plane(tile[buf][0], n0);
+      commit_plane(tile[buf][1], n1);
       __syncthreads();
+      if (pz < ze) { n0 = fetch_plane(r0, g, pz + 1, x0, y0); n1 = fetch_plane(r1, g, pz + 1, x0, y0); }
       wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
       float dummy;
       sobel_plane(tile[buf][0], tx, ty, wa[2], dummy);       // hp(H) h(W) R0
