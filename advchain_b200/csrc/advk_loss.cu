@@ -25,27 +25,43 @@ namespace advk {
 __device__ __forceinline__ float sob_h(int o) { return o == 0 ? 2.f : 1.f; }      // o in {-1,0,1}
 __device__ __forceinline__ float sob_hp(int o) { return (float)(-o); }           // [1,0,-1]
 
+// KC > 0: class count known at compile time -> the logits of a voxel are loaded once into registers;
+// KC == 0: any K, re-reading them from L1.
+template <int KC>
 __global__ void __launch_bounds__(256)
-loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const float* __restrict__ ref,
+loss_softmax_kernel(i64 S, int N, int Krt, const float* __restrict__ out, const float* __restrict__ ref,
                     const float* __restrict__ mask, int is_gt, int want_kl, float* __restrict__ E,
                     float* __restrict__ pred, double* __restrict__ acc) {
   __shared__ float red[64];
+  const int K = KC > 0 ? KC : Krt;
+  constexpr int KA = KC > 0 ? KC : 1;
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   float v[2] = {0.f, 0.f};
   if (p < S) {
     const float* o = out + (i64)n * K * S + p;
     const float* r = ref + (i64)n * K * S + p;
+    float ov[KA], rv[KA];
+    if (KC > 0) {
+#pragma unroll
+      for (int c = 0; c < KA; ++c) { ov[c] = o[c * S]; rv[c] = r[c * S]; }
+    }
+#define LO(c) (KC > 0 ? ov[(KC > 0) ? (c) : 0] : o[(c) * S])
+#define LR(c) (KC > 0 ? rv[(KC > 0) ? (c) : 0] : r[(c) * S])
     float mo = -INFINITY, mr = -INFINITY;
-    for (int c = 0; c < K; ++c) { mo = fmaxf(mo, o[c * S]); mr = fmaxf(mr, r[c * S]); }
+#pragma unroll
+    for (int c = 0; c < K; ++c) { mo = fmaxf(mo, LO(c)); mr = fmaxf(mr, LR(c)); }
     float so = 0.f, sr = 0.f;
-    for (int c = 0; c < K; ++c) { so += expf(o[c * S] - mo); sr += expf(r[c * S] - mr); }
+#pragma unroll
+    for (int c = 0; c < K; ++c) { so += expf(LO(c) - mo); sr += expf(LR(c) - mr); }
     const float m = mask ? mask[(i64)n * S + p] : 1.f;
     const float lso = logf(so), lsr = logf(sr);
     float s = 0.f, plogp = 0.f, plogq = 0.f;
+#pragma unroll
     for (int c = 0; c < K; ++c) {
-      float pc = expf(o[c * S] - mo) / so;
-      float tc = is_gt ? r[c * S] : expf(r[c * S] - mr) / sr;
+      const float oc = LO(c), rc = LR(c);
+      float pc = expf(oc - mo) / so;
+      float tc = is_gt ? rc : expf(rc - mr) / sr;
       float e = pc - tc;
       i64 q = ((i64)n * K + c) * S + p;
       E[q] = e;
@@ -54,12 +70,14 @@ loss_softmax_kernel(i64 S, int N, int K, const float* __restrict__ out, const fl
       s += me * me;
       if (want_kl) {                    // kl_divergence, common/loss.py:223-249
         float pk, lpk;
-        if (is_gt) { pk = (r[c * S] == 0.f) ? 1e-8f : 1.f - 1e-8f; lpk = logf(pk); }
-        else { pk = tc; lpk = (r[c * S] - mr) - lsr; }
+        if (is_gt) { pk = (rc == 0.f) ? 1e-8f : 1.f - 1e-8f; lpk = logf(pk); }
+        else { pk = tc; lpk = (rc - mr) - lsr; }
         plogp += m * (pk * lpk);
-        plogq += m * (pk * ((o[c * S] - mo) - lso));
+        plogq += m * (pk * ((oc - mo) - lso));
       }
     }
+#undef LO
+#undef LR
     v[0] = s;
     v[1] = plogp - plogq;
   }
@@ -248,18 +266,48 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse
 
 // g_pred_c = 2 A_mse m^2 E_c + 2 A_cont s_c  (s_c = contour adjoint, already in g_out for c >= 1);
 // g_out_c = pred_c (g_pred_c - sum_j g_pred_j pred_j) * upstream
+template <int KC>
 __global__ void __launch_bounds__(256)
-loss_grad_kernel(i64 S, int K, const float* __restrict__ E, const float* __restrict__ pred,
+loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __restrict__ pred,
                  const float* __restrict__ mask, float a_mse, float a_cont, float a_kl, int is_gt,
                  const float* __restrict__ upstream, float* __restrict__ g_out) {
+  const int K = KC > 0 ? KC : Krt;
+  constexpr int KA = KC > 0 ? KC : 1;
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S) return;
   const float m = mask ? mask[(i64)n * S + p] : 1.f;
   const float up = upstream ? upstream[0] : 1.f;
   const float cm = 2.f * a_mse * m * m, cc = 2.f * a_cont;
+  const i64 q0 = (i64)n * K * S + p;
+  if (KC > 0) {
+    // everything of the voxel in registers: E, pred and the contour adjoint are read once, g_out written once
+    float e[KA], pr[KA], gp[KA];
+    float dot = 0.f, psum = 0.f;
+#pragma unroll
+    for (int c = 0; c < KA; ++c) {
+      const i64 q = q0 + (i64)c * S;
+      e[c] = E[q]; pr[c] = pred[q];
+      gp[c] = cm * e[c];
+      if (c >= 1 && a_cont != 0.f) gp[c] += cc * g_out[q];
+      dot += gp[c] * pr[c];
+      const float t = pr[c] - e[c];
+      psum += is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
+    }
+#pragma unroll
+    for (int c = 0; c < KA; ++c) {
+      float go = pr[c] * (gp[c] - dot);
+      if (a_kl != 0.f) {
+        const float t = pr[c] - e[c];
+        const float pk = is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
+        go += a_kl * m * (pr[c] * psum - pk);
+      }
+      g_out[q0 + (i64)c * S] = up * go;
+    }
+    return;
+  }
   float dot = 0.f;
-  i64 q = (i64)n * K * S + p;
+  i64 q = q0;
   for (int c = 0; c < K; ++c, q += S) {
     float gp = cm * E[q];
     if (c >= 1 && a_cont != 0.f) gp += cc * g_out[q];
@@ -269,13 +317,13 @@ loss_grad_kernel(i64 S, int K, const float* __restrict__ E, const float* __restr
   // 'kl' differentiates straight to the logits: d/do_c = A_kl m (softmax(o)_c sum_j p_j - p_c)
   float psum = 0.f;
   if (a_kl != 0.f) {
-    q = (i64)n * K * S + p;
+    q = q0;
     for (int c = 0; c < K; ++c, q += S) {
       const float t = pred[q] - E[q];
       psum += is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
     }
   }
-  q = (i64)n * K * S + p;
+  q = q0;
   for (int c = 0; c < K; ++c, q += S) {
     float go = pred[q] * (g_out[q] - dot);
     if (a_kl != 0.f) {
@@ -324,7 +372,17 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   loss_scales(g, K, gg->d, w_mse, w_contour, w_kl, a_mse, a_cont, a_kl);
   cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
   dim3 grid(blocks_for(g.S, 256), g.N);
-  ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, w_kl != 0.f ? 1 : 0, E, pred, acc));
+  const int wkl = w_kl != 0.f ? 1 : 0;
+#define ADVK_SOFTMAX(KC) ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<KC><<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, wkl, E, pred, acc))
+  switch (K) {
+    case 2: ADVK_SOFTMAX(2); break;
+    case 3: ADVK_SOFTMAX(3); break;
+    case 4: ADVK_SOFTMAX(4); break;
+    case 5: ADVK_SOFTMAX(5); break;
+    case 8: ADVK_SOFTMAX(8); break;
+    default: ADVK_SOFTMAX(0); break;
+  }
+#undef ADVK_SOFTMAX
   if (K > 1 && w_contour != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
@@ -357,6 +415,15 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
     else ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
   }
   dim3 grid(blocks_for(g.S, 256), g.N);
-  ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output));
+#define ADVK_LGRAD(KC) ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<KC><<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output))
+  switch (K) {
+    case 2: ADVK_LGRAD(2); break;
+    case 3: ADVK_LGRAD(3); break;
+    case 4: ADVK_LGRAD(4); break;
+    case 5: ADVK_LGRAD(5); break;
+    case 8: ADVK_LGRAD(8); break;
+    default: ADVK_LGRAD(0); break;
+  }
+#undef ADVK_LGRAD
   return check_launch("consistency_loss_bwd");
 }

@@ -347,7 +347,8 @@ def test_clamp_and_mask():
     assert torch.equal(got.cpu(), (m != 0).float())
 
 
-LOSS = [(2, [2, 4, 37, 53]), (3, [2, 4, 11, 19, 23]), (3, [1, 3, 16, 16, 16]), (2, [3, 2, 32, 48])]
+LOSS = [(2, [2, 4, 37, 53]), (3, [2, 4, 11, 19, 23]), (3, [1, 3, 16, 16, 16]), (2, [3, 2, 32, 48]),
+        (2, [1, 6, 20, 24]), (3, [1, 8, 8, 12, 16])]      # K = 6: run-time class count, K = 8: register path
 
 
 @pytest.mark.parametrize("d,size", LOSS)
