@@ -191,7 +191,7 @@ unorm2_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float* __restr
   if (threadIdx.x == 0) atomicAdd(out, v[0]);
 }
 
-// Row-wise version of the two kernels above: a CTA owns 8 rows x 32 voxels of one z-plane.  The z and
+// Row-wise version of the two kernels above: a CTA owns 8 whole rows of one z-plane.  The z and
 // y interpolation weights are shared by a whole row, so the CTA first reduces the lattice to one line
 // of Wl values per (channel, row) in shared memory and every voxel only interpolates along x
 // (2 shared reads per channel instead of 2^d global ones; ~35 instead of ~150 instructions per voxel).
@@ -206,7 +206,7 @@ init_phi0_rows_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int z = (DIM == 3) ? blockIdx.z % g.D : 0;
   const int n = (DIM == 3) ? blockIdx.z / g.D : blockIdx.z;
-  const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
+  const int y = blockIdx.y * 8 + ty;
   const int lr = c.Dl * c.Hl * c.Wl;
   UpAxis uz;
   if (DIM == 3) uz = up_axis(z, c.Dl, c.sD);
@@ -227,16 +227,20 @@ init_phi0_rows_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float 
   }
   __syncthreads();
   float v[1] = {0.f};
-  if (x < g.W && y < g.H) {
-    const UpAxis ux = up_axis(x, c.Wl, c.sW);
-    float u[3] = {0.f, 0.f, 0.f};
+  if (y < g.H) {
+    // the CTA owns whole rows: the lattice lines above are shared by every x of the row
+    const float by = base_coord_s(y, g.H, g.stH), bz = (DIM == 3) ? base_coord_s(z, g.D, g.stD) : 0.f;
+    const i64 rowp = (i64)n * g.S + ((i64)z * g.H + y) * g.W;
+    for (int x = tx; x < g.W; x += 32) {
+      const UpAxis ux = up_axis(x, c.Wl, c.sW);
+      float u[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ch = 0; ch < DIM; ++ch) u[ch] = ux.l0 * rowbuf[ch][ty][ux.i0] + ux.l1 * rowbuf[ch][ty][ux.i1];
-    v[0] = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-    if (phi0)
-      phi0[(i64)n * g.S + ((i64)z * g.H + y) * g.W + x] =
-          V<DIM>::make(base_coord_s(x, g.W, g.stW) + u[0] * inv2n, base_coord_s(y, g.H, g.stH) + u[1] * inv2n,
-                       (DIM == 3 ? base_coord_s(z, g.D, g.stD) + u[2] * inv2n : 0.f));
+      for (int ch = 0; ch < DIM; ++ch) u[ch] = ux.l0 * rowbuf[ch][ty][ux.i0] + ux.l1 * rowbuf[ch][ty][ux.i1];
+      v[0] += u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+      if (phi0)
+        phi0[rowp + x] = V<DIM>::make(base_coord_s(x, g.W, g.stW) + u[0] * inv2n, by + u[1] * inv2n,
+                                      (DIM == 3 ? bz + u[2] * inv2n : 0.f));
+    }
   }
   if (norm2) {
     block_sum<1>(v, red);
@@ -250,7 +254,7 @@ static void launch_init_phi0(const MorphCfg& c, const Dims& g, const float* u_lr
   typedef typename V<DIM>::T T;
   const i64 gz = (DIM == 3) ? (i64)g.N * g.D : g.N;
   if (c.Wl <= LRW_MAX && gz <= 65535) {
-    dim3 grid((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)gz);
+    dim3 grid(1, (g.H + 7) / 8, (unsigned)gz);
     ADVK_LAUNCH(phi0 ? K_init_phi0 : K_unorm2, st, init_phi0_rows_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, (T*)phi0, norm2));
   } else {
     dim3 grid(blocks_for(g.S, 256), g.N);
