@@ -1,0 +1,105 @@
+"""Two-GPU (NCCL) end-to-end check of exact-global batch sharding: two ranks, each running the CUDA
+inner loop on its half of the batch with a ShardContext, reproduce the parameters and the loss of the
+unsharded loop on one GPU.  Needs >= 2 CUDA devices; skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _build(d, size, dev):
+    from advchain_b200.augmentor import (AdvAffine, AdvBias, AdvMorph, AdvNoise,
+                                         ComposeAdversarialTransformSolver)
+    from tests.golden.cases import stage_cfgs
+    cfgs = stage_cfgs(d, size, vector=[3] * d)
+    ts = [AdvNoise(d, cfgs["noise"], device=dev), AdvBias(d, cfgs["bias"], device=dev),
+          AdvMorph(d, cfgs["morph"], device=dev), AdvAffine(d, cfgs["affine"], device=dev)]
+    return ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                             if_norm_image=True)
+
+
+def _worker(rank, world, port, d, gsize, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from advchain_b200.augmentor.sharding import ShardContext
+        torch.backends.cudnn.allow_tf32 = False
+        torch.manual_seed(0)                                   # every rank builds the same global problem
+        data = (torch.rand(*gsize) * 1.5 - 0.2)
+        conv = (torch.nn.Conv2d if d == 2 else torch.nn.Conv3d)(1, 4, 3, 1, 1).eval()
+        full = _build(d, gsize, dev)
+        for t in full.chain_of_transforms:
+            t.init_parameters()
+        start = [t.param.detach().cpu().clone() for t in full.chain_of_transforms]
+        conv = conv.to(dev)
+        ctx = ShardContext(gsize[0])
+        sl = ctx.local
+        lsize = [sl.stop - sl.start] + list(gsize[1:])
+        sol = _build(d, lsize, dev)
+        sol.shard = ctx
+        x = data[sl].to(dev)
+        init = sol.get_init_output(conv, x)
+        for t, p in zip(sol.chain_of_transforms, start):
+            t.init_parameters()
+            t.param = p[sl].to(dev).clone()
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True] * 4, n_iter=1,
+                                 step_sizes=[1.0] * 4)
+        res = {"rank": rank, "slice": (sl.start, sl.stop), "dist": float(sol.last_dist),
+               "params": [t.param.detach().cpu() for t in sol.chain_of_transforms]}
+        if rank == 0:                                          # the unsharded loop on one GPU
+            xf = data.to(dev)
+            initf = full.get_init_output(conv, xf)
+            for t, p in zip(full.chain_of_transforms, start):
+                t.param = p.to(dev).clone()
+            full.optimizing_transform(model=conv, data=xf, init_output=initf, optimize_flags=[True] * 4, n_iter=1,
+                                      step_sizes=[1.0] * 4)
+            res["full_dist"] = float(full.last_dist)
+            res["full_params"] = [t.param.detach().cpu() for t in full.chain_of_transforms]
+        q.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("d,gsize", [(2, [4, 1, 48, 64]), (3, [2, 1, 24, 24, 32])])
+def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, d, gsize, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    results.sort(key=lambda r: r["rank"])
+    ref = results[0]
+    # the all-reduced loss of the shards is the whole-batch loss
+    for r in results:
+        assert abs(r["dist"] - ref["full_dist"]) <= 2e-5 * abs(ref["full_dist"]), (r["dist"], ref["full_dist"])
+    names = ["noise", "bias", "morph", "affine"]
+    for i, name in enumerate(names):
+        got = torch.cat([r["params"][i] for r in results], 0)
+        want = ref["full_params"][i]
+        tol = 0.25 if name == "affine" else 2e-3          # sign step of the affine parameters may flip at |g| ~ 0
+        assert float((got - want).norm() / want.norm()) < tol, name
