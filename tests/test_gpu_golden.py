@@ -238,3 +238,39 @@ def test_graph_loop_redoes_eagerly_when_the_3d_step_count_changes():
         redos.append(getattr(sol, "graph_redos", 0))
     assert redos == [0, 1], redos
     assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_nan_loss_skips_the_update(graph):
+    """adv_compose_solver.py:345-346: a NaN / Inf consistency loss skips backward and the parameter
+    updates of that step.  The eager loop tests the loss on the host, the graph loop on the device
+    (advk_pgd_update_guarded): either way the parameters only go through the final rescale."""
+    from advchain_b200.augmentor import AdvMorph, AdvNoise, ComposeAdversarialTransformSolver
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [2, 1, 32, 40]
+    cfgs = stage_cfgs(2, size)
+    ts = [AdvNoise(2, cfgs["noise"], device=dev), AdvMorph(2, cfgs["morph"], device=dev)]
+    sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                            if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+    sol.use_cuda_graph = graph
+    torch.manual_seed(13)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv2d(1, 3, 3, 1, 1).eval().to(dev)
+    init = sol.get_init_output(conv, x)
+    bad_init = init.clone()
+    bad_init[0, 0, 3, 4] = float("nan")                     # poisons the loss, not the transforms
+    sol.init_random_transformation()
+    start = [t.param.detach().clone() for t in ts]
+    sol.optimizing_transform(model=conv, data=x, init_output=bad_init, optimize_flags=[True, True], n_iter=2,
+                             step_sizes=[1.0, 1.0])
+    assert not torch.isfinite(sol.last_dist)
+    for t, p0 in zip(ts, start):
+        assert torch.isfinite(t.param).all()
+        want = p0 / (p0.reshape(p0.shape[0], -1).norm(dim=1).view(-1, *([1] * (p0.dim() - 1))) + 1e-20)
+        assert rel_err(t.param, want) < 1e-6, t.get_name()  # unchanged up to the final unit re-normalisation
+    # and the same solver keeps working with a clean reference afterwards
+    sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True, True], n_iter=1,
+                             step_sizes=[1.0, 1.0])
+    assert torch.isfinite(sol.last_dist)
+    assert any(rel_err(t.param, p0) > 1e-3 for t, p0 in zip(ts, start))
