@@ -463,11 +463,75 @@ class ComposeAdversarialTransformSolver(object):
                 finally:
                     t._guard = None
                 buf.copy_(t.param.detach())
+        if st.get("want_norm"):
+            # norm of the velocity field the NEXT iteration will integrate (3-D step rule, adv_morph.py:
+            # 159-162): the host reads it between replays and picks the graph captured for that count
+            for j, t in enumerate(t_ for t_ in chain if isinstance(t_, AdvMorph) and t_.spatial_dims == 3):
+                buf = st["params"][chain.index(t)]
+                n2 = _ops.morph_unorm2(buf, t.data_size, t._morph_cfg(), t._scale())
+                st["norm2"][j:j + 1].copy_(n2.reshape(1))
         model.zero_grad()
 
+    @staticmethod
+    def _steps_from_norm2(norm2, min_steps):
+        """adv_morph.py:159-162: smallest n >= min_steps with ||u|| / 2^n <= 0.5."""
+        import math
+        nrm = math.sqrt(max(float(norm2), 0.0))
+        n = int(min_steps)
+        while nrm / (2.0 ** n) > 0.5:
+            n += 1
+        return n
+
+    def _capture_iteration(self, model, st, morph3d, nsteps, want_norm, start):
+        """Captures one PGD iteration for the given 3-D step counts into st["graphs"]; returns the entry or
+        None when the model / driver refuses capture."""
+        saved_range = (self.min_intensity, self.max_intensity)
+        if st["range"] is not None:
+            self.min_intensity, self.max_intensity = st["range"]  # bake the bounds, no aminmax in the graph
+        for t, n in zip(morph3d, nsteps):
+            t._fixed_steps = (n, st["viol"])
+        st["want_norm"] = want_norm
+        keep = [b.clone() for b in st["params"]]
+        entry = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._graph_iteration(model, st)                 # warm-up (allocator, cuDNN plans)
+            torch.cuda.current_stream().wait_stream(side)
+            for buf, p in zip(st["params"], keep):
+                buf.copy_(p)
+            graph = torch.cuda.CUDAGraph()
+            from .. import _lib
+            before = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                self._graph_iteration(model, st)
+            entry = (graph, _lib.launch_count() - before)
+            st["graphs"][(nsteps, want_norm)] = entry
+        except Exception as exc:                                 # model or driver refuses capture
+            logging.warning("advchain_b200: CUDA-graph capture failed (%s); running eagerly", exc)
+            torch.cuda.synchronize()
+            for buf, p in zip(st["params"], keep):
+                buf.copy_(p)
+        finally:
+            self.min_intensity, self.max_intensity = saved_range
+            st["viol"].zero_()
+            for t in morph3d:
+                t._fixed_steps = None
+                t._steps_cache = None
+        return entry
+
     def _optimize_with_graph(self, model, data, init_output, optimize_flags, n_iter, step_sizes):
-        """Runs the n_iter PGD iterations as replays of one captured CUDA graph.  Returns False when the
-        loop has to run eagerly (capture unsupported for this model, 3-D step-count rule violated)."""
+        """Runs the n_iter PGD iterations as replays of captured CUDA graphs.  Returns False when the loop
+        has to run eagerly (capture unsupported for this model, 3-D step count of the first iteration
+        different from the one assumed).
+
+        3-D step count (adv_morph.py:159-162): a graph is captured per count.  The first iteration of a
+        call assumes the count the previous call started with (verified on the device by
+        advk_morph_steps_check: one scalar read after the loop; mismatch -> eager redo); every further
+        iteration reads the norm the previous replay left behind (one scalar read per iteration) and
+        replays the graph captured for exactly that count, so a count that grows during a 5- or 10-step
+        loop costs a capture the first time, not a redo."""
         chain = self.chain_of_transforms
         if self.shard is not None:
             return False                 # the scalar all-reduces of exact-global mode run eagerly
@@ -483,64 +547,25 @@ class ComposeAdversarialTransformSolver(object):
         for t in morph3d:
             t._fixed_steps = None
             t._steps_cache = None
-        # The step count of the 3-D squaring rule needs a device reduction + a scalar read.  A loop that was
-        # already captured re-uses the count it last ran with (no host round trip before the replays);
-        # the device-side check of every replay (advk_morph_steps_check) reports if the rule now gives a
-        # different count, in which case the loop is redone eagerly below.
         nsteps = tuple(t._last_nb_steps if getattr(t, "_last_nb_steps", None) is not None else t._nb_steps()
                        for t in morph3d)
         rng = self._intensity_range(data) if self.if_norm_image else None
         key = (id(model), model.training, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
                float(step), tuple(id(t) for t in chain), tuple(t.power_iteration for t in chain),
-               tuple(tuple(t.param.shape) for t in chain), nsteps, rng, self.use_fused_chain,
+               tuple(tuple(t.param.shape) for t in chain), rng, self.use_fused_chain,
                tuple(self.divergence_types), tuple(self.divergence_weights))
         st = self._graphs.get(key)
+        if st is False:
+            return False
         start = [t.param.detach().clone() for t in chain]
         if st is None:
-            st = dict(flags=list(optimize_flags), step=step,
+            st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, want_norm=False,
                       data=data.detach().clone(), init_output=init_output.detach().clone(),
                       params=[p.clone() for p in start],
                       dist=torch.zeros(1, dtype=torch.float32, device=data.device),
-                      viol=torch.zeros(1, dtype=torch.int32, device=data.device))
-            saved_range = (self.min_intensity, self.max_intensity)
-            if rng is not None:
-                self.min_intensity, self.max_intensity = rng      # bake the bounds, no aminmax in the graph
-            for t, n in zip(morph3d, nsteps):
-                t._fixed_steps = (n, st["viol"])
-            try:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    self._graph_iteration(model, st)                 # warm-up (allocator, cuDNN plans)
-                torch.cuda.current_stream().wait_stream(side)
-                for buf, p in zip(st["params"], start):
-                    buf.copy_(p)
-                graph = torch.cuda.CUDAGraph()
-                from .. import _lib
-                before = _lib.launch_count()
-                with torch.cuda.graph(graph):
-                    self._graph_iteration(model, st)
-                st["graph"] = graph
-                st["advk_launches"] = _lib.launch_count() - before     # per replay
-                st["range"] = rng
-            except Exception as exc:                                 # model or driver refuses capture
-                logging.warning("advchain_b200: CUDA-graph capture failed (%s); running eagerly", exc)
-                torch.cuda.synchronize()
-                st = None
-            finally:
-                self.min_intensity, self.max_intensity = saved_range
-                for t in morph3d:
-                    t._fixed_steps = None
-                    t._steps_cache = None
-            if st is None:
-                for t, p in zip(chain, start):
-                    t.param = p
-                    t.is_training = False
-                self._graphs[key] = False
-                return False
+                      viol=torch.zeros(1, dtype=torch.int32, device=data.device),
+                      norm2=torch.zeros(max(len(morph3d), 1), dtype=torch.float32, device=data.device))
             self._graphs[key] = st
-        elif st is False:
-            return False
         st["data"].copy_(data.detach())
         # the clean prediction usually is the same tensor for every call of a training step: skip the
         # device-to-device refresh when neither its storage nor its version counter moved
@@ -551,20 +576,36 @@ class ComposeAdversarialTransformSolver(object):
         for buf, p in zip(st["params"], start):
             buf.copy_(p)
         st["viol"].zero_()
-        for _ in range(n_iter):
-            st["graph"].replay()
-        self.graph_replays = getattr(self, "graph_replays", 0) + n_iter
-        self.graph_launches_per_replay = st["advk_launches"]
-        self.last_dist = st["dist"][0]
-        if morph3d and int(st["viol"].item()) != 0:
-            # the 3-D step count changed during the loop: redo it eagerly from the start parameters
+        want_norm = bool(morph3d) and n_iter > 1
+        cur, launches = nsteps, 0
+
+        def fail():
             for t, p in zip(chain, start):
                 t.param = p
                 t.is_training = False
+            return False
+
+        for i in range(n_iter):
+            entry = st["graphs"].get((cur, want_norm))
+            if entry is None:
+                entry = self._capture_iteration(model, st, morph3d, cur, want_norm, start)
+                if entry is None:
+                    self._graphs[key] = False
+                    return fail()
+            entry[0].replay()
+            launches = entry[1]
+            if want_norm and i + 1 < n_iter:
+                vals = st["norm2"].tolist()                      # one scalar read: waits for the replay
+                cur = tuple(self._steps_from_norm2(v, t.num_steps) for v, t in zip(vals, morph3d))
+        self.graph_replays = getattr(self, "graph_replays", 0) + n_iter
+        self.graph_launches_per_replay = launches
+        self.last_dist = st["dist"][0]
+        if morph3d and int(st["viol"].item()) != 0:
+            # the count assumed for the first iteration was wrong: redo the loop eagerly from the start
             for t in morph3d:
                 t._last_nb_steps = None
             self.graph_redos = getattr(self, "graph_redos", 0) + 1
-            return False
+            return fail()
         for t, n in zip(morph3d, nsteps):
             t._last_nb_steps = n
         for t, buf in zip(chain, st["params"]):

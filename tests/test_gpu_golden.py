@@ -140,7 +140,7 @@ def test_cuda_graph_loop_matches_eager_loop(name):
                                  n_iter=1, step_sizes=[meta["steps"][0]] * len(chain))
         one = [t.param.detach().clone() for t in chain]
         if graph:
-            assert any(isinstance(v, dict) and "graph" in v for v in sol._graphs.values()), "no graph was captured"
+            assert any(isinstance(v, dict) and v.get("graphs") for v in sol._graphs.values()), "no graph was captured"
             assert getattr(sol, "graph_replays", 0) == 1
         # second call re-uses the captured graph with new start parameters
         for i, t in enumerate(chain):
@@ -199,12 +199,14 @@ def test_anatomy_preserving_branch_matches_reference():
         assert float((p1 - p0).norm() / p0.norm()) < tol, t.get_name()
 
 
-def test_graph_loop_redoes_eagerly_when_the_3d_step_count_changes():
+def test_graph_loop_follows_the_3d_step_count():
     """adv_morph.py:159-162: in 3-D the number of squaring steps follows the norm of the velocity field,
-    which grows during the PGD loop.  The captured loop runs with a fixed count and verifies the rule on
-    the device; when a replay violates it the whole loop is redone eagerly -- same result as the eager
-    loop, and the redo is counted."""
+    which grows during the PGD loop.  The graph loop reads that norm between replays and replays the graph
+    captured for exactly that count (no redo); the count ASSUMED for the first iteration of a later call
+    is verified on the device, and a stale one makes the loop redo itself eagerly.  Either way the result
+    is the eager loop's."""
     from advchain_b200.augmentor import AdvMorph, ComposeAdversarialTransformSolver
+    from advchain_b200.augmentor import _ops
     from tests.golden.cases import stage_cfgs
     dev = torch.device("cuda:0")
     size = [1, 1, 24, 24, 24]
@@ -216,11 +218,9 @@ def test_graph_loop_redoes_eagerly_when_the_3d_step_count_changes():
     probe.init_parameters()
     v0 = probe.param.detach().clone()
     # pick epsilon so that ||u|| / 2^8 sits just below the 0.5 threshold at the start of the loop
-    probe.epsilon = 1.0
-    from advchain_b200.augmentor import _ops
     n2 = float(_ops.morph_unorm2(v0, size, probe._morph_cfg(), 1.0).item()) ** 0.5
     eps = 0.47 * 256.0 / n2
-    outs, redos = [], []
+    outs, sols, ts = [], [], []
     for graph in (False, True):
         c = dict(cfg)
         c["epsilon"] = eps
@@ -235,9 +235,23 @@ def test_graph_loop_redoes_eagerly_when_the_3d_step_count_changes():
         sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True], n_iter=3,
                                  step_sizes=[1.0])
         outs.append(t.param.detach().clone())
-        redos.append(getattr(sol, "graph_redos", 0))
-    assert redos == [0, 1], redos
+        sols.append((sol, init))
+        ts.append(t)
+    gsol = sols[1][0]
+    assert getattr(gsol, "graph_redos", 0) == 0
+    assert getattr(gsol, "graph_replays", 0) == 3
+    counts = set(k[0] for v in gsol._graphs.values() if isinstance(v, dict) for k in v["graphs"])
+    assert len(counts) >= 2, counts                       # the count grew inside the loop: two graphs
     assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
+    # a later call whose start parameters need MORE steps than the last call started with
+    res = []
+    for (sol, init), t in zip(sols, ts):
+        t.param = (3.0 * v0).clone()
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True], n_iter=1,
+                                 step_sizes=[1.0])
+        res.append(t.param.detach().clone())
+    assert getattr(gsol, "graph_redos", 0) == 1
+    assert float((res[1] - res[0]).norm() / res[0].norm()) < 2e-3
 
 
 @pytest.mark.parametrize("graph", [False, True])
