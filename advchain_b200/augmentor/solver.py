@@ -9,6 +9,7 @@ every call, the valid-region mask computed forward-only on one channel (it contr
 zero to every parameter gradient), and all transform arithmetic in the advk_*
 CUDA kernels.
 """
+import collections
 import logging
 import os
 
@@ -23,6 +24,14 @@ from .morph import AdvMorph
 from .noise import AdvNoise
 
 _FUSABLE = (AdvNoise, AdvBias, AdvMorph, AdvAffine)
+
+
+# Captured PGD iterations, shared by every solver of the process.  The key holds everything the capture
+# baked in (model, shapes, chain objects, flags, step size, loss configuration, clamp range); an entry
+# owns its static buffers and the private memory pool of its graphs, so the cache is small and bounded.
+_GRAPH_CACHE = collections.OrderedDict()
+_GRAPH_CACHE_MAX = 8
+_GRAPH_SEEN = {}
 
 
 class ComposeAdversarialTransformSolver(object):
@@ -48,8 +57,9 @@ class ComposeAdversarialTransformSolver(object):
         self.use_fused_chain = True       # one advk_chain_apply launch per chain pass
         self.use_cuda_graph = False       # capture one PGD iteration in a CUDA graph and replay it
         self.shard = None                 # sharding.ShardContext: "exact-global" multi-GPU semantics
-        self._graphs = {}
+        self._graphs = _GRAPH_CACHE      # shared by all solvers: training loops build a solver per step
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
+        self.graph_capture_after = 1      # eager runs of a configuration before it is captured
         self.overlap_field_builds = os.environ.get("ADVK_OVERLAP_FIELDS", "1") != "0"   # graph loop only
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
@@ -557,6 +567,16 @@ class ComposeAdversarialTransformSolver(object):
         st = self._graphs.get(key)
         if st is False:
             return False
+        if st is None and self.graph_capture_after > 0:
+            # a configuration is captured the (graph_capture_after + 1)-th time it shows up: loops that
+            # sample a new sub-chain every step (README recipe, random_chain) would otherwise pay a
+            # capture (~0.1 s) for configurations they never see again
+            seen = _GRAPH_SEEN.get(key, 0)
+            if seen < self.graph_capture_after:
+                _GRAPH_SEEN[key] = seen + 1
+                if len(_GRAPH_SEEN) > 4096:
+                    _GRAPH_SEEN.clear()
+                return False
         start = [t.param.detach().clone() for t in chain]
         if st is None:
             st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, want_norm=False,
@@ -566,6 +586,8 @@ class ComposeAdversarialTransformSolver(object):
                       viol=torch.zeros(1, dtype=torch.int32, device=data.device),
                       norm2=torch.zeros(max(len(morph3d), 1), dtype=torch.float32, device=data.device))
             self._graphs[key] = st
+            while len(self._graphs) > _GRAPH_CACHE_MAX:          # least recently captured goes first
+                self._graphs.pop(next(iter(self._graphs)))
         st["data"].copy_(data.detach())
         # the clean prediction usually is the same tensor for every call of a training step: skip the
         # device-to-device refresh when neither its storage nor its version counter moved

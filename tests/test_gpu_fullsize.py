@@ -186,6 +186,7 @@ def test_graph_loop_equals_eager_loop_fullsize(name):
     for graph in (False, True):
         sol = _solver(d, size, chain)
         sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0       # capture at first sight (default: second)
         init = sol.get_init_output(conv, x)
         sol.init_random_transformation()
         if start is None:

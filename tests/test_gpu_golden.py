@@ -131,6 +131,7 @@ def test_cuda_graph_loop_matches_eager_loop(name):
     for graph in (False, True):
         sol = cuda_solver(case, dev, min_intensity=0.0, max_intensity=1.0)
         sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0       # capture at first sight (default: second)
         chain = sol.chain_of_transforms
         for i, t in enumerate(chain):
             t.init_parameters()
@@ -228,6 +229,7 @@ def test_graph_loop_follows_the_3d_step_count():
         sol = ComposeAdversarialTransformSolver([t], divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
                                                 if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
         sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0       # capture at first sight (default: second)
         init = sol.get_init_output(conv, x)
         t.init_parameters()
         t.param = v0.clone()
@@ -268,6 +270,7 @@ def test_nan_loss_skips_the_update(graph):
     sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
                                             if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
     sol.use_cuda_graph = graph
+    sol.graph_capture_after = 0       # capture at first sight (default: second)
     torch.manual_seed(13)
     x = torch.rand(*size, device=dev)
     conv = torch.nn.Conv2d(1, 3, 3, 1, 1).eval().to(dev)
@@ -288,3 +291,32 @@ def test_nan_loss_skips_the_update(graph):
                              step_sizes=[1.0, 1.0])
     assert torch.isfinite(sol.last_dist)
     assert any(rel_err(t.param, p0) > 1e-3 for t, p0 in zip(ts, start))
+
+
+def test_graph_cache_is_shared_and_captures_on_second_sight():
+    """Training loops build a new solver per step (README recipe): captured iterations live in a
+    process-wide, bounded cache keyed by everything a capture bakes in, and a configuration is captured
+    the second time it is seen, so one-off sub-chains never pay for a capture."""
+    from advchain_b200.augmentor import AdvAffine, AdvNoise, ComposeAdversarialTransformSolver
+    from advchain_b200.augmentor import solver as solver_mod
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [2, 1, 32, 40]
+    cfgs = stage_cfgs(2, size)
+    ts = [AdvNoise(2, cfgs["noise"], device=dev), AdvAffine(2, cfgs["affine"], device=dev)]
+    torch.manual_seed(17)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv2d(1, 3, 3, 1, 1).eval().to(dev)
+    replays = []
+    for it in range(3):
+        sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = True
+        init = sol.get_init_output(conv, x)
+        sol.init_random_transformation()
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True, True], n_iter=1,
+                                 step_sizes=[1.0, 1.0])
+        replays.append(getattr(sol, "graph_replays", 0))
+        assert torch.isfinite(sol.last_dist)
+    assert replays == [0, 1, 1], replays          # eager, capture + replay, replay from the shared cache
+    assert len(solver_mod._GRAPH_CACHE) <= solver_mod._GRAPH_CACHE_MAX
