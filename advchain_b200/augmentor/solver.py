@@ -11,6 +11,7 @@ CUDA kernels.
 """
 import collections
 import logging
+import weakref
 import os
 
 import torch
@@ -560,11 +561,20 @@ class ComposeAdversarialTransformSolver(object):
         nsteps = tuple(t._last_nb_steps if getattr(t, "_last_nb_steps", None) is not None else t._nb_steps()
                        for t in morph3d)
         rng = self._intensity_range(data) if self.if_norm_image else None
-        key = (id(model), model.training, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
+        # a captured graph holds raw pointers: the key carries the storage of every model parameter / buffer
+        # (in-place optimizer updates keep it, re-assigned tensors change it), and a hit is only taken when
+        # the model and the transforms are the very objects of the capture (ids can be recycled)
+        mptrs = tuple(p.data_ptr() for p in model.parameters()) + tuple(b.data_ptr() for b in model.buffers())
+        key = (id(model), model.training, mptrs, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
                float(step), tuple(id(t) for t in chain), tuple(t.power_iteration for t in chain),
                tuple(tuple(t.param.shape) for t in chain), rng, self.use_fused_chain,
                tuple(self.divergence_types), tuple(self.divergence_weights))
         st = self._graphs.get(key)
+        if isinstance(st, dict):
+            objs = [r() for r in st["refs"]]
+            if objs[0] is not model or any(o is not t for o, t in zip(objs[1:], chain)):
+                self._graphs.pop(key)                     # recycled id: the capture belongs to dead objects
+                st = None
         if st is False:
             return False
         if st is None and self.graph_capture_after > 0:
@@ -580,6 +590,7 @@ class ComposeAdversarialTransformSolver(object):
         start = [t.param.detach().clone() for t in chain]
         if st is None:
             st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, want_norm=False,
+                      refs=[weakref.ref(model)] + [weakref.ref(t) for t in chain],
                       data=data.detach().clone(), init_output=init_output.detach().clone(),
                       params=[p.clone() for p in start],
                       dist=torch.zeros(1, dtype=torch.float32, device=data.device),
