@@ -196,7 +196,7 @@ __device__ __forceinline__ float gather_corners(const Corners<DIM>& ct, const fl
   return acc + pv;
 }
 
-template <int DIM, bool FIELD>
+template <int DIM, bool FIELD, bool ZL>
 __device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
   unsigned t0, t1, dt;
@@ -207,7 +207,7 @@ __device__ void stage_warp_fwd(const Program& P, const Stage& s, bool last) {
     if (!v.ok) continue;
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
-    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, ZL ? (int)ADVK_PAD_ZEROS : s.pad, ZL ? (int)ADVK_INTERP_LINEAR : s.interp);
     Corners<DIM> ct;
     make_corners<DIM>(st, g, true, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
@@ -251,7 +251,7 @@ __device__ __forceinline__ float4 load_corner4(const Stage& s, bool packed, cons
   return make_float4(v.x - pv, v.y - pv, v.z - pv, v.w - pv);
 }
 
-template <int DIM, bool FIELD>
+template <int DIM, bool FIELD, bool ZL>
 __device__ void stage_warp_fwd_pk(const Program& P, const Stage& s, bool last) {
   const Dims& g = P.g;
   unsigned t0, t1, dt;
@@ -263,7 +263,7 @@ __device__ void stage_warp_fwd_pk(const Program& P, const Stage& s, bool last) {
     if (!v.ok) continue;
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
-    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, ZL ? (int)ADVK_PAD_ZEROS : s.pad, ZL ? (int)ADVK_INTERP_LINEAR : s.interp);
     Corners<DIM> ct;
     make_corners<DIM>(st, g, true, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
@@ -304,13 +304,17 @@ __device__ __forceinline__ void run_stage_fwd(const Program& P, int k) {
   const Stage& s = P.st[k];
   const bool last = (k == P.n - 1);
   if (PK) {
-    if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_fwd_pk<DIM, true>(P, s, last);
-    else stage_warp_fwd_pk<DIM, false>(P, s, last);
+    const bool zl = s.pad == ADVK_PAD_ZEROS && s.interp == ADVK_INTERP_LINEAR;    // the default configuration
+    if (s.kind == ADVK_STAGE_WARP_FIELD) { if (zl) stage_warp_fwd_pk<DIM, true, true>(P, s, last); else stage_warp_fwd_pk<DIM, true, false>(P, s, last); }
+    else { if (zl) stage_warp_fwd_pk<DIM, false, true>(P, s, last); else stage_warp_fwd_pk<DIM, false, false>(P, s, last); }
     return;
   }
   if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_fwd<DIM>(P, s, last);
-  else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_fwd<DIM, true>(P, s, last);
-  else stage_warp_fwd<DIM, false>(P, s, last);
+  else {
+    const bool zl = s.pad == ADVK_PAD_ZEROS && s.interp == ADVK_INTERP_LINEAR;
+    if (s.kind == ADVK_STAGE_WARP_FIELD) { if (zl) stage_warp_fwd<DIM, true, true>(P, s, last); else stage_warp_fwd<DIM, true, false>(P, s, last); }
+    else { if (zl) stage_warp_fwd<DIM, false, true>(P, s, last); else stage_warp_fwd<DIM, false, false>(P, s, last); }
+  }
 }
 
 template <int DIM, int MINB, bool PK>
@@ -385,7 +389,7 @@ __device__ void stage_intensity_bwd(const Program& P, const Stage& s, bool last)
 // contribution over and the RED count halves; the hand-off pattern is decided once per voxel and shared
 // by all channels.  The coordinate gradient sum_c (src_c - pv) * go_c is accumulated per corner and
 // turned into d/dx, d/dy, d/dz after the channel loop.
-template <int DIM, bool FIELD>
+template <int DIM, bool FIELD, bool ZL>
 __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, float* red) {
   constexpr int NG = DIM * (DIM + 1);
   constexpr int NC = Corners<DIM>::NC;
@@ -418,7 +422,7 @@ __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, floa
     // no early exit for !v.ok: the whole warp takes part in the shuffles below
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
-    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, ZL ? (int)ADVK_PAD_ZEROS : s.pad, ZL ? (int)ADVK_INTERP_LINEAR : s.interp);
     Corners<DIM> ct;
     make_corners<DIM>(st, g, v.ok, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
@@ -510,7 +514,7 @@ __device__ void stage_warp_bwd(const Program& P, const Stage& s, bool last, floa
   }
 }
 
-template <int DIM, bool FIELD>
+template <int DIM, bool FIELD, bool ZL>
 __device__ void stage_warp_bwd_pk(const Program& P, const Stage& s, bool last, float* red) {
   constexpr int NG = DIM * (DIM + 1);
   constexpr int NC = Corners<DIM>::NC;
@@ -544,7 +548,7 @@ __device__ void stage_warp_bwd_pk(const Program& P, const Stage& s, bool last, f
     }
     float cx, cy, cz, rx, ry, rz, bx, by, bz;
     stage_coords<DIM, FIELD>(P, s, v, cx, cy, cz, rx, ry, rz, bx, by, bz);
-    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, s.pad, s.interp);
+    Stencil<DIM> st = make_stencil<DIM>(cx, cy, cz, g, ZL ? (int)ADVK_PAD_ZEROS : s.pad, ZL ? (int)ADVK_INTERP_LINEAR : s.interp);
     Corners<DIM> ct;
     make_corners<DIM>(st, g, v.ok, ct);
     const float pv = s.pv ? s.pv[v.n] : 0.f;
@@ -672,13 +676,17 @@ __device__ __forceinline__ void run_stage_bwd(const Program& P, int k, float* re
   const Stage& s = P.st[k];
   const bool last = (k == P.n - 1);
   if (PK) {
-    if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_bwd_pk<DIM, true>(P, s, last, red);
-    else stage_warp_bwd_pk<DIM, false>(P, s, last, red);
+    const bool zl = s.pad == ADVK_PAD_ZEROS && s.interp == ADVK_INTERP_LINEAR;
+    if (s.kind == ADVK_STAGE_WARP_FIELD) { if (zl) stage_warp_bwd_pk<DIM, true, true>(P, s, last, red); else stage_warp_bwd_pk<DIM, true, false>(P, s, last, red); }
+    else { if (zl) stage_warp_bwd_pk<DIM, false, true>(P, s, last, red); else stage_warp_bwd_pk<DIM, false, false>(P, s, last, red); }
     return;
   }
   if (s.kind == ADVK_STAGE_INTENSITY) stage_intensity_bwd<DIM>(P, s, last);
-  else if (s.kind == ADVK_STAGE_WARP_FIELD) stage_warp_bwd<DIM, true>(P, s, last, red);
-  else stage_warp_bwd<DIM, false>(P, s, last, red);
+  else {
+    const bool zl = s.pad == ADVK_PAD_ZEROS && s.interp == ADVK_INTERP_LINEAR;
+    if (s.kind == ADVK_STAGE_WARP_FIELD) { if (zl) stage_warp_bwd<DIM, true, true>(P, s, last, red); else stage_warp_bwd<DIM, true, false>(P, s, last, red); }
+    else { if (zl) stage_warp_bwd<DIM, false, true>(P, s, last, red); else stage_warp_bwd<DIM, false, false>(P, s, last, red); }
+  }
 }
 
 template <int DIM, int MINB, bool PK>
