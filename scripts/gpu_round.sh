@@ -16,8 +16,16 @@ done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/${TAG}_launches.csv python scripts/one_step.py > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
 # one full capture per hot kernel family (2 launches each)
+# (gpurun brings back at most 64 MiB: the big chain kernels are captured without their source listing)
 for k in ss_step_bwd_kernel ss_step_kernel chain_bwd_kernel chain_fwd_kernel smooth3d_xy smooth3d_z loss_contour; do
-  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${k} -c 2 \
+  SRC="--import-source on"
+  case $k in chain_*) SRC="";; esac
+  timeout 600 ncu --set full --clock-control none $SRC --profile-from-start off -k regex:${k} -c 2 \
       -f -o gpurun_out/${TAG}_full_${k} python scripts/one_step.py > gpurun_out/${TAG}_ncu_full_${k}.log 2>&1; echo "ncu full ${k} rc=$?"
+  case $k in chain_*)      # 30 MB reports (the SASS of the multi-stage kernels): keep the raw metric page only
+    ncu -i gpurun_out/${TAG}_full_${k}.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${k}.csv 2>/dev/null
+    rm -f gpurun_out/${TAG}_full_${k}.ncu-rep;;
+  esac
 done
+du -sh gpurun_out
 ls -la gpurun_out | tail -30

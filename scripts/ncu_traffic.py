@@ -31,7 +31,8 @@ def main():
     tag, reps = sys.argv[1], sys.argv[2:]
     acc = collections.OrderedDict()
     for rep in reps:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = (open(rep).read() if rep.endswith(".csv") else
+                   subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
         kn, ir, iw, it = (hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"),

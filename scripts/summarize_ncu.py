@@ -62,7 +62,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def full():
     import glob
-    reps = sorted(glob.glob(os.path.join(G, tag + "_full_*.ncu-rep")))
+    reps = sorted(glob.glob(os.path.join(G, tag + "_full_*.ncu-rep")) + glob.glob(os.path.join(G, tag + "_full_*.csv")))
     legacy = os.path.join(G, tag + "_prof.ncu-rep")
     if os.path.exists(legacy):
         reps.append(legacy)
@@ -72,7 +72,8 @@ def full():
         f.write("# ncu --set full --clock-control none --import-source on (per launch; cold cache, serialised) -- %s\n\n" % tag)
         f.write("Workload m128 (1x1x128^3, full chain), `scripts/one_step.py`; one block per captured launch.\n\n")
         for rep in reps:
-            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            raw = (open(rep).read() if rep.endswith(".csv") else
+                   subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
             rows = list(csv.reader(raw.splitlines()))
             if len(rows) < 3:
                 continue
