@@ -79,7 +79,7 @@ SIGNATURES = {
     "advk_warp_field_fwd": (_I, [_G, _I, _P, _P, _I, _I, _P, _P, _P]),
     "advk_warp_field_bwd": (_I, [_G, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "advk_morph_unorm2": (_I, [_G, C.POINTER(MorphCfg), _P, _F, _P, _P, _P]),
-    "advk_morph_field_fwd": (_I, [_G, C.POINTER(MorphCfg), _P, _F, _I, _P, _P, _P, _P]),
+    "advk_morph_field_fwd": (_I, [_G, C.POINTER(MorphCfg), _P, _F, _I, _P, _P, _P, _P, _P]),
     "advk_morph_lr_scratch_floats": (_Z, [_G, C.POINTER(MorphCfg)]),
     "advk_morph_field_bwd": (_I, [_G, C.POINTER(MorphCfg), _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "advk_bias_lowfield_fwd": (_I, [C.POINTER(BiasCfg), _I, _P, _F, _P, _P]),

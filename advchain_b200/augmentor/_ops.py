@@ -164,7 +164,7 @@ class MorphField(Function):
     """velocity -> (unclamped) deformation field; DemonsCompose, adv_morph.py:454-491."""
 
     @staticmethod
-    def forward(ctx, v, size, cfg, scale, nb_steps):
+    def forward(ctx, v, size, cfg, scale, nb_steps, norm_out=None):
         v = _f32c(v)
         g = _lib.geom(size)
         lanes = field_lanes(g.d)
@@ -174,7 +174,7 @@ class MorphField(Function):
         levels = torch.empty((nb_steps + 2) * nvox * lanes, dtype=torch.float32, device=v.device)
         field = torch.empty((g.N,) + spatial + (lanes,), dtype=torch.float32, device=v.device)
         call("advk_morph_field_fwd", C.byref(g), C.byref(cfg), ptr(v), float(scale), nb_steps,
-             ptr(u_lr), ptr(levels), ptr(field), stream())
+             ptr(u_lr), ptr(levels), ptr(field), ptr(norm_out), stream())
         ctx.save_for_backward(levels, field)
         ctx.meta = (g, cfg, float(scale), nb_steps, v.shape)
         return field
@@ -191,7 +191,7 @@ class MorphField(Function):
         g_v = torch.empty(vshape, dtype=torch.float32, device=field.device)
         call("advk_morph_field_bwd", C.byref(g), C.byref(cfg), scale, nb, ptr(levels), ptr(field),
              ptr(g_field), ptr(scratch), ptr(lr_scratch), ptr(g_v), stream())
-        return g_v, None, None, None, None
+        return g_v, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- intensity

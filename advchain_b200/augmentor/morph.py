@@ -184,8 +184,21 @@ class AdvMorph(AdvTransformBase):
         if e is not None and self._valid(e):
             return e[4]
         p = self.param
-        field = _ops.MorphField.apply(p, self.data_size, self._morph_cfg(), sign * self._scale(),
-                                      self._nb_steps())
+        norm_out = None
+        e = self._steps_cache
+        fresh = e is not None and e[0]() is p and e[1] == p._version and e[2] == self._scale()
+        if self.spatial_dims == 3 and self._fixed_steps is not None and not fresh:
+            # graph loop: run with the captured count and let the build itself produce the norm the
+            # step rule needs (no separate reduction pass); the rule is checked on the device afterwards
+            nb, viol = self._fixed_steps
+            norm_out = torch.empty(1, dtype=torch.float32, device=p.device)
+        else:
+            nb = self._nb_steps()
+        field = _ops.MorphField.apply(p, self.data_size, self._morph_cfg(), sign * self._scale(), nb, norm_out)
+        if norm_out is not None:
+            _ops.call("advk_morph_steps_check", _ops.ptr(norm_out), int(nb), int(self.num_steps), viol.data_ptr(),
+                      _ops.stream())
+            self._steps_cache = (weakref.ref(p), p._version, self._scale(), nb)
         self._cache[sign] = (weakref.ref(p), p._version, self._scale(),
                              torch.is_grad_enabled() and p.requires_grad, field)
         return field

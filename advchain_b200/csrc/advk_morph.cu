@@ -736,7 +736,10 @@ __device__ __forceinline__ void sm_add(float* d, float v) { atomicAdd(d, v); }
 template <typename T>
 __global__ void __launch_bounds__(256)
 adjoint_axis_big_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out,
-                        int n_in, int n_out, i64 inner, float scale) {
+                        int n_in, int n_out, i64 inner, float scale, i64 sl_in, i64 sp_in, i64 so_in,
+                        i64 sl_out, i64 sj_out, i64 so_out) {
+  // lanes run over `inner` positions (stride sl_*), the axis has stride sp_in / sj_out, blockIdx.y strides
+  // so_*: the same kernel serves [outer][axis][inner] (lanes = inner) and [outer][axis] (lanes = outer)
   extern __shared__ float4 adj_smem4[];
   T* acc = reinterpret_cast<T*>(adj_smem4);                 // [n_out][32]
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -756,7 +759,7 @@ adjoint_axis_big_kernel(const T* __restrict__ a, const T* __restrict__ b, float 
         if (c0 >= 0) { sm_add(acc + c0 * 32 + lane, s0); sm_add(acc + c1 * 32 + lane, s1); }
         c0 = u.i0; c1 = u.i1; s0 = t_zero<T>(); s1 = t_zero<T>();
       }
-      const i64 q = (o * n_in + p) * inner + i;
+      const i64 q = o * so_in + (i64)p * sp_in + i * sl_in;
       const T av = a[q];
       const T bv = hb ? b[q] : av;
       t_fma(s0, u.l0, av, bv, hb);
@@ -768,7 +771,7 @@ adjoint_axis_big_kernel(const T* __restrict__ a, const T* __restrict__ b, float 
   for (int k = threadIdx.x; k < n_out * 32; k += 256) {
     const int j = k >> 5, l = k & 31;
     const i64 ii = (i64)blockIdx.x * 32 + l;
-    if (ii < inner) out[(o * n_out + j) * inner + ii] = t_scale(acc[k], vs);
+    if (ii < inner) out[o * so_out + (i64)j * sj_out + ii * sl_out] = t_scale(acc[k], vs);
   }
 }
 
@@ -778,7 +781,14 @@ static void launch_adjoint_axis(const T* a, const T* a2, const T* b, float vs, T
   i64 tot = outer * n_out * inner;
   if (!a2 && inner >= 32 && n_out <= ADJ_NOUT_MAX && outer <= 65535) {
     dim3 grid((unsigned)((inner + 31) / 32), (unsigned)outer);
-    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(a, b, vs, out, n_in, n_out, inner, scale));
+    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(
+        a, b, vs, out, n_in, n_out, inner, scale, 1, inner, (i64)n_in * inner, 1, inner, (i64)n_out * inner));
+    return;
+  }
+  if (!a2 && inner == 1 && outer >= 32 && n_out <= ADJ_NOUT_MAX) {      // last axis: lanes over the rows
+    dim3 grid((unsigned)((outer + 31) / 32), 1);
+    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(
+        a, b, vs, out, n_in, n_out, outer, scale, n_in, 1, 0, n_out, 1, 0));
     return;
   }
   ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, a2, b, vs, out, outer, n_in, n_out, inner, scale));
@@ -799,7 +809,7 @@ __global__ void aos_to_planar_kernel(const typename V<DIM>::T* __restrict__ in, 
 // ---------------------------------------------------------------------------------------
 template <int DIM>
 static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float scale, int nb, float* u_lr,
-                     void* levels, void* field_out, cudaStream_t st) {
+                     void* levels, void* field_out, float* norm2_out, cudaStream_t st) {
   typedef typename V<DIM>::T T;
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   int NC = g.N * DIM;
@@ -808,7 +818,8 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   i64 F = (i64)g.N * g.S;
   dim3 grid(blocks_for(g.S, 256), g.N);
   float inv2n = 1.0f / (float)(1u << nb);
-  launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, nullptr, st);
+  if (norm2_out) cudaMemsetAsync(norm2_out, 0, sizeof(float), st);
+  launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, norm2_out, st);     // sum |u|^2 as a by-product when asked for
   for (int k = 1; k <= nb; ++k) ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
   launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
   return check_launch("morph_field_fwd");
@@ -905,7 +916,7 @@ extern "C" int advk_morph_unorm2(const advk_geom* gg, const advk_morph_cfg* cfg,
 
 extern "C" int advk_morph_field_fwd(const advk_geom* gg, const advk_morph_cfg* cfg, const float* v,
                                     float scale, int nb_steps, float* u_lr, void* levels,
-                                    void* field_out, void* stream) {
+                                    void* field_out, float* norm2_out, void* stream) {
   Dims g; MorphCfg c;
   ADVK_REQUIRE(make_dims(gg, g), "bad geometry");
   ADVK_REQUIRE(make_cfg(cfg, g, gg->d, c), "bad morph config (ktaps must be 9)");
@@ -914,8 +925,8 @@ extern "C" int advk_morph_field_fwd(const advk_geom* gg, const advk_morph_cfg* c
   ADVK_REQUIRE(nb_steps >= 1 && nb_steps <= 30, "nb_steps out of range");
   ADVK_REQUIRE((i64)g.N * g.D <= 65535, "batch x depth too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
-  return gg->d == 2 ? field_fwd<2>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st)
-                    : field_fwd<3>(g, c, v, scale, nb_steps, u_lr, levels, field_out, st);
+  return gg->d == 2 ? field_fwd<2>(g, c, v, scale, nb_steps, u_lr, levels, field_out, norm2_out, st)
+                    : field_fwd<3>(g, c, v, scale, nb_steps, u_lr, levels, field_out, norm2_out, st);
 }
 
 extern "C" size_t advk_morph_lr_scratch_floats(const advk_geom* gg, const advk_morph_cfg* cfg) {

@@ -141,12 +141,14 @@ int advk_warp_field_bwd(const advk_geom* g, int C, const float* g_out, const flo
  * levels: (nb_steps+2) fields of N*S elements each: phi_0 .. phi_n, kept for the backward, plus one
  *   scratch field used by the forward.
  * field_out: the UNCLAMPED composed field (consumers clamp on load); N*S elements.
- * u_lr: scratch N x d x lr floats. */
+ * u_lr: scratch N x d x lr floats.
+ * norm2_out (nullable): 1 float, receives the same sum as advk_morph_unorm2 as a by-product of the
+ *   build (graph-captured loops check the step-count rule after the fact, advk_morph_steps_check). */
 int advk_morph_unorm2(const advk_geom* g, const advk_morph_cfg* cfg, const float* v, float scale,
                       float* u_lr, float* out_norm2, void* stream);
 int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const float* v,
                          float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
-                         void* stream);
+                         float* norm2_out, void* stream);
 /* scratch: 5 fields of N*S elements (4 are used); lr_scratch: advk_morph_lr_scratch_floats() floats.
  * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
 size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
