@@ -587,7 +587,7 @@ class ComposeAdversarialTransformSolver(object):
                 if len(_GRAPH_SEEN) > 4096:
                     _GRAPH_SEEN.clear()
                 return False
-        start = [t.param.detach().clone() for t in chain]
+        start = [t.param.detach() for t in chain]      # the incoming tensors themselves: never written here
         if st is None:
             st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, want_norm=False,
                       refs=[weakref.ref(model)] + [weakref.ref(t) for t in chain],
