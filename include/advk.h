@@ -158,8 +158,10 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
 /* Kernel variant of the squaring-step backward (A/B timing and tests): bit 0 = neighbouring lanes
  * combine contributions before the RED; bits 2-3 = who zeroes the ping-pong buffers: 0 memset nodes,
  * 2 (value 8) the kernel, after its REDs, 1 (value 4) the kernel, before its REDs (slow; measured
- * counter-example).  Default 9; environment ADVK_SSB_MODE.  Results agree up to fp32 summation
- * order.  A negative mask only queries; returns the previous mask. */
+ * counter-example); bits 4-6 = warp-box kernel (hand-offs along x, y and z, Jacobian term folded into
+ * a corner RED) with box shape 1 = 32x1x1, 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (2-D: 8x4), 0 = off;
+ * bit 7 = box kernel compiled for 5 resident CTAs per SM.  Default 9; environment ADVK_SSB_MODE.
+ * Results agree up to fp32 summation order.  A negative mask only queries; returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
 
 /* ---- AdvNoise / AdvBias: intensity stage ------------------------------------------------

@@ -2,7 +2,12 @@
 squaring-step kernel variants (advk_morph_tune) and check that the variants agree.
 
     python scripts/bench_morph.py [workload] [vnorm ...]
+
+Environment: BENCH_MORPH_MASKS = comma-separated advk_morph_tune masks to time (default: all variants),
+BENCH_MORPH_OUT = JSON file that receives {mask: us of ss_step_bwd per build} summed over the vnorms
+plus "best" (fastest mask whose field and gradient agree with mask 0).
 """
+import json
 import os
 import sys
 
@@ -47,13 +52,26 @@ def run(vn, mask, reps=5):
     _lib.prof_configure(None)
     line = " ".join("%s=%.1f" % (k, 1e3 * sum(vs) / reps) for k, vs in sorted(r.items(), key=lambda kv: -sum(kv[1])))
     print("vnorm %.1f tile-mask %d  [us per build, %d reps]: %s" % (vn, mask, reps, line), flush=True)
+    ssb_us[mask] = ssb_us.get(mask, 0.0) + 1e3 * sum(r.get("ss_step_bwd", [0.0])) / reps
     return res
 
 
+ssb_us = {}
+agree = {}
+masks = [int(m) for m in os.environ.get("BENCH_MORPH_MASKS", "9,137,24,40,56,72,152,168,184,200").split(",")]
 for vn in vnorms:
     base = run(vn, 0)
-    for mask in (1, 8, 9):
+    for mask in masks:
         out = run(vn, mask)
         ef = float((out[0] - base[0]).abs().max() / base[0].abs().max())
         eg = float((out[1] - base[1]).abs().max() / base[1].abs().max())
+        agree[mask] = agree.get(mask, True) and ef < 1e-6 and eg < 1e-4
         print("   mask %d vs 0: field rel err %.2e, grad rel err %.2e" % (mask, ef, eg), flush=True)
+ok = [m for m in masks if agree.get(m)]
+best = min(ok, key=lambda m: ssb_us[m]) if ok else 9
+print("ss_step_bwd us per build (sum over vnorms): %s -> best %d" % (
+    " ".join("%d=%.1f" % (m, ssb_us[m]) for m in [0] + masks), best), flush=True)
+if os.environ.get("BENCH_MORPH_OUT"):
+    with open(os.environ["BENCH_MORPH_OUT"], "w") as fh:
+        json.dump({"workload": wl, "us": {str(m): ssb_us[m] for m in ssb_us}, "agree": {str(m): bool(v) for m, v in agree.items()},
+                   "best": best}, fh)
