@@ -324,11 +324,26 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
 //         REDs (default; 522 us vs 494 + 8 memsets), 1 = before them (1311 us: a store to a line whose
 //         load is still in flight stalls the LSU -- the counter-example is kept selectable).
 
+// ADVK_SSB_DIAG (never defined in the product build; scripts/build_diag.sh compiles side libraries
+// with it for scripts/diag_ssb.py): timing diagnostics that take the kernel apart -- 1: the REDs become
+// register adds + one plain store, 2: the gathers read the thread's own phi, 3: the REDs become plain
+// (racy) stores, 4 = 1 + 2.  Results are WRONG by construction; only the launch time means anything.
+#ifndef ADVK_SSB_DIAG
+#define ADVK_SSB_DIAG 0
+#endif
+template <typename T>
+__device__ __forceinline__ void ssb_red(T* addr, T val, float& sink) {
+  if (ADVK_SSB_DIAG == 1 || ADVK_SSB_DIAG == 4) sink += val.x + val.y;
+  else if (ADVK_SSB_DIAG == 3) *addr = val;
+  else atomicAdd(addr, val);
+}
+
 // Emits one corner row (y,z fixed; corners a0 and a0+1 along x) of one voxel: RED of c0 to a0 and c1
 // to a0+1, with the lane hand-off described above when LANE.
 template <int DIM, bool LANE>
 __device__ __forceinline__ void ssb_emit_row(typename V<DIM>::T* __restrict__ dst, int lane, bool v0, bool v1, int a0,
-                                             float c0x, float c0y, float c0z, float c1x, float c1y, float c1z) {
+                                             float c0x, float c0y, float c0z, float c1x, float c1y, float c1z,
+                                             float& sink) {
   if (LANE) {
     const unsigned FULL = 0xffffffffu;
     const int a0_next = __shfl_down_sync(FULL, v0 ? a0 : -1, 1);
@@ -338,11 +353,11 @@ __device__ __forceinline__ void ssb_emit_row(typename V<DIM>::T* __restrict__ ds
     float rz = 0.f;
     if (DIM == 3) rz = __shfl_up_sync(FULL, hand ? c1z : 0.f, 1);
     if (lane > 0) { c0x += rx; c0y += ry; c0z += rz; }
-    if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
-    if (v1 && !hand) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
+    if (v0) ssb_red(dst + a0, V<DIM>::make(c0x, c0y, c0z), sink);
+    if (v1 && !hand) ssb_red(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z), sink);
   } else {
-    if (v0) atomicAdd(dst + a0, V<DIM>::make(c0x, c0y, c0z));
-    if (v1) atomicAdd(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z));
+    if (v0) ssb_red(dst + a0, V<DIM>::make(c0x, c0y, c0z), sink);
+    if (v1) ssb_red(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z), sink);
   }
 }
 
@@ -372,6 +387,8 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
   const int HW = g.H * g.W;
   const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
   float jx = 0.f, jy = 0.f, jz = 0.f;
+  float sink = 0.f;                                                  // ADVK_SSB_DIAG only
+  constexpr bool no_gather = ADVK_SSB_DIAG == 2 || ADVK_SSB_DIAG == 4;
 #pragma unroll
   for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
     const bool vz = dz ? az.v1 : az.v0;
@@ -385,25 +402,26 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
       const int a0 = (az.i0 + dz) * HW + (ay.i0 + dy) * g.W + ax.i0;      // S < 2^31 (host-checked)
       // Jacobian: sum over corners of (+-) <phi(corner), g> * (other-axis weights)
       if (v0) {
-        T s0 = __ldg(src + a0);
+        T s0 = no_gather ? f : __ldg(src + a0);
         float dot = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
         jx -= dot * (wy * wz);
         jy += (dy ? dot : -dot) * (ax.w0 * wz);
         if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w0 * wy);
       }
       if (v1) {
-        T s1 = __ldg(src + a0 + 1);
+        T s1 = no_gather ? f : __ldg(src + a0 + 1);
         float dot = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
         jx += dot * (wy * wz);
         jy += (dy ? dot : -dot) * (ax.w1 * wz);
         if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w1 * wy);
       }
       const float w0 = ax.w0 * wy * wz, w1 = ax.w1 * wy * wz;
-      ssb_emit_row<DIM, LANE>(dst, lane, v0, v1, a0, gx * w0, gy * w0, gz * w0, gx * w1, gy * w1, gz * w1);
+      ssb_emit_row<DIM, LANE>(dst, lane, v0, v1, a0, gx * w0, gy * w0, gz * w0, gx * w1, gy * w1, gz * w1, sink);
     }
   }
   if (live) {
-    atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+    if (ADVK_SSB_DIAG == 1 || ADVK_SSB_DIAG == 4) dst[p] = V<DIM>::make(jx * ax.mult + sink, jy * ay.mult, jz * az.mult);
+    else atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
     if (ZSTORE == 2) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
   }
 }
