@@ -46,6 +46,17 @@ template <> struct V<3> {
   static __device__ __forceinline__ float z(const T& v) { return v.z; }
 };
 
+// Hides how a per-sample base pointer was computed from the optimiser, so that base + 32-bit voxel offset
+// stays ONE IMAD.WIDE per address instead of a re-derived 64-bit (n*S + offset)*sizeof chain.
+template <typename P>
+__device__ __forceinline__ P* opaque_ptr(P* p) {
+  unsigned long long v = (unsigned long long)p;
+  asm("" : "+l"(v));
+  P* q = (P*)v;
+  __builtin_assume(__isGlobal(q));       // keep LDG / REDG / STG (the barrier hides the address space too)
+  return q;
+}
+
 // ---------------------------------------------------------------------------------------
 // Low-res depthwise Gaussian (direct 9^d taps; the lattice is tiny: 16x16 / 8x8x8).
 // in/out planar [NC][Dl][Hl][Wl]; out = G (*) (scale*in).  Self-adjoint -> also used backward.
@@ -306,6 +317,42 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
   out[(i64)n * g.S + p] = V<DIM>::make(ox, oy, oz);
 }
 
+// Same step with no validity predicates (see ss_step_bwd_lean_kernel: under border padding a corner
+// outside the volume has weight exactly 0, so it is redirected to corner 0 of its axis and adds s * 0).
+template <int DIM>
+__global__ void __launch_bounds__(256, 8)
+ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
+  typedef typename V<DIM>::T T;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
+  if (p >= g.S) return;
+  const i64 nb = (i64)blockIdx.y * g.S;
+  const T* src = opaque_ptr(in + nb);
+  const T f = __ldg(src + p);
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
+  Axis az;
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
+  const int HW = g.H * g.W;
+  const int dxo = ax.v1 ? 1 : 0, dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
+  const T* c000 = src + (az.i0 * HW + ay.i0 * g.W + ax.i0);
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll
+  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const T s = __ldg(c000 + (dz * dzo + dy * dyo + dx * dxo));
+        const float w = (dx ? ax.w1 : ax.w0) * (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
+        ox += s.x * w; oy += s.y * w;
+        if (DIM == 3) oz += V<DIM>::z(s) * w;
+      }
+    }
+  }
+  (out + nb)[p] = V<DIM>::make(ox, oy, oz);
+}
+
 // Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
 //     dL/dphi_{k-1}(y) = sum_x g_k(x) * w(phi_{k-1}(x), y)            scatter adjoint of the gather
 //                      + mult * < d(sample)/d(coord) at y , g_k(y) >   spatial-Jacobian term
@@ -423,6 +470,127 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
     if (ADVK_SSB_DIAG == 1 || ADVK_SSB_DIAG == 4) dst[p] = V<DIM>::make(jx * ax.mult + sink, jy * ay.mult, jz * az.mult);
     else atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
     if (ZSTORE == 2) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
+  }
+}
+
+// Lean variant of the LANE kernel.  Taking the kernel apart on B200 (scripts/diag_ssb.py, gpurun_out/r01l:
+// 50 us per launch at 128^3; 35 us with the REDs turned into register adds, 42 us with the gathers turned
+// into register moves, 29 us with both gone -- and 48 us with the REDs turned into plain stores) shows that
+// the skeleton, i.e. instruction issue, is the larger part of a launch, so this variant spends fewer
+// instructions on the same arithmetic:
+//   * per-sample base pointers are made opaque to the optimiser, so that a corner address is one
+//     IMAD.WIDE of a 32-bit voxel offset instead of a re-derived 64-bit (n*S + offset)*16 chain;
+//   * the x hand-off ships the upstream value once and ONE weight per corner row (the receiver forms
+//     g*w0 + g_prev*w1_prev with FMAs) instead of a 3-vector per row, on one address test per voxel (a
+//     neighbour whose corner (0,0,0) is one voxel further sees the same rows with the same validity);
+//   * the Jacobian term is built from the 2^d dot products <phi(corner), g> by separable differences
+//     (interpolate along x, difference along y, ...) instead of three weighted sums over all corners.
+// Same result as LANE up to fp32 summation order.
+template <int DIM, bool ZS>
+__global__ void __launch_bounds__(256)
+ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
+                        typename V<DIM>::T* __restrict__ out) {
+  typedef typename V<DIM>::T T;
+  constexpr int NZ = DIM == 3 ? 2 : 1;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
+  const bool live = p < g.S;
+  const i64 nb = (i64)blockIdx.y * g.S;
+  const T* src = opaque_ptr(phi_prev + nb);
+  T* dst = opaque_ptr(out + nb);
+  T* upn = opaque_ptr(up + nb);
+  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
+  if (live) {
+    f = __ldg(src + p);
+    go = upn[p];
+  }
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
+  Axis az;
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
+  const int HW = g.H * g.W;
+  const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
+  // Border padding: corner 0 of an axis is always inside, and corner 1 is outside exactly when the clipped
+  // coordinate sits ON the last voxel -- where its weight (x - floor x) is exactly 0 and d(index)/d(coord)
+  // (`mult`) is 0 as well.  So an outside corner is simply redirected to corner 0 of that axis: whatever
+  // is gathered there meets a zero weight or a zero `mult`, whatever is scattered there is a zero.  No
+  // validity predicate is left on any gather or RED (a dead lane of the last CTA works on zeros at the
+  // in-bounds voxel its zero coordinate points to, and skips the REDs).
+  const int dxo = ax.v1 ? 1 : 0, dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
+  const int a000 = az.i0 * HW + ay.i0 * g.W + ax.i0;
+  const T* s000 = src + a000;
+  // gathers -> d = <phi(corner), g>
+  float d[NZ][2][2];
+#pragma unroll
+  for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const T* r = s000 + (dz * dzo + dy * dyo);
+      const T s0 = __ldg(r), s1 = __ldg(r + dxo);
+      d[dz][dy][0] = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
+      d[dz][dy][1] = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
+    }
+  }
+  // Jacobian term: d(sample)/d(coord) = differences of the interpolated dot products
+  float jx, jy, jz = 0.f;
+  {
+    float jxz[NZ], eyd[NZ], ey[NZ];
+#pragma unroll
+    for (int dz = 0; dz < NZ; ++dz) {
+      const float e0 = ax.w0 * d[dz][0][0] + ax.w1 * d[dz][0][1], e1 = ax.w0 * d[dz][1][0] + ax.w1 * d[dz][1][1];
+      jxz[dz] = ay.w0 * (d[dz][0][1] - d[dz][0][0]) + ay.w1 * (d[dz][1][1] - d[dz][1][0]);
+      eyd[dz] = e1 - e0;
+      ey[dz] = ay.w0 * e0 + ay.w1 * e1;
+    }
+    if (DIM == 3) {
+      jx = az.w0 * jxz[0] + az.w1 * jxz[NZ - 1];
+      jy = az.w0 * eyd[0] + az.w1 * eyd[NZ - 1];
+      jz = ey[NZ - 1] - ey[0];
+    } else {
+      jx = jxz[0]; jy = eyd[0];
+    }
+  }
+  // x hand-off (every shuffle is executed by all lanes): lane i's corner-1 column is lane i+1's corner-0
+  // column when that lane's corner (0,0,0) is one voxel further -- then both see the same rows.
+  const int next = __shfl_down_sync(FULL, live ? a000 : -1, 1);
+  const bool hand = live && ax.v1 && lane < 31 && next == a000 + 1;
+  const float px = __shfl_up_sync(FULL, gx, 1), py = __shfl_up_sync(FULL, gy, 1);
+  const float pz = DIM == 3 ? __shfl_up_sync(FULL, gz, 1) : 0.f;
+  float w0[NZ][2], w1[NZ][2], ws[NZ][2];
+#pragma unroll
+  for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const float wr = (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
+      w0[dz][dy] = ax.w0 * wr; w1[dz][dy] = ax.w1 * wr;
+      const float got = __shfl_up_sync(FULL, hand ? w1[dz][dy] : 0.f, 1);
+      ws[dz][dy] = lane ? got : 0.f;
+    }
+  }
+  if (live) {
+    T* d000 = dst + a000;
+#pragma unroll
+    for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float a = w0[dz][dy], b = ws[dz][dy];
+        atomicAdd(d000 + (dz * dzo + dy * dyo), V<DIM>::make(gx * a + px * b, gy * a + py * b, gz * a + pz * b));
+      }
+    }
+    if (ax.v1 && !hand) {                                           // row ends and non-smooth spots only
+#pragma unroll
+      for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const float c = w1[dz][dy];
+          atomicAdd(d000 + (dz * dzo + dy * dyo + 1), V<DIM>::make(gx * c, gy * c, gz * c));
+        }
+      }
+    }
+    atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+    if (ZS) upn[p] = V<DIM>::make(0.f, 0.f, 0.f);               // after the REDs (see ZSTORE above)
   }
 }
 
@@ -579,13 +747,14 @@ ss_step_bwd_box_kernel(Dims g, int ctz, const typename V<DIM>::T* __restrict__ p
 // bit 0: LANE; bits 2-3: ZSTORE (0 memset nodes, 1 zero before the REDs -- slow, kept as the
 // measured counter-example --, 2 zero after the REDs); bits 4-6: warp-box kernel, shape 1 = 32x1x1,
 // 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (3-D only; 2-D runs 8x4), 0 = the kernels above; bit 7: box kernel
-// (or, with shape 0 and zero-after, the kernel above) compiled for 5 resident CTAs per SM.
+// (or, with shape 0 and zero-after, the kernel above) compiled for 5 resident CTAs per SM; bit 8: the lean
+// kernel (x hand-off, fewer instructions); bit 9: the lean FORWARD step (ss_step_lean_kernel).
 // Default: LANE + zero after.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 253) : 9;
+    g_ssb_mode = e ? (atoi(e) & 1021) : 9;
   }
   return g_ssb_mode;
 }
@@ -626,6 +795,12 @@ static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev
                                typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
   const int mode = ssb_mode();
   const int zs = may_zero_up ? ((mode >> 2) & 3) : 0;
+  if (mode & 256) {
+    dim3 grid(blocks_for(g.S, 256), g.N);
+    if (zs) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+    else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+    return;
+  }
   const int shape = (mode >> 4) & 7;
   if (shape) {
     const bool z = zs != 0;
@@ -1021,7 +1196,11 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   float inv2n = 1.0f / (float)(1u << nb);
   if (norm2_out) cudaMemsetAsync(norm2_out, 0, sizeof(float), st);
   launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, norm2_out, st);     // sum |u|^2 as a by-product when asked for
-  for (int k = 1; k <= nb; ++k) ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
+  const bool lean = (ssb_mode() & 512) != 0;
+  for (int k = 1; k <= nb; ++k) {
+    if (lean) ADVK_LAUNCH(K_ss_step, st, ss_step_lean_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
+    else ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
+  }
   launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
   return check_launch("morph_field_fwd");
 }
@@ -1089,7 +1268,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 253;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 1021;
   return prev;
 }
 

@@ -148,6 +148,59 @@ def _box_kernel(phi, up, lbx, lby, lbz):
     return out.reshape(D, H, W, 3), reds
 
 
+def _lean_kernel(phi, up):
+    """`ss_step_bwd_lean_kernel`: 32 consecutive voxels per warp, x hand-off by weight, outside corners
+    redirected to corner 0 of their axis (zero weight / zero mult), Jacobian by separable differences."""
+    D, H, W, _ = phi.shape
+    HW, S = H * W, D * H * W
+    src, upf = phi.reshape(-1, 3), up.reshape(-1, 3)
+    out = np.zeros((S, 3))
+    lane = np.arange(32)
+    for w in range(-(-S // 32)):
+        p = w * 32 + lane
+        live = p < S
+        ps = np.where(live, p, 0)
+        f = np.where(live[:, None], src[ps], 0.0)
+        g = np.where(live[:, None], upf[ps], 0.0)
+        ix, wx0, wx1, vx1, mx = _axis(f[:, 0], W)
+        iy, wy0, wy1, vy1, my = _axis(f[:, 1], H)
+        iz, wz0, wz1, vz1, mz = _axis(f[:, 2], D)
+        dxo, dyo, dzo = np.where(vx1, 1, 0), np.where(vy1, W, 0), np.where(vz1, HW, 0)
+        a000 = iz * HW + iy * W + ix
+        d = np.zeros((2, 2, 2, 32))
+        for dz in range(2):
+            for dy in range(2):
+                r = a000 + dz * dzo + dy * dyo
+                d[dz, dy, 0] = (src[r] * g).sum(1)
+                d[dz, dy, 1] = (src[r + dxo] * g).sum(1)
+        jxz, eyd, ey = [], [], []
+        for dz in range(2):
+            e0 = wx0 * d[dz, 0, 0] + wx1 * d[dz, 0, 1]
+            e1 = wx0 * d[dz, 1, 0] + wx1 * d[dz, 1, 1]
+            jxz.append(wy0 * (d[dz, 0, 1] - d[dz, 0, 0]) + wy1 * (d[dz, 1, 1] - d[dz, 1, 0]))
+            eyd.append(e1 - e0)
+            ey.append(wy0 * e0 + wy1 * e1)
+        j = np.stack([(wz0 * jxz[0] + wz1 * jxz[1]) * mx, (wz0 * eyd[0] + wz1 * eyd[1]) * my, (ey[1] - ey[0]) * mz], 1)
+        nxt = _shfl_down(np.where(live, a000, -1), 1)
+        hand = live & vx1 & (lane < 31) & (nxt == a000 + 1)
+        gp = _shfl_up(g, 1)
+        for dz in range(2):
+            for dy in range(2):
+                wr = (wy1 if dy else wy0) * (wz1 if dz else wz0)
+                w0, w1 = wx0 * wr, wx1 * wr
+                ws = _shfl_up(np.where(hand, w1, 0.0), 1)
+                ws[0] = 0.0
+                c0 = g * w0[:, None] + gp * ws[:, None]
+                r = a000 + dz * dzo + dy * dyo
+                for i in np.nonzero(live)[0]:
+                    out[r[i]] += c0[i]
+                for i in np.nonzero(live & vx1 & ~hand)[0]:
+                    out[r[i] + 1] += g[i] * w1[i]
+        for i in np.nonzero(live)[0]:
+            out[p[i]] += j[i]
+    return out.reshape(D, H, W, 3)
+
+
 def _field(rng, D, H, W, amp_vox):
     """Absolute sampling coordinates base + displacement (normalised), smooth-ish + a few outliers."""
     zz, yy, xx = np.meshgrid(np.linspace(-1, 1, D), np.linspace(-1, 1, H), np.linspace(-1, 1, W), indexing="ij")
@@ -172,6 +225,22 @@ def test_box_handoff_equals_plain_scatter(lbx, lby, lbz, size, amp):
     up = rng.standard_normal((D, H, W, 3))
     ref = _direct(phi, up)
     out, reds = _box_kernel(phi, up, lbx, lby, lbz)
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("size,amp", [((5, 7, 19), 0.4), ((4, 6, 9), 2.7), ((1, 9, 21), 0.6), ((3, 5, 1), 0.8)])
+def test_lean_kernel_equals_plain_scatter(size, amp):
+    """Coordinates ON and beyond the last voxel of every axis are in the field (clipped by the border
+    padding): the redirected corners must contribute nothing."""
+    rng = np.random.default_rng(12)
+    D, H, W = size
+    phi = _field(rng, D, H, W, amp)
+    phi[..., -1, 0] = 1.0            # x exactly on the last voxel
+    phi[:, -1, :, 1] = 1.3           # y clipped
+    phi[0, :, :, 2] = -1.0           # z exactly on the first voxel
+    up = rng.standard_normal((D, H, W, 3))
+    ref = _direct(phi, up)
+    out = _lean_kernel(phi, up)
     assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
