@@ -749,12 +749,12 @@ ss_step_bwd_box_kernel(Dims g, int ctz, const typename V<DIM>::T* __restrict__ p
 // 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (3-D only; 2-D runs 8x4), 0 = the kernels above; bit 7: box kernel
 // (or, with shape 0 and zero-after, the kernel above) compiled for 5 resident CTAs per SM; bit 8: the lean
 // kernel (x hand-off, fewer instructions); bit 9: the lean FORWARD step (ss_step_lean_kernel).
-// Default: LANE + zero after.
+// Default 776: both lean kernels, zero after the REDs.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 1021) : 9;
+    g_ssb_mode = e ? (atoi(e) & 1021) : 776;
   }
   return g_ssb_mode;
 }

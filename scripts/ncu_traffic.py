@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # kernel function name fragment -> kernel id used by bench.py / advk_kernel_name()
-IDS = [("ss_step_bwd_box_kernel", "ss_step_bwd"), ("ss_step_bwd_kernel", "ss_step_bwd"), ("ss_step_kernel", "ss_step"), ("smooth3d_xy_kernel<0>", "smooth_fwd_xy"),
+IDS = [("ss_step_bwd_lean_kernel", "ss_step_bwd"), ("ss_step_lean_kernel", "ss_step"), ("ss_step_bwd_box_kernel", "ss_step_bwd"), ("ss_step_bwd_kernel", "ss_step_bwd"), ("ss_step_kernel", "ss_step"), ("smooth3d_xy_kernel<0>", "smooth_fwd_xy"),
        ("smooth3d_z_kernel<0>", "smooth_fwd_z"), ("smooth3d_xy_kernel<1>", "smooth_bwd_xy"),
        ("smooth3d_z_kernel<1>", "smooth_bwd_z"), ("chain_fwd", "chain_fwd"), ("chain_bwd", "chain_bwd"),
        ("init_phi0", "init_phi0"), ("loss_contour_adj", "loss_contour_adj"), ("loss_contour", "loss_contour"),
