@@ -317,60 +317,15 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
   out[(i64)n * g.S + p] = V<DIM>::make(ox, oy, oz);
 }
 
-// CTA tiling of the lean kernels (advk_morph_tune bit 10).  Both squaring-step kernels run at ONE 32-byte
-// sector request per SM per clock (profiles/r01l_ssb_taken_apart.md), and the gather fills are the part of
-// those requests a kernel can shrink: L1 only captures the reuse INSIDE a CTA.  A CTA of 256 consecutive voxels
-// (2 rows of 128) touches 3 rows x 2 planes of phi = 1.5 sectors per voxel; a CTA tile of 32 x 4 x 2 voxels
-// (32 x 8 in 2-D) touches 5 x 3 runs of 33 voxels = 1.0.  A warp is still 32 consecutive voxels of one row,
-// so the coalescing and the x hand-off are unchanged.  Used when W is a multiple of 32 (no dead lanes).
-struct TileMap {
-  int on;            // 0: linear mapping, blockIdx.y = sample
-  FastDiv ftz;       // CTA tiles along z per sample (3-D): blockIdx.z = n * tz + bz
-};
-template <int DIM>
-__device__ __forceinline__ void tile_voxel_of_thread(const Dims& g, const TileMap& tm, int& n, int& p, bool& live) {
-  if (!tm.on) {
-    n = blockIdx.y;
-    p = blockIdx.x * blockDim.x + threadIdx.x;                   // S < 2^31 (host-checked)
-    live = p < g.S;
-    return;
-  }
-  const int t = threadIdx.x;
-  const int x = blockIdx.x * 32 + (t & 31);
-  int y, z = 0;
-  if (DIM == 3) {
-    n = (int)fast_div(blockIdx.z, tm.ftz);
-    z = ((int)blockIdx.z - n * (int)tm.ftz.d) * 2 + (t >> 7);
-    y = blockIdx.y * 4 + ((t >> 5) & 3);
-  } else {
-    n = blockIdx.z;
-    y = blockIdx.y * 8 + (t >> 5);
-  }
-  live = x < g.W && y < g.H && z < g.D;
-  p = (z * g.H + y) * g.W + x;
-}
-template <int DIM>
-static bool make_tile_grid(const Dims& g, bool want, TileMap& tm, dim3& grid) {
-  tm.on = 0; tm.ftz = make_fastdiv(1);
-  grid = dim3(blocks_for(g.S, 256), g.N);
-  if (!want || (g.W & 31)) return false;
-  const i64 ty = (g.H + (DIM == 3 ? 3 : 7)) / (DIM == 3 ? 4 : 8), tz = DIM == 3 ? (g.D + 1) / 2 : 1;
-  if (ty > 65535 || tz * g.N > 65535) return false;
-  tm.on = 1; tm.ftz = make_fastdiv((unsigned)tz);
-  grid = dim3((unsigned)(g.W / 32), (unsigned)ty, (unsigned)(tz * g.N));
-  return true;
-}
-
 // Same step with no validity predicates (see ss_step_bwd_lean_kernel: under border padding a corner
 // outside the volume has weight exactly 0, so it is redirected to corner 0 of its axis and adds s * 0).
 template <int DIM>
 __global__ void __launch_bounds__(256, 8)
-ss_step_lean_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
+ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
-  int n, p; bool live;
-  tile_voxel_of_thread<DIM>(g, tm, n, p, live);
-  if (!live) return;
-  const i64 nb = (i64)n * g.S;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
+  if (p >= g.S) return;
+  const i64 nb = (i64)blockIdx.y * g.S;
   const T* src = opaque_ptr(in + nb);
   const T f = __ldg(src + p);
   Axis ax = make_axis_border(f.x, g.W);
@@ -533,15 +488,15 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
 // Same result as LANE up to fp32 summation order.
 template <int DIM, bool ZS>
 __global__ void __launch_bounds__(256)
-ss_step_bwd_lean_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
+ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
                         typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
   constexpr int NZ = DIM == 3 ? 2 : 1;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  int n, p; bool live;
-  tile_voxel_of_thread<DIM>(g, tm, n, p, live);
-  const i64 nb = (i64)n * g.S;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
+  const bool live = p < g.S;
+  const i64 nb = (i64)blockIdx.y * g.S;
   const T* src = opaque_ptr(phi_prev + nb);
   T* dst = opaque_ptr(out + nb);
   T* upn = opaque_ptr(up + nb);
@@ -793,14 +748,13 @@ ss_step_bwd_box_kernel(Dims g, int ctz, const typename V<DIM>::T* __restrict__ p
 // measured counter-example --, 2 zero after the REDs); bits 4-6: warp-box kernel, shape 1 = 32x1x1,
 // 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (3-D only; 2-D runs 8x4), 0 = the kernels above; bit 7: box kernel
 // (or, with shape 0 and zero-after, the kernel above) compiled for 5 resident CTAs per SM; bit 8: the lean
-// kernel (x hand-off, fewer instructions); bit 9: the lean FORWARD step (ss_step_lean_kernel);
-// bit 10: the lean kernels run on 32 x 4 x 2 CTA tiles (TileMap) when W is a multiple of 32.
+// kernel (x hand-off, fewer instructions); bit 9: the lean FORWARD step (ss_step_lean_kernel).
 // Default 776: both lean kernels, zero after the REDs.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 2045) : 776;
+    g_ssb_mode = e ? (atoi(e) & 1021) : 776;
   }
   return g_ssb_mode;
 }
@@ -842,10 +796,9 @@ static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev
   const int mode = ssb_mode();
   const int zs = may_zero_up ? ((mode >> 2) & 3) : 0;
   if (mode & 256) {
-    TileMap tm; dim3 grid;
-    make_tile_grid<DIM>(g, (mode & 1024) != 0, tm, grid);
-    if (zs) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, tm, phi_prev, up, out)));
-    else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, tm, phi_prev, up, out)));
+    dim3 grid(blocks_for(g.S, 256), g.N);
+    if (zs) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+    else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
     return;
   }
   const int shape = (mode >> 4) & 7;
@@ -1244,10 +1197,8 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   if (norm2_out) cudaMemsetAsync(norm2_out, 0, sizeof(float), st);
   launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, norm2_out, st);     // sum |u|^2 as a by-product when asked for
   const bool lean = (ssb_mode() & 512) != 0;
-  TileMap tm; dim3 tgrid;
-  make_tile_grid<DIM>(g, (ssb_mode() & 1024) != 0, tm, tgrid);
   for (int k = 1; k <= nb; ++k) {
-    if (lean) ADVK_LAUNCH(K_ss_step, st, ss_step_lean_kernel<DIM><<<tgrid, 256, 0, st>>>(g, tm, L + (k - 1) * F, L + k * F));
+    if (lean) ADVK_LAUNCH(K_ss_step, st, ss_step_lean_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
     else ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
   }
   launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
@@ -1317,7 +1268,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 2045;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 1021;
   return prev;
 }
 

@@ -162,8 +162,7 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  * a corner RED) with box shape 1 = 32x1x1, 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (2-D: 8x4), 0 = off;
  * bit 7 = box kernel compiled for 5 resident CTAs per SM; bit 8 (256) = lean adjoint kernel (x hand-off by
  * weight, no validity predicates: an outside corner has weight 0 under border padding and is redirected
- * to an inside one); bit 9 (512) = lean forward step; bit 10 (1024) = the lean kernels
- * run on 32x4x2 CTA tiles (32x8 in 2-D) when W is a multiple of 32.  Default 776 (both lean kernels, zeroing after the REDs); environment
+ * to an inside one); bit 9 (512) = lean forward step.  Default 776 (both lean kernels, zeroing after the REDs); environment
  * ADVK_SSB_MODE.
  * Results agree up to fp32 summation order.  A negative mask only queries; returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);

@@ -191,8 +191,7 @@ def test_affine_theta(d, pscale):
 
 
 MORPH = [(2, [2, 1, 48, 80], [3, 5], 1.5), (2, [1, 1, 64, 64], [4, 4], -1.5),
-         (3, [2, 1, 16, 24, 40], [2, 3, 4], 1.5), (3, [1, 1, 20, 20, 12], [3, 3, 2], -1.5),
-         (3, [2, 1, 9, 10, 64], [2, 3, 4], 1.5)]      # W % 32 == 0 with ragged y / z: the CTA-tile mapping (mask bit 10)
+         (3, [2, 1, 16, 24, 40], [2, 3, 4], 1.5), (3, [1, 1, 20, 20, 12], [3, 3, 2], -1.5)]
 
 
 # Gradient of the field build at the volume FACES is decided by ties in the reference algorithm
@@ -208,7 +207,7 @@ MORPH_TIE_TOL = 1e-2
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
 @pytest.mark.parametrize("support", ["interior", "full"])
-@pytest.mark.parametrize("tile", [9, 0, 1, 4, 24, 40, 56, 72, 64, 200, 184, 264, 256, 521, 776, 1800, 1280])
+@pytest.mark.parametrize("tile", [9, 0, 1, 4, 24, 40, 56, 72, 64, 200, 184, 264, 256, 521, 776])
 def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
     """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp.
     `tile` is the advk_morph_tune mask of the squaring-step backward: 0 plain + memsets, 1 lane-combined REDs,
@@ -216,7 +215,7 @@ def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
     warp-box kernel with box shape s = 1..4 (32x1x1, 16x2x1, 8x4x1, 8x2x2) zeroing after its REDs, 64 the
     8x2x2 box with memset zeroing, +128 the box kernel compiled for 5 resident CTAs per SM; 264 / 256 the lean
     adjoint (zeroing after its REDs / memset zeroing), 521 the lean forward step with the default adjoint,
-    776 both lean kernels (the default), +1024 the lean kernels on 32x4x2 CTA tiles (taken when W % 32 == 0)."""
+    776 both lean kernels (the default)."""
     from advchain_b200 import _lib
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()
