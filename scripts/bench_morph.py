@@ -58,7 +58,7 @@ def run(vn, mask, reps=5):
 
 ssb_us = {}
 agree = {}
-masks = [int(m) for m in os.environ.get("BENCH_MORPH_MASKS", "9,264,776,521,137,24,72").split(",")]
+masks = [int(m) for m in os.environ.get("BENCH_MORPH_MASKS", "9,776,264,521").split(",")]
 for vn in vnorms:
     base = run(vn, 0)
     for mask in masks:

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One short GPU-box visit for the warp-box squaring-step adjoint: parity of every variant, kernel A/B,
+# One short GPU-box visit for the squaring-step kernel variants (advk_morph_tune masks): parity of every variant, kernel A/B,
 # whole-step A/B (bench.py with the default and with the fastest variant), one ncu capture of the winner.
 # Usage (through gpurun): bash scripts/gpu_exp_box.sh <tag>
 TAG=${1:-r01k}
@@ -25,11 +25,11 @@ for n in ("default", "best"):
     except Exception as e:
         print(n, "unreadable:", e)
 PY
-ADVK_SSB_MODE=$BEST timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off \
+[ -n "$SKIP_NCU" ] || ADVK_SSB_MODE=$BEST timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:ss_step_bwd -c 2 -f -o $O/${TAG}_full_ss_step_bwd python scripts/one_step.py > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ADVK_SSB_MODE=$BEST timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+[ -n "$SKIP_NCU" ] || ADVK_SSB_MODE=$BEST timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $O/${TAG}_launches.csv python scripts/one_step.py > $O/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
-ADVK_SSB_MODE=$BEST timeout 400 python -m pytest tests/test_gpu_golden.py tests/test_gpu_fullsize.py -q -x > $O/${TAG}_pytest_best.log 2>&1; echo "pytest golden+fullsize (best mask) rc=$?" | tee -a $O/${TAG}_pytest_best.log
+ADVK_SSB_MODE=$BEST timeout 400 python -m pytest tests -m gpu -q -x > $O/${TAG}_pytest_best.log 2>&1; echo "pytest -m gpu (best mask as the default) rc=$?" | tee -a $O/${TAG}_pytest_best.log
 tail -3 $O/${TAG}_pytest_best.log
 ADVK_SSB_MODE=$BEST timeout 120 python bench.py --workload c2 --no-cpu-baseline --steps 50 > $O/${TAG}_bench_c2_best.json 2>> $O/${TAG}_bench.err; echo "bench c2 best rc=$?"
 timeout 120 python bench.py --workload c2 --no-cpu-baseline --steps 50 > $O/${TAG}_bench_c2_default.json 2>> $O/${TAG}_bench.err; echo "bench c2 default rc=$?"
