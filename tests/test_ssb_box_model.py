@@ -1,13 +1,17 @@
-"""Lane-level numpy model of `ss_step_bwd_box_kernel` (advchain_b200/csrc/advk_morph.cu).
+"""Lane-level numpy models of `ss_step_bwd_lean_kernel` (the default squaring-step adjoint) and
+`ss_step_bwd_box_kernel` (advchain_b200/csrc/advk_morph.cu).
 
-The warp-box variant of the squaring-step adjoint hands contributions from lane to lane along x, y
-and z before it issues a RED, and lets the Jacobian term ride on the corner that lands on the
-voxel itself.  Whether those hand-offs add up to the plain scatter for ANY field (ragged boxes at the
+The lean kernel hands the x1 corner column of a lane to its neighbour by WEIGHT (the receiver forms
+g*w0 + g_prev*w1_prev), redirects corners outside the volume to inside ones (their weight is exactly 0
+under border padding) and builds the Jacobian term by separable differences.  The warp-box variant
+hands contributions from lane to lane along x, y and z before it issues a RED, and lets the Jacobian
+term ride on the corner that lands on the voxel itself.  Whether those hand-offs add up to the plain
+scatter for ANY field (ragged boxes at the
 volume faces, displacements of many voxels, coordinates clipped by the border padding) is index
 logic that can be checked without a GPU: this test executes the kernel's statements for 32 lanes at a
 time, with CUDA's shuffle semantics, and compares with the direct adjoint
 (grid_sample(phi, phi, border, align_corners=True) backward, adv_morph.py:133-135 / 166-168).
-The GPU parity of the real kernel is in tests/test_gpu_kernels.py::test_morph_field (tile masks >= 16).
+The GPU parity of the real kernels is in tests/test_gpu_kernels.py::test_morph_field (tile masks >= 16).
 """
 import numpy as np
 import pytest
