@@ -1,6 +1,8 @@
 #!/bin/bash
 # Short GPU-box visit: take the squaring-step adjoint apart (scripts/diag_ssb.py) + one ncu capture of the
-# warp-box variant for the record.  Usage (through gpurun): bash scripts/gpu_exp_diag.sh <tag>
+# warp-box variant for the record.  Build the side libraries in the build container first
+# (bash scripts/build_diag.sh -> scripts/_diag/, git-ignored, shipped by gpurun), then through gpurun:
+#   bash scripts/gpu_exp_diag.sh <tag>
 TAG=${1:-r01l}
 O=gpurun_out
 mkdir -p $O
