@@ -28,4 +28,10 @@ def install_as_advchain():
     sys.modules["advchain.common.loss"] = loss
     sys.modules["advchain.common.utils"] = utils
     sys.modules["advchain.common.layers"] = layers
+    # the reference's per-class modules (user code imports e.g. advchain.augmentor.adv_bias.AdvBias)
+    from .augmentor import affine, base, bias, morph, noise, solver
+    for name, mod in (("adv_affine", affine), ("adv_bias", bias), ("adv_morph", morph), ("adv_noise", noise),
+                      ("adv_transformation_base", base), ("adv_compose_solver", solver)):
+        sys.modules["advchain.augmentor." + name] = mod
+        setattr(augmentor, name, mod)
     return root

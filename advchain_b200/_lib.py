@@ -139,16 +139,22 @@ def call(name, *args):
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.advk_last_error().decode()))
 
 
-def ptr(t):
-    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor of exactly `dtype` (None -> NULL).  The kernels launch
+    on the calling thread's current device and stream (`stream()`): a tensor living on another device is
+    refused here instead of being dereferenced on the wrong one."""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("advchain_b200 runs on CUDA tensors only (got %s); there is no CPU "
                            "fallback" % t.device)
-    if t.dtype not in (torch.float32, torch.float64) or not t.is_contiguous():
-        raise RuntimeError("advchain_b200: expected a contiguous fp32 tensor, got %s contiguous=%s"
-                           % (t.dtype, t.is_contiguous()))
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError("advchain_b200: expected a contiguous %s tensor, got %s contiguous=%s"
+                           % (dtype, t.dtype, t.is_contiguous()))
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("advchain_b200: tensor on %s but the current CUDA device is %d; run under "
+                           "`torch.cuda.device(tensor.device)` (one process per GPU sets it once)"
+                           % (t.device, torch.cuda.current_device()))
     return t.data_ptr()
 
 

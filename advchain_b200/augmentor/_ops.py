@@ -529,6 +529,7 @@ def pgd_update_(param, grad, step, mode, guard=None):
     n = param.shape[0]
     per = param.numel() // n
     ss = torch.empty(n, dtype=torch.float64, device=param.device)
-    call("advk_pgd_update_guarded", ptr(param), ptr(_f32c(grad)), float(step), mode, n, per, ptr(ss),
+    call("advk_pgd_update_guarded", ptr(param), ptr(_f32c(grad)), float(step), mode, n, per,
+         ptr(ss, torch.float64),
          None if guard is None else ptr(guard), stream())
     return param

@@ -140,13 +140,15 @@ class ComposeAdversarialTransformSolver(object):
         lo, hi = self.min_intensity, self.max_intensity
         if lo is not None and hi is not None:
             return lo, hi
-        key = (data.data_ptr(), data._version, tuple(data.shape))
-        if self._range_cache is None or self._range_cache[0] != key:
+        # cached on the tensor OBJECT (weak reference) + its version counter: an address does not identify
+        # a tensor (a new batch is usually allocated where the previous one was freed)
+        rc = self._range_cache
+        if rc is None or rc[0]() is not data or rc[3] != data._version:
             if self.shard is not None:
                 mn, mx = self.shard.global_minmax(data)           # min/max of the whole (sharded) batch
             else:
                 mn, mx = torch.aminmax(data.detach())
-            self._range_cache = (key, float(mn), float(mx))
+            self._range_cache = rc = (weakref.ref(data), float(mn), float(mx), data._version)
         return (self._range_cache[1] if lo is None else lo,
                 self._range_cache[2] if hi is None else hi)
 
@@ -484,6 +486,22 @@ class ComposeAdversarialTransformSolver(object):
         model.zero_grad()
 
     @staticmethod
+    def _config_fingerprint(t):
+        """Everything of a transform's configuration that a captured iteration bakes into kernel arguments."""
+        def flat(v):
+            if isinstance(v, (list, tuple)):
+                return tuple(flat(x) for x in v)
+            if isinstance(v, dict):
+                return tuple(sorted((k, flat(x)) for k, x in v.items()))
+            return v if isinstance(v, (int, float, str, bool, type(None))) else repr(v)
+        names = ("epsilon", "xi", "ignore_values", "image_padding_mode", "forward_interp", "backward_interp",
+                 "data_size", "vector_size", "control_point_spacing", "downscale", "interpolation_order",
+                 "use_log", "space", "rot", "scale", "shift", "num_steps")
+        fp = [(n, flat(getattr(t, n))) for n in names if hasattr(t, n)]
+        fp.append(("config", flat(getattr(t, "config_dict", None))))
+        return tuple(fp)
+
+    @staticmethod
     def _steps_from_norm2(norm2, min_steps):
         """adv_morph.py:159-162: smallest n >= min_steps with ||u|| / 2^n <= 0.5."""
         import math
@@ -568,7 +586,9 @@ class ComposeAdversarialTransformSolver(object):
         key = (id(model), model.training, mptrs, tuple(data.shape), tuple(init_output.shape), tuple(optimize_flags),
                float(step), tuple(id(t) for t in chain), tuple(t.power_iteration for t in chain),
                tuple(tuple(t.param.shape) for t in chain), rng, self.use_fused_chain,
-               tuple(self.divergence_types), tuple(self.divergence_weights))
+               tuple(self.divergence_types), tuple(self.divergence_weights), bool(self.is_gt),
+               None if self.class_weights is None else tuple(self.class_weights),
+               tuple(self._config_fingerprint(t) for t in chain))
         st = self._graphs.get(key)
         if isinstance(st, dict):
             objs = [r() for r in st["refs"]]
@@ -600,12 +620,9 @@ class ComposeAdversarialTransformSolver(object):
             while len(self._graphs) > _GRAPH_CACHE_MAX:          # least recently captured goes first
                 self._graphs.pop(next(iter(self._graphs)))
         st["data"].copy_(data.detach())
-        # the clean prediction usually is the same tensor for every call of a training step: skip the
-        # device-to-device refresh when neither its storage nor its version counter moved
-        tag = (init_output.data_ptr(), init_output._version, tuple(init_output.shape))
-        if st.get("init_tag") != tag:
-            st["init_output"].copy_(init_output.detach())
-            st["init_tag"] = tag
+        # always refreshed: (data_ptr, _version, shape) does not identify a tensor -- a training loop makes a
+        # new clean prediction every step, typically at the freed address of the previous one, version 0
+        st["init_output"].copy_(init_output.detach())
         for buf, p in zip(st["params"], start):
             buf.copy_(p)
         st["viol"].zero_()

@@ -73,7 +73,10 @@ def _fusable(output, reference, divergence_types, divergence_weights, scales, ma
     if mask is not None:
         if not mask.is_cuda or mask.shape[0] != output.shape[0] or mask.shape[2:] != output.shape[2:]:
             return False
-        if mask.shape[1] != 1 and not (mask.shape[1] == output.shape[1] and mask.stride(1) == 0):
+        # a K-channel view of ONE channel (the solver's valid-region mask).  An N x 1 x spatial mask changes
+        # the reference's Q9 divisor numel(mask)/K (loss.py:62-64) to N*S/K, which the kernel does not
+        # implement: it takes the PyTorch formulation below.
+        if not (mask.shape[1] == output.shape[1] and (mask.stride(1) == 0 or output.shape[1] == 1)):
             return False
     return True
 

@@ -358,74 +358,22 @@ ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename 
 //                      + mult * < d(sample)/d(coord) at y , g_k(y) >   spatial-Jacobian term
 // accumulated with vector REDs into ONE buffer `out` that must be zero on entry.
 //
-// Measured on B200 (profiles/r01i, r01j): the kernel is bound by L2 request traffic (2^d L1-missing
-// gathers + 2^d + 1 REDs per voxel).  A shared-memory tile version (stage phi on tile + halo, scatter
-// into a shared accumulator with an owner election, flush once) executed 1.55x the instructions at
-// 25 % occupancy and ran 2x slower, so the scatter goes straight to L2.  Variants (advk_morph_tune bits):
-//   LANE  neighbouring lanes combine contributions that land on the same voxel before the RED: lane
-//         i's x1 corner is lane i+1's x0 corner whenever both sample the same source row with
-//         consecutive x0 (always, for a smooth field) -- one shuffle hands the x1 contribution over,
-//         halving the REDs.  Lanes without a matching neighbour issue their own RED (exact for any field).
-//         (128^3, 8 steps: 494 us plain -> 399 us; pairing voxels in z per thread on top: 477 us, dropped.)
-//   ZSTORE zero the consumed upstream buffer in the kernel instead of by a memset node: 2 = after the
-//         REDs (default; 522 us vs 494 + 8 memsets), 1 = before them (1311 us: a store to a line whose
-//         load is still in flight stalls the LSU -- the counter-example is kept selectable).
-
-// ADVK_SSB_DIAG (never defined in the product build; scripts/build_diag.sh compiles side libraries
-// with it for scripts/diag_ssb.py): timing diagnostics that take the kernel apart -- 1: the REDs become
-// register adds + one plain store, 2: the gathers read the thread's own phi, 3: the REDs become plain
-// (racy) stores, 4 = 1 + 2.  Results are WRONG by construction; only the launch time means anything.
-#ifndef ADVK_SSB_DIAG
-#define ADVK_SSB_DIAG 0
-#endif
-template <typename T>
-__device__ __forceinline__ void ssb_red(T* addr, T val, float& sink) {
-  if (ADVK_SSB_DIAG == 1 || ADVK_SSB_DIAG == 4) sink += val.x + val.y;
-  else if (ADVK_SSB_DIAG == 3) *addr = val;
-  else atomicAdd(addr, val);
-}
-
-// Emits one corner row (y,z fixed; corners a0 and a0+1 along x) of one voxel: RED of c0 to a0 and c1
-// to a0+1, with the lane hand-off described above when LANE.
-template <int DIM, bool LANE>
-__device__ __forceinline__ void ssb_emit_row(typename V<DIM>::T* __restrict__ dst, int lane, bool v0, bool v1, int a0,
-                                             float c0x, float c0y, float c0z, float c1x, float c1y, float c1z,
-                                             float& sink) {
-  if (LANE) {
-    const unsigned FULL = 0xffffffffu;
-    const int a0_next = __shfl_down_sync(FULL, v0 ? a0 : -1, 1);
-    const bool hand = v1 && lane < 31 && a0_next == a0 + 1;
-    const float rx = __shfl_up_sync(FULL, hand ? c1x : 0.f, 1);
-    const float ry = __shfl_up_sync(FULL, hand ? c1y : 0.f, 1);
-    float rz = 0.f;
-    if (DIM == 3) rz = __shfl_up_sync(FULL, hand ? c1z : 0.f, 1);
-    if (lane > 0) { c0x += rx; c0y += ry; c0z += rz; }
-    if (v0) ssb_red(dst + a0, V<DIM>::make(c0x, c0y, c0z), sink);
-    if (v1 && !hand) ssb_red(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z), sink);
-  } else {
-    if (v0) ssb_red(dst + a0, V<DIM>::make(c0x, c0y, c0z), sink);
-    if (v1) ssb_red(dst + a0 + 1, V<DIM>::make(c1x, c1y, c1z), sink);
-  }
-}
-
-template <int DIM, bool LANE, int ZSTORE, int MB>
-__global__ void __launch_bounds__(256, MB)
-ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
-                   typename V<DIM>::T* __restrict__ out) {
+// ss_step_bwd_plain_kernel is the straightforward form (one RED per corner, validity predicates, the
+// caller zeroes `out` with a memset node): the A/B predecessor of the lean kernel below and the
+// independent implementation the parity tests compare it with (advk_morph_tune bit 0).
+// What was measured and dropped on B200 (shared-memory tiles, warp-box hand-offs along y and z, planar
+// field levels, stores before the REDs) is recorded in DESIGN.md section 3.2 and profiles/r01l_ssb_taken_apart.md.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+ss_step_bwd_plain_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, const typename V<DIM>::T* __restrict__ up,
+                         typename V<DIM>::T* __restrict__ out) {
   typedef typename V<DIM>::T T;
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
-  const bool live = p < g.S;
-  const i64 nb = (i64)n * g.S;
+  if (p >= g.S) return;
+  const i64 nb = (i64)blockIdx.y * g.S;
   const T* src = phi_prev + nb;
   T* dst = out + nb;
-  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
-  if (live) {
-    f = __ldg(src + p);
-    go = up[nb + p];
-    if (ZSTORE == 1) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
-  }
+  const T f = __ldg(src + p), go = up[nb + p];
   Axis ax = make_axis_border(f.x, g.W);
   Axis ay = make_axis_border(f.y, g.H);
   Axis az;
@@ -434,46 +382,29 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
   const int HW = g.H * g.W;
   const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
   float jx = 0.f, jy = 0.f, jz = 0.f;
-  float sink = 0.f;                                                  // ADVK_SSB_DIAG only
-  constexpr bool no_gather = ADVK_SSB_DIAG == 2 || ADVK_SSB_DIAG == 4;
 #pragma unroll
   for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-    const bool vz = dz ? az.v1 : az.v0;
-    const float wz = dz ? az.w1 : az.w0;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      const bool vy = dy ? ay.v1 : ay.v0;
-      const float wy = dy ? ay.w1 : ay.w0;
-      const bool row = live && vy && vz;
-      const bool v0 = row && ax.v0, v1 = row && ax.v1;
-      const int a0 = (az.i0 + dz) * HW + (ay.i0 + dy) * g.W + ax.i0;      // S < 2^31 (host-checked)
-      // Jacobian: sum over corners of (+-) <phi(corner), g> * (other-axis weights)
-      if (v0) {
-        T s0 = no_gather ? f : __ldg(src + a0);
-        float dot = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
-        jx -= dot * (wy * wz);
-        jy += (dy ? dot : -dot) * (ax.w0 * wz);
-        if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w0 * wy);
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        if (!((dx ? ax.v1 : ax.v0) && (dy ? ay.v1 : ay.v0) && (dz ? az.v1 : az.v0))) continue;
+        const float wx = dx ? ax.w1 : ax.w0, wy = dy ? ay.w1 : ay.w0, wz = dz ? az.w1 : az.w0;
+        const int a = (az.i0 + dz) * HW + (ay.i0 + dy) * g.W + ax.i0 + dx;
+        const T s = __ldg(src + a);
+        const float dot = s.x * gx + s.y * gy + V<DIM>::z(s) * gz;
+        jx += (dx ? dot : -dot) * (wy * wz);
+        jy += (dy ? dot : -dot) * (wx * wz);
+        if (DIM == 3) jz += (dz ? dot : -dot) * (wx * wy);
+        const float w = wx * wy * wz;
+        atomicAdd(dst + a, V<DIM>::make(gx * w, gy * w, gz * w));
       }
-      if (v1) {
-        T s1 = no_gather ? f : __ldg(src + a0 + 1);
-        float dot = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
-        jx += dot * (wy * wz);
-        jy += (dy ? dot : -dot) * (ax.w1 * wz);
-        if (DIM == 3) jz += (dz ? dot : -dot) * (ax.w1 * wy);
-      }
-      const float w0 = ax.w0 * wy * wz, w1 = ax.w1 * wy * wz;
-      ssb_emit_row<DIM, LANE>(dst, lane, v0, v1, a0, gx * w0, gy * w0, gz * w0, gx * w1, gy * w1, gz * w1, sink);
     }
   }
-  if (live) {
-    if (ADVK_SSB_DIAG == 1 || ADVK_SSB_DIAG == 4) dst[p] = V<DIM>::make(jx * ax.mult + sink, jy * ay.mult, jz * az.mult);
-    else atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
-    if (ZSTORE == 2) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);
-  }
+  atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
 }
 
-// Lean variant of the LANE kernel.  Taking the kernel apart on B200 (scripts/diag_ssb.py, gpurun_out/r01l:
+// Lean adjoint.  Taking the plain kernel apart on B200 (profiles/r01l_ssb_taken_apart.md:
 // 50 us per launch at 128^3; 35 us with the REDs turned into register adds, 42 us with the gathers turned
 // into register moves, 29 us with both gone -- and 48 us with the REDs turned into plain stores) shows that
 // the skeleton, i.e. instruction issue, is the larger part of a launch, so this variant spends fewer
@@ -485,7 +416,7 @@ ss_step_bwd_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, type
 //     neighbour whose corner (0,0,0) is one voxel further sees the same rows with the same validity);
 //   * the Jacobian term is built from the 2^d dot products <phi(corner), g> by separable differences
 //     (interpolate along x, difference along y, ...) instead of three weighted sums over all corners.
-// Same result as LANE up to fp32 summation order.
+// Same result as the plain kernel up to fp32 summation order.
 template <int DIM, bool ZS>
 __global__ void __launch_bounds__(256)
 ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
@@ -590,227 +521,28 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
       }
     }
     atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
-    if (ZS) upn[p] = V<DIM>::make(0.f, 0.f, 0.f);               // after the REDs (see ZSTORE above)
+    if (ZS) upn[p] = V<DIM>::make(0.f, 0.f, 0.f);               // AFTER the REDs: a store to a line whose load is in flight stalls the LSU
   }
 }
 
-// Warp-box variant of the same adjoint.  The RED count per voxel is what the kernel pays for (ncu,
-// profiles/r01final_ncu_full.md: 2.9 RED sectors per voxel at L2, l1tex -> xbar requests the busiest
-// unit), so the combining of the LANE variant is extended from x to all axes and to the Jacobian term:
-//   * a warp owns a box of 2^LBX x 2^LBY x 2^LBZ voxels (x fastest in the lane id), a CTA 2x2x2 boxes
-//     (2x4 in 2-D): after the x hand-off (lane+1) every corner row is one value per lane; the dy=1 rows
-//     are then handed to lane + 2^LBX (whose dy=0 row is the same source row whenever the field is
-//     smooth), and the dz=1 row to lane + 2^(LBX+LBY).  Every hand-off is checked on the exact target
-//     address, so lanes without a matching neighbour issue their own RED and the result is the same
-//     sum for ANY field (only the fp32 summation order differs);
-//   * the Jacobian term of voxel p is added to the corner contribution that lands on p itself (there
-//     is one whenever the displacement is below one voxel -- all early squaring levels) instead of
-//     being a RED of its own; it needs all 2^d gathers, so the gathers run as a first pass.
-// MB = resident CTAs per SM asked of ptxas: 4 = no register cap (57 registers in 3-D), 5 = 48 registers
-// with 12-20 bytes of spill (62 % instead of 50 % occupancy).
-// RED lane-operations per voxel (smooth field, sub-voxel displacement): 32x1x1 -> 4.1, 16x2x1 -> 3.3,
-// 8x4x1 and 8x2x2 -> 3.0, against 5.1 for LANE.  2^LBX * 16 B is the contiguous run of every access.
-template <int DIM, int LBX, int LBY, int LBZ, bool ZS, int MB>
-__global__ void __launch_bounds__(256, MB)
-ss_step_bwd_box_kernel(Dims g, int ctz, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
-                       typename V<DIM>::T* __restrict__ out) {
-  typedef typename V<DIM>::T T;
-  static_assert(LBX + LBY + LBZ == 5, "a box is one warp");
-  static_assert(DIM == 3 || LBZ == 0, "2-D boxes are flat");
-  constexpr int BX = 1 << LBX, BY = 1 << LBY, BZ = 1 << LBZ;
-  constexpr int NZ = DIM == 3 ? 2 : 1;
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lx = lane & (BX - 1), ly = (lane >> LBX) & (BY - 1), lz = lane >> (LBX + LBY);
-  const int wx = warp & 1, wy = DIM == 3 ? ((warp >> 1) & 1) : (warp >> 1), wz = DIM == 3 ? (warp >> 2) : 0;
-  int n = blockIdx.z, cz = 0;
-  if (DIM == 3) { n = blockIdx.z / ctz; cz = blockIdx.z - n * ctz; }
-  const int x = (blockIdx.x * 2 + wx) * BX + lx;
-  const int y = (blockIdx.y * (DIM == 3 ? 2 : 4) + wy) * BY + ly;
-  const int z = (cz * 2 + wz) * BZ + lz;
-  const bool live = x < g.W && y < g.H && z < g.D;
-  const int p = (z * g.H + y) * g.W + x;                          // S < 2^31 (host-checked); used when live
-  const i64 nb = (i64)n * g.S;
-  const T* src = phi_prev + nb;
-  T* dst = out + nb;
-  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
-  if (live) {
-    f = __ldg(src + p);
-    go = up[nb + p];
-  }
-  Axis ax = make_axis_border(f.x, g.W);
-  Axis ay = make_axis_border(f.y, g.H);
-  Axis az;
-  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
-  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
-  const int HW = g.H * g.W;
-  const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
-  const int a000 = az.i0 * HW + ay.i0 * g.W + ax.i0;             // corner (0,0,0): always in bounds (border)
-  // pass 1: the 2^d gathers -> Jacobian term  sum over corners of (+-) <phi(corner), g> * (other-axis weights)
-  float jx = 0.f, jy = 0.f, jz = 0.f;
-#pragma unroll
-  for (int dz = 0; dz < NZ; ++dz) {
-    const bool vz = dz ? az.v1 : az.v0;
-    const float wz_ = dz ? az.w1 : az.w0;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const bool row = live && (dy ? ay.v1 : ay.v0) && vz;
-      const float wy_ = dy ? ay.w1 : ay.w0;
-      const int a0 = a000 + dz * HW + dy * g.W;
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        if (row && (dx ? ax.v1 : ax.v0)) {
-          const T s = __ldg(src + a0 + dx);
-          const float dot = s.x * gx + s.y * gy + V<DIM>::z(s) * gz;
-          const float wx_ = dx ? ax.w1 : ax.w0;
-          jx += (dx ? dot : -dot) * (wy_ * wz_);
-          jy += (dy ? dot : -dot) * (wx_ * wz_);
-          if (DIM == 3) jz += (dz ? dot : -dot) * (wx_ * wy_);
-        }
-      }
-    }
-  }
-  jx *= ax.mult; jy *= ay.mult; jz *= az.mult;
-  // pass 2: scatter.  A hand-off needs the neighbour's corner (0,0,0) to sit exactly one voxel further
-  // along the axis: then (border padding: corner 0 is always in bounds, corner 1 unless the coordinate
-  // sits on the last voxel) both lanes see the same rows with the same validity, so ONE test per axis
-  // covers all rows.  Along x the sender ships its upstream value once and one weight per row, the
-  // receiver forms the sum with FMAs; along y and z the row sums themselves travel.
-  const int key = live ? a000 : -1;
-  const int next_x = __shfl_down_sync(FULL, key, 1);              // (every shuffle is executed by all lanes)
-  const bool hand_x = live && ax.v1 && lx < BX - 1 && next_x == a000 + 1;
-  const float px = __shfl_up_sync(FULL, gx, 1), py = __shfl_up_sync(FULL, gy, 1);
-  const float pz = DIM == 3 ? __shfl_up_sync(FULL, gz, 1) : 0.f;
-  // the Jacobian term rides on the corner-0 contribution of the row that lands on p itself
-  int frow = -1;
-  if (live && ax.i0 == x) {
-    const int ddy = y - ay.i0, ddz = DIM == 3 ? z - az.i0 : 0;
-    if ((unsigned)ddy < 2u && (unsigned)ddz < 2u) frow = ddz * 2 + ddy;
-  }
-  float R[NZ][2][3];
-#pragma unroll
-  for (int dz = 0; dz < NZ; ++dz) {
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const bool row = live && (dy ? ay.v1 : ay.v0) && (dz ? az.v1 : az.v0);
-      const float wr = (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
-      const float w0 = ax.w0 * wr, w1 = ax.w1 * wr;
-      float ws = __shfl_up_sync(FULL, (hand_x && row) ? w1 : 0.f, 1);
-      if (lane == 0) ws = 0.f;
-      float c0x = gx * w0 + px * ws, c0y = gy * w0 + py * ws, c0z = gz * w0 + pz * ws;
-      if (frow == dz * 2 + dy) { c0x += jx; c0y += jy; c0z += jz; }
-      if (row && ax.v1 && !hand_x) atomicAdd(dst + (a000 + dz * HW + dy * g.W + 1), V<DIM>::make(gx * w1, gy * w1, gz * w1));
-      R[dz][dy][0] = c0x; R[dz][dy][1] = c0y; R[dz][dy][2] = c0z;
-    }
-  }
-  // y: the dy=1 rows go to the lane one box row up, whose dy=0 rows are the same source rows
-  {
-    bool hand_y = false;
-    if (LBY > 0) {
-      const int next_y = __shfl_down_sync(FULL, key, BX);
-      hand_y = live && ay.v1 && ly < BY - 1 && next_y == a000 + g.W;
-    }
-#pragma unroll
-    for (int dz = 0; dz < NZ; ++dz) {
-      const bool rv1 = live && ay.v1 && (dz ? az.v1 : az.v0);
-      if (LBY > 0) {
-        const bool h = hand_y && rv1;
-        const float rx = __shfl_up_sync(FULL, h ? R[dz][1][0] : 0.f, BX);
-        const float ry = __shfl_up_sync(FULL, h ? R[dz][1][1] : 0.f, BX);
-        const float rz = DIM == 3 ? __shfl_up_sync(FULL, h ? R[dz][1][2] : 0.f, BX) : 0.f;
-        if (ly > 0) { R[dz][0][0] += rx; R[dz][0][1] += ry; R[dz][0][2] += rz; }
-      }
-      if (rv1 && !hand_y) atomicAdd(dst + (a000 + dz * HW + g.W), V<DIM>::make(R[dz][1][0], R[dz][1][1], R[dz][1][2]));
-    }
-  }
-  // z: the dz=1 row goes to the lane one box plane up
-  if (DIM == 3) {
-    const bool rv1 = live && az.v1;
-    bool hand_z = false;
-    if (LBZ > 0) {
-      const int next_z = __shfl_down_sync(FULL, key, BX * BY);
-      hand_z = rv1 && lz < BZ - 1 && next_z == a000 + HW;
-      const float rx = __shfl_up_sync(FULL, hand_z ? R[NZ - 1][0][0] : 0.f, BX * BY);
-      const float ry = __shfl_up_sync(FULL, hand_z ? R[NZ - 1][0][1] : 0.f, BX * BY);
-      const float rz = __shfl_up_sync(FULL, hand_z ? R[NZ - 1][0][2] : 0.f, BX * BY);
-      if (lz > 0) { R[0][0][0] += rx; R[0][0][1] += ry; R[0][0][2] += rz; }
-    }
-    if (rv1 && !hand_z) atomicAdd(dst + (a000 + HW), V<DIM>::make(R[NZ - 1][0][0], R[NZ - 1][0][1], R[NZ - 1][0][2]));
-  }
-  if (live) {
-    atomicAdd(dst + a000, V<DIM>::make(R[0][0][0], R[0][0][1], R[0][0][2]));
-    if (frow < 0) atomicAdd(dst + p, V<DIM>::make(jx, jy, jz));
-    if (ZS) up[nb + p] = V<DIM>::make(0.f, 0.f, 0.f);         // after the REDs (see ZSTORE above)
-  }
-}
-
-// bit 0: LANE; bits 2-3: ZSTORE (0 memset nodes, 1 zero before the REDs -- slow, kept as the
-// measured counter-example --, 2 zero after the REDs); bits 4-6: warp-box kernel, shape 1 = 32x1x1,
-// 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (3-D only; 2-D runs 8x4), 0 = the kernels above; bit 7: box kernel
-// (or, with shape 0 and zero-after, the kernel above) compiled for 5 resident CTAs per SM; bit 8: the lean
-// kernel (x hand-off, fewer instructions); bit 9: the lean FORWARD step (ss_step_lean_kernel).
-// Default 776: both lean kernels, zero after the REDs.
+// advk_morph_tune / ADVK_SSB_MODE: 0 = the lean kernels (default), 1 = the plain predecessors
+// (predicated forward step, one-RED-per-corner adjoint with memset nodes).
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 1021) : 776;
+    g_ssb_mode = e ? (atoi(e) & 1) : 0;
   }
   return g_ssb_mode;
-}
-
-template <int DIM, int LBX, int LBY, int LBZ, int MB>
-static bool launch_ss_step_bwd_box(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
-                                   typename V<DIM>::T* out, bool zs, cudaStream_t st) {
-  const int TX = 2 << LBX, TY = (DIM == 3 ? 2 : 4) << LBY, TZ = DIM == 3 ? (2 << LBZ) : 1;
-  const i64 ctx = (g.W + TX - 1) / TX, cty = (g.H + TY - 1) / TY, ctz = (g.D + TZ - 1) / TZ;
-  if (cty > 65535 || ctz * g.N > 65535) return false;           // grid limits: the caller falls back
-  dim3 grid((unsigned)ctx, (unsigned)cty, (unsigned)(ctz * g.N));
-  if (zs) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_box_kernel<DIM, LBX, LBY, LBZ, true, MB><<<grid, 256, 0, st>>>(g, (int)ctz, phi_prev, up, out)));
-  else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_box_kernel<DIM, LBX, LBY, LBZ, false, MB><<<grid, 256, 0, st>>>(g, (int)ctz, phi_prev, up, out)));
-  return true;
-}
-
-template <int DIM, bool LANE>
-static void launch_ss_step_bwd_z(int zs, bool occ5, const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
-                                 typename V<DIM>::T* out, cudaStream_t st) {
-  dim3 grid(blocks_for(g.S, 256), g.N);
-  if (zs == 1) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 1, 4><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-  else if (zs == 2 && occ5) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 2, 5><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-  else if (zs == 2) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 2, 4><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-  else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_kernel<DIM, LANE, 0, 4><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-}
-
-template <int DIM, int MB>
-static bool launch_ss_step_bwd_shape(int shape, const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
-                                     typename V<DIM>::T* out, bool zs, cudaStream_t st) {
-  if (shape == 1) return launch_ss_step_bwd_box<DIM, 5, 0, 0, MB>(g, phi_prev, up, out, zs, st);
-  if (shape == 2) return launch_ss_step_bwd_box<DIM, 4, 1, 0, MB>(g, phi_prev, up, out, zs, st);
-  if (shape == 3 || DIM == 2) return launch_ss_step_bwd_box<DIM, 3, 2, 0, MB>(g, phi_prev, up, out, zs, st);
-  return launch_ss_step_bwd_box<DIM, 3, DIM == 3 ? 1 : 2, DIM == 3 ? 1 : 0, MB>(g, phi_prev, up, out, zs, st);
 }
 
 template <int DIM>
 static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
                                typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
-  const int mode = ssb_mode();
-  const int zs = may_zero_up ? ((mode >> 2) & 3) : 0;
-  if (mode & 256) {
-    dim3 grid(blocks_for(g.S, 256), g.N);
-    if (zs) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-    else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-    return;
-  }
-  const int shape = (mode >> 4) & 7;
-  if (shape) {
-    const bool z = zs != 0;
-    bool ok;
-    if (mode & 128) ok = launch_ss_step_bwd_shape<DIM, 5>(shape, g, phi_prev, up, out, z, st);
-    else ok = launch_ss_step_bwd_shape<DIM, 4>(shape, g, phi_prev, up, out, z, st);
-    if (ok) return;
-  }
-  if (mode & 1) launch_ss_step_bwd_z<DIM, true>(zs, (mode & 128) != 0, g, phi_prev, up, out, st);
-  else launch_ss_step_bwd_z<DIM, false>(zs, (mode & 128) != 0, g, phi_prev, up, out, st);
+  dim3 grid(blocks_for(g.S, 256), g.N);
+  if (ssb_mode() & 1) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_plain_kernel<DIM><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+  else if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+  else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1196,7 +928,7 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   float inv2n = 1.0f / (float)(1u << nb);
   if (norm2_out) cudaMemsetAsync(norm2_out, 0, sizeof(float), st);
   launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, norm2_out, st);     // sum |u|^2 as a by-product when asked for
-  const bool lean = (ssb_mode() & 512) != 0;
+  const bool lean = (ssb_mode() & 1) == 0;
   for (int k = 1; k <= nb; ++k) {
     if (lean) ADVK_LAUNCH(K_ss_step, st, ss_step_lean_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
     else ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
@@ -1228,7 +960,7 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, g_off + 3 * F, st);
   // dL/dphi_n = g_off ; walk the squaring steps back, ping-ponging between two buffers that are
   // zeroed by memset nodes (g_off is kept for the Q1 subtraction below)
-  const bool self_zero = ((ssb_mode() >> 2) & 3) != 0;
+  const bool self_zero = (ssb_mode() & 1) == 0;       // the lean adjoint zeroes the buffer it consumed
   if (self_zero) cudaMemsetAsync(buf[0], 0, sizeof(T) * F * (nb > 1 ? 2 : 1), st);
   T* cur = g_off;
   for (int k = nb; k >= 1; --k) {
@@ -1268,7 +1000,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 1021;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 1;
   return prev;
 }
 

@@ -155,16 +155,12 @@ size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cf
 int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
                          const void* levels, const void* field_out, const void* g_field,
                          void* scratch, float* lr_scratch, float* g_v, void* stream);
-/* Kernel variant of the squaring-step backward (A/B timing and tests): bit 0 = neighbouring lanes
- * combine contributions before the RED; bits 2-3 = who zeroes the ping-pong buffers: 0 memset nodes,
- * 2 (value 8) the kernel, after its REDs, 1 (value 4) the kernel, before its REDs (slow; measured
- * counter-example); bits 4-6 = warp-box kernel (hand-offs along x, y and z, Jacobian term folded into
- * a corner RED) with box shape 1 = 32x1x1, 2 = 16x2x1, 3 = 8x4x1, 4 = 8x2x2 (2-D: 8x4), 0 = off;
- * bit 7 = box kernel compiled for 5 resident CTAs per SM; bit 8 (256) = lean adjoint kernel (x hand-off by
- * weight, no validity predicates: an outside corner has weight 0 under border padding and is redirected
- * to an inside one); bit 9 (512) = lean forward step.  Default 776 (both lean kernels, zeroing after the REDs); environment
- * ADVK_SSB_MODE.
- * Results agree up to fp32 summation order.  A negative mask only queries; returns the previous mask. */
+/* Kernel variant of the squaring steps (A/B timing and tests): 0 = the lean kernels (default: no
+ * validity predicates -- an outside corner has weight 0 under border padding and is redirected to an inside
+ * one --, x hand-off by weight before the RED, the adjoint zeroes the ping-pong buffer it consumed);
+ * 1 = the plain predecessors (predicated forward step; one RED per corner, memset nodes).  Environment
+ * ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries; returns the
+ * previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
 
 /* ---- AdvNoise / AdvBias: intensity stage ------------------------------------------------

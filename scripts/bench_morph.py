@@ -58,19 +58,19 @@ def run(vn, mask, reps=5):
 
 ssb_us = {}
 agree = {}
-masks = [int(m) for m in os.environ.get("BENCH_MORPH_MASKS", "9,776,264,521").split(",")]
+masks = [int(m) for m in os.environ.get("BENCH_MORPH_MASKS", "0").split(",")]
 for vn in vnorms:
-    base = run(vn, 0)
+    base = run(vn, 1)
     for mask in masks:
         out = run(vn, mask)
         ef = float((out[0] - base[0]).abs().max() / base[0].abs().max())
         eg = float((out[1] - base[1]).abs().max() / base[1].abs().max())
         agree[mask] = agree.get(mask, True) and ef < 1e-6 and eg < 1e-4
-        print("   mask %d vs 0: field rel err %.2e, grad rel err %.2e" % (mask, ef, eg), flush=True)
+        print("   mask %d vs 1 (plain): field rel err %.2e, grad rel err %.2e" % (mask, ef, eg), flush=True)
 ok = [m for m in masks if agree.get(m)]
-best = min(ok, key=lambda m: ssb_us[m]) if ok else 9
+best = min(ok, key=lambda m: ssb_us[m]) if ok else 0
 print("ss_step_bwd us per build (sum over vnorms): %s -> best %d" % (
-    " ".join("%d=%.1f" % (m, ssb_us[m]) for m in [0] + masks), best), flush=True)
+    " ".join("%d=%.1f" % (m, ssb_us[m]) for m in [1] + masks), best), flush=True)
 if os.environ.get("BENCH_MORPH_OUT"):
     with open(os.environ["BENCH_MORPH_OUT"], "w") as fh:
         json.dump({"workload": wl, "us": {str(m): ssb_us[m] for m in ssb_us}, "agree": {str(m): bool(v) for m, v in agree.items()},

@@ -14,7 +14,7 @@ from advchain_b200 import _lib  # noqa: E402
 from advchain_b200.augmentor import AdvMorph  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "m128"
-masks = [int(a) for a in sys.argv[2:]] or [0, 9]
+masks = [int(a) for a in sys.argv[2:]] or [0, 1]
 d, size, chain = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
 cfg = bench.make_cfgs(d, size)["morph"]

