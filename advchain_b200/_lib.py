@@ -90,7 +90,7 @@ SIGNATURES = {
     "advk_bias_scratch_floats": (_Z, [_G, C.POINTER(BiasCfg)]),
     "advk_bias_upsample_adjoint": (_I, [_G, C.POINTER(BiasCfg), _P, _P, _P, _P]),
     "advk_chain_set_cooperative": (_I, [_I]),
-    "advk_chain_tune": (_I, [_I, _I]),
+    "advk_chain_set_lean": (_I, [_I]),
     "advk_chain_set_packed": (_I, [_I]),
     "advk_chain_workspace_floats": (_I, [C.POINTER(ChainDesc), C.POINTER(_Z), C.POINTER(_Z)]),
     "advk_chain_apply_fwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),

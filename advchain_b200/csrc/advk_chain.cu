@@ -43,6 +43,7 @@ struct Stage {
   const float* src; float* dst;
   const float* msrc; float* mdst; int binarize;
   int src_pk, dst_pk;        // channel-packed (float4 per voxel per group of 4 channels) source / destination
+  int src_vm, dst_vm;        // lean path, C == 1: float2 {value, mask} per voxel (see advk_chain_lean.cuh)
   // adjoint
   const float* g_dst; float* g_src; int zero_g_src;
   float* g_src_user;         // packed mode, first stage: planar user buffer the packed g_src is unpacked into
@@ -57,8 +58,14 @@ struct Program {
   FastDiv ftps;
   int interleave;   // 0: block owns a contiguous tile range; 1: tiles dealt round-robin
   i64 n_tiles;
+  int lean;         // runs the specialised per-stage kernels (advk_chain_lean.cuh)
+  const float* user_src; float* src_packed;   // lean + pack: the chain input and its packed copy (stash)
   Stage st[MAX_STAGES];
 };
+
+}  // namespace advk
+#include "advk_chain_lean.cuh"
+namespace advk {
 
 template <int DIM> struct Stencil { Axis x, y, z; };
 
@@ -749,13 +756,38 @@ static int coop_grid(K kernel) {
   return sms * occ;
 }
 
+static int g_lean = -1;
+static bool lean_enabled() {
+  if (g_lean < 0) {
+    const char* e = getenv("ADVK_CHAIN_LEAN");
+    g_lean = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_lean == 1;
+}
+
+// zeros padding + linear interpolation + no pad values on every warp stage (the defaults of the reference's
+// constructors and of every BASELINE workload); anything else runs the generic executor above
+static bool lean_eligible(const Program& P) {
+  if (!lean_enabled() || P.g.S >= (1LL << 29) || P.g.N > 65535) return false;
+  for (int k = 0; k < P.n; ++k) {
+    const Stage& s = P.st[k];
+    if (s.kind == ADVK_STAGE_INTENSITY) continue;
+    if (s.pad != ADVK_PAD_ZEROS || s.interp != ADVK_INTERP_LINEAR || s.pv) return false;
+  }
+  if (P.pack && P.do_clamp) return false;
+  return true;
+}
+
 // intermediates are laid out in slots rounded up to 4 floats so that every slot is 16-byte aligned
 static inline i64 slot_floats(i64 n) { return (n + 3) & ~(i64)3; }
 
-// Stash layout (floats): for k = 0 .. n-2: dst of stage k (N*C*S); then, if want_mask, one N*S
-// mask buffer per warp stage except the last warp stage (whose mask output is `mask_out`).
+// Stash layout (floats): for k = 0 .. n-2: dst of stage k (N*C*S), followed -- if want_mask and stage k is a
+// warp stage other than the last warp stage (whose mask output is `mask_out`) -- by its N*S mask; then, for the
+// channel-packed prediction path, one N*C*S slot for the packed copy of the chain input.
+// `bwd`: the adjoint rebuilds the forward's data-path pointers (same stash layout, masks included) but has
+// no chain / mask outputs.
 static bool build_program(const advk_chain_desc* d, Program& P, const float* src, const float* mask_src,
-                          float* stash, float* out, float* mask_out) {
+                          float* stash, float* out, float* mask_out, bool bwd = false) {
   if (!d || !make_dims(&d->g, P.g) || d->C < 1 || d->n_stages < 1 || d->n_stages > MAX_STAGES) return false;
   P.C = d->C; P.n = d->n_stages; P.first_bwd = 0;
   P.do_clamp = d->do_clamp; P.lo = d->clamp_lo; P.hi = d->clamp_hi; P.want_mask = d->want_mask;
@@ -772,7 +804,7 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
     else all_warps = false;
   }
   P.pack = (pack_enabled() && all_warps && P.n >= 2 && (P.C % 4) == 0) ? 4 : 0;
-  float* mstash = stash ? stash + (i64)(P.n - 1) * ncs : nullptr;
+  float* cursor = stash;
   const float* cur = src;
   const float* mcur = mask_src;
   for (int k = 0; k < P.n; ++k) {
@@ -806,41 +838,37 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
     if (k == P.n - 1) s.dst = out;
     else {
       if (!stash) return false;
-      s.dst = stash + (i64)k * ncs;
+      s.dst = cursor;
+      cursor += ncs;
     }
     cur = s.dst;
     if (P.want_mask && a.kind != ADVK_STAGE_INTENSITY) {
       s.msrc = mcur;
-      if (k == last_warp) { s.mdst = mask_out; s.binarize = d->binarize_mask; if (!mask_out) return false; }
-      else { s.mdst = mstash; mstash += ns; }
+      if (k == last_warp) { s.mdst = mask_out; s.binarize = d->binarize_mask; if (!mask_out && !bwd) return false; }
+      else { s.mdst = cursor; cursor += ns; }        // right behind the stage's data slot (see dst_vm)
       mcur = s.mdst;
+    }
+  }
+  P.user_src = src;
+  P.src_packed = (P.pack && stash) ? cursor : nullptr;
+  P.lean = lean_eligible(P) ? 1 : 0;
+  if (P.lean && P.C == 1 && !P.pack) {
+    // value + mask interleaved between two consecutive warp stages (the mask slot follows the data slot)
+    for (int k = 0; k + 1 < P.n; ++k) {
+      Stage& s = P.st[k];
+      Stage& t = P.st[k + 1];
+      if (s.kind != ADVK_STAGE_INTENSITY && t.kind != ADVK_STAGE_INTENSITY && s.mdst && s.mdst == s.dst + ncs &&
+          t.msrc == s.mdst) {
+        s.dst_vm = 1; t.src_vm = 1;
+      }
     }
   }
   return true;
 }
 
-// Tuning knobs (environment, read once; advk_chain_tune() overrides): resident blocks per SM the
-// kernels are compiled for (register cap) and the tile-to-block assignment.
-static int g_minb = -1, g_minb_bwd = -1, g_interleave = -1;
-static bool minb_ok(int v) { return v == 2 || v == 3 || v == 4 || v == 6; }
-static void tune_defaults() {
-  if (g_minb < 0) {
-    const char* e = getenv("ADVK_CHAIN_MINB");
-    g_minb = e ? atoi(e) : 4;
-    if (!minb_ok(g_minb)) g_minb = 4;
-  }
-  if (g_minb_bwd < 0) {
-    // the adjoint keeps the corner table, per-corner partial sums and the theta accumulators live:
-    // ~110 registers without spills, so it is compiled for 3 resident CTAs (80 regs, 80 B spilled)
-    const char* e = getenv("ADVK_CHAIN_MINB_BWD");
-    g_minb_bwd = e ? atoi(e) : 3;
-    if (!minb_ok(g_minb_bwd)) g_minb_bwd = 3;
-  }
-  if (g_interleave < 0) {
-    const char* e = getenv("ADVK_CHAIN_INTERLEAVE");
-    g_interleave = (e && e[0] == '0') ? 0 : 1;      // measured: round-robin tiles 5-15 % faster (r01f)
-  }
-}
+// Generic executor: compiled for 4 (forward) / 3 (adjoint: corner table + per-corner partial sums + theta
+// accumulators) resident CTAs per SM; tiles dealt round-robin (measured 5-15 % faster than contiguous ranges).
+constexpr int GEN_MINB_FWD = 4, GEN_MINB_BWD = 3;
 
 template <int DIM, int MINB, bool PK>
 static int launch_fwd_p(Program& P, cudaStream_t st) {
@@ -885,46 +913,146 @@ static int launch_bwd_t(Program& P, cudaStream_t st) {
   return P.pack ? launch_bwd_p<DIM, MINB, true>(P, st) : launch_bwd_p<DIM, MINB, false>(P, st);
 }
 
-template <int DIM>
-static int launch_fwd(Program& P, cudaStream_t st) {
-  tune_defaults();
-  P.interleave = g_interleave;
-  switch (g_minb) {
-    case 2: return launch_fwd_t<DIM, 2>(P, st);
-    case 3: return launch_fwd_t<DIM, 3>(P, st);
-    case 6: return launch_fwd_t<DIM, 6>(P, st);
-    default: return launch_fwd_t<DIM, 4>(P, st);
+
+// ---- lean per-stage launches (advk_chain_lean.cuh) ------------------------------------------------
+static void lean_fill_int(const Program& P, const Stage& s, bool last, LeanInt& a) {
+  a.g = P.g; a.C = P.C; a.order = s.order; a.ns = s.ns; a.use_ig = s.use_ig; a.ig = s.ig; a.b = s.b;
+  a.src = s.src; a.delta = s.delta; a.low = s.low; a.dst = s.dst;
+  a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
+  a.g_dst = s.g_dst; a.g_src = s.g_src; a.g_delta = s.g_delta; a.g_up = s.g_up;
+}
+
+template <int DIM, bool FIELD>
+static void lean_launch_warp_fwd(const Program& P, const Stage& s, int k, cudaStream_t st) {
+  const bool last = (k == P.n - 1);
+  LeanFwd a;
+  a.g = P.g; a.C = P.C; a.src = s.src; a.dst = s.dst; a.phi = s.phi; a.theta = s.theta;
+  a.msrc = s.msrc; a.mdst = s.mdst; a.binarize = s.binarize;
+  a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
+  const dim3 grid(blocks_for(P.g.S, 256), P.g.N);
+  const int mm = s.mdst ? (s.msrc ? 2 : 1) : 0;
+  if (!P.pack) {
+#define ADVK_LF(MM, VS, VD) ADVK_LAUNCH(K_chain_img_fwd, st, (lean_warp_fwd_kernel<DIM, FIELD, MM, VS, VD><<<grid, 256, 0, st>>>(a)))
+    if (s.src_vm && s.dst_vm) ADVK_LF(2, true, true);
+    else if (s.src_vm) ADVK_LF(2, true, false);
+    else if (s.dst_vm && mm == 2) ADVK_LF(2, false, true);
+    else if (s.dst_vm) ADVK_LF(1, false, true);
+    else if (mm == 0) ADVK_LF(0, false, false);
+    else if (mm == 1) ADVK_LF(1, false, false);
+    else ADVK_LF(2, false, false);
+#undef ADVK_LF
+  } else {
+    if (k == 0) a.src = P.src_packed;            // the packed copy of the chain input
+#define ADVK_LF(MM, DP) ADVK_LAUNCH(K_chain_pk_fwd, st, (lean_warp_fwd_pk_kernel<DIM, FIELD, MM, DP><<<grid, 256, 0, st>>>(a)))
+#define ADVK_LF2(DP) do { if (mm == 0) ADVK_LF(0, DP); else if (mm == 1) ADVK_LF(1, DP); else ADVK_LF(2, DP); } while (0)
+    if (s.dst_pk) ADVK_LF2(true);
+    else ADVK_LF2(false);
+#undef ADVK_LF2
+#undef ADVK_LF
   }
 }
 
 template <int DIM>
-static int launch_bwd(Program& P, cudaStream_t st) {
-  tune_defaults();
-  P.interleave = g_interleave;
-  switch (g_minb_bwd) {
-    case 2: return launch_bwd_t<DIM, 2>(P, st);
-    case 3: return launch_bwd_t<DIM, 3>(P, st);
-    case 6: return launch_bwd_t<DIM, 6>(P, st);
-    case 4: return launch_bwd_t<DIM, 4>(P, st);
-    default: return launch_bwd_t<DIM, 3>(P, st);
+static int lean_fwd(Program& P, cudaStream_t st) {
+  const dim3 grid(blocks_for(P.g.S, 256), P.g.N);
+  if (P.pack) {
+    if (!P.src_packed) { set_error("chain_apply_fwd: stash is NULL"); return ADVK_ERR_ARG; }
+    const dim3 gp(blocks_for(P.g.S, 256), (unsigned)(P.g.N * (P.C >> 2)));
+    ADVK_LAUNCH(K_chain_pk_fwd, st, (lean_pack_kernel<<<gp, 256, 0, st>>>(P.user_src, reinterpret_cast<float4*>(P.src_packed), (int)P.g.S)));
   }
+  for (int k = 0; k < P.n; ++k) {
+    const Stage& s = P.st[k];
+    if (s.kind == ADVK_STAGE_INTENSITY) {
+      LeanInt a;
+      lean_fill_int(P, s, k == P.n - 1, a);
+      ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_kernel<DIM, false><<<grid, 256, 0, st>>>(a)));
+    } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_fwd<DIM, true>(P, s, k, st);
+    else lean_launch_warp_fwd<DIM, false>(P, s, k, st);
+  }
+  return check_launch("chain_apply_fwd (lean)");
+}
+
+static int lean_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+  }
+  return sms;
+}
+
+template <int DIM, bool FIELD>
+static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaStream_t st) {
+  const bool last = (k == P.n - 1);
+  LeanBwd a;
+  a.g = P.g; a.C = P.C; a.tps = P.tps; a.ftps = P.ftps; a.n_tiles = (unsigned)P.n_tiles;
+  a.src = s.src; a.g_dst = s.g_dst; a.g_src = s.g_src; a.phi = s.phi; a.theta = s.theta;
+  a.g_phi = s.g_phi; a.g_theta = s.g_theta;
+  a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
+  // the theta gradient is reduced per block: a block walks several tiles so that the per-sample atomics stay few
+  unsigned grid = (unsigned)P.n_tiles;
+  if (!FIELD && s.g_theta) { const unsigned cap = (unsigned)lean_sms() * 16u; if (grid > cap) grid = cap; }
+  if (!P.pack) {
+    if (s.src_vm) ADVK_LAUNCH(K_chain_img_bwd, st, (lean_warp_bwd_kernel<DIM, FIELD, true><<<grid, 256, 0, st>>>(a)));
+    else ADVK_LAUNCH(K_chain_img_bwd, st, (lean_warp_bwd_kernel<DIM, FIELD, false><<<grid, 256, 0, st>>>(a)));
+  } else {
+    if (k == 0) a.src = P.src_packed;
+    if (!last) ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_warp_bwd_pk_kernel<DIM, FIELD, true><<<grid, 256, 0, st>>>(a)));
+    else ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_warp_bwd_pk_kernel<DIM, FIELD, false><<<grid, 256, 0, st>>>(a)));
+  }
+}
+
+template <int DIM>
+static int lean_bwd(Program& P, cudaStream_t st) {
+  if (P.pack && !P.src_packed) { set_error("chain_apply_bwd: stash is NULL"); return ADVK_ERR_ARG; }
+  const i64 tot = (i64)P.g.N * P.C * P.g.S;
+  for (int k = P.first_bwd; k < P.n; ++k) {
+    const Stage& s = P.st[k];
+    if (s.zero_g_src && s.g_src) cudaMemsetAsync(s.g_src, 0, sizeof(float) * tot, st);
+  }
+  const dim3 grid(blocks_for(P.g.S, 256), P.g.N);
+  for (int k = P.n - 1; k >= P.first_bwd; --k) {
+    const Stage& s = P.st[k];
+    const bool last = (k == P.n - 1);
+    if (s.kind == ADVK_STAGE_INTENSITY) {
+      LeanInt a;
+      lean_fill_int(P, s, last, a);
+      ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_kernel<DIM, true><<<grid, 256, 0, st>>>(a)));
+    } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_bwd<DIM, true>(P, s, k, st);
+    else lean_launch_warp_bwd<DIM, false>(P, s, k, st);
+  }
+  const Stage& f = P.st[P.first_bwd];
+  if (P.pack && f.g_src_user && f.g_src) {
+    const dim3 gu(blocks_for(P.g.S, 256), (unsigned)(P.g.N * (P.C >> 2)));
+    ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_unpack_kernel<<<gu, 256, 0, st>>>(reinterpret_cast<const float4*>(f.g_src), f.g_src_user, (int)P.g.S)));
+  }
+  return check_launch("chain_apply_bwd (lean)");
+}
+
+template <int DIM>
+static int launch_fwd(Program& P, cudaStream_t st) {
+  if (P.lean) return lean_fwd<DIM>(P, st);
+  P.interleave = 1;
+  return launch_fwd_t<DIM, GEN_MINB_FWD>(P, st);
+}
+
+template <int DIM>
+static int launch_bwd(Program& P, cudaStream_t st) {
+  if (P.lean) return lean_bwd<DIM>(P, st);
+  P.interleave = 1;
+  return launch_bwd_t<DIM, GEN_MINB_BWD>(P, st);
 }
 
 }  // namespace advk
 
 using namespace advk;
 
-extern "C" int advk_chain_tune(int min_blocks_per_sm, int interleave) {
-  tune_defaults();
-  // one digit: both directions; two digits "FB": forward F, backward B
-  if (min_blocks_per_sm >= 10) {
-    if (minb_ok(min_blocks_per_sm / 10)) g_minb = min_blocks_per_sm / 10;
-    if (minb_ok(min_blocks_per_sm % 10)) g_minb_bwd = min_blocks_per_sm % 10;
-  } else if (minb_ok(min_blocks_per_sm)) {
-    g_minb = g_minb_bwd = min_blocks_per_sm;
-  }
-  if (interleave == 0 || interleave == 1) g_interleave = interleave;
-  return (g_minb * 10 + g_minb_bwd) * 10 + g_interleave;
+extern "C" int advk_chain_set_lean(int enable) {
+  int prev = lean_enabled() ? 1 : 0;
+  g_lean = enable ? 1 : 0;
+  return prev;
 }
 
 extern "C" int advk_chain_set_packed(int enable) {
@@ -953,8 +1081,11 @@ extern "C" int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* sta
   int warps = 0;
   for (int k = 0; k < d->n_stages; ++k)
     if (d->stages[k].kind != ADVK_STAGE_INTENSITY) ++warps;
+  // + one slot for the packed copy of the chain input (channel-packed prediction path, lean kernels)
+  const bool may_pack = warps == d->n_stages && d->n_stages >= 2 && (d->C % 4) == 0;
   if (stash_floats)
-    *stash_floats = (size_t)((i64)(d->n_stages - 1) * ncs + ((d->want_mask && warps > 1) ? (i64)(warps - 1) * ns : 0));
+    *stash_floats = (size_t)((i64)(d->n_stages - 1) * ncs + ((d->want_mask && warps > 1) ? (i64)(warps - 1) * ns : 0) +
+                             (may_pack ? ncs : 0));
   // one slot per stage boundary, plus one for the packed gradient of the chain input (packed mode)
   if (scratch_floats) *scratch_floats = (size_t)((i64)d->n_stages * ncs);
   return ADVK_OK;
@@ -973,11 +1104,11 @@ extern "C" int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out
                                     const float* stash, float* scratch, float* g_src, void* stream) {
   Program P;
   ADVK_REQUIRE(src && g_out, "null pointer");
-  // data-path pointers are rebuilt exactly as in the forward (dst of the last stage / masks unused)
-  advk_chain_desc dd = *d;
-  dd.want_mask = 0;
-  ADVK_REQUIRE(build_program(&dd, P, src, nullptr, const_cast<float*>(stash), nullptr, nullptr),
+  // data-path pointers are rebuilt exactly as in the forward (same stash layout; the last stage's dst and
+  // the mask outputs are unused)
+  ADVK_REQUIRE(build_program(d, P, src, nullptr, const_cast<float*>(stash), nullptr, nullptr, true),
                "bad chain descriptor");
+  P.want_mask = 0;
   const i64 slot = slot_floats((i64)P.g.N * P.C * P.g.S);
   // gradient plumbing: g_dst of stage k = g_src of stage k+1 (scratch slot k), last = g_out
   int first = P.n;   // earliest stage that produces a requested gradient

@@ -287,12 +287,12 @@ int advk_chain_set_cooperative(int enable);
  * per voxel per 4 channels; 0: planar everywhere.  Returns the previous setting.  Results agree up
  * to fp32 summation order. */
 int advk_chain_set_packed(int enable);
-/* Tuning (A/B timing): resident blocks per SM the chain kernels are compiled for (2, 3, 4 or 6 =
- * register cap 128/80/64/40; one digit sets forward and backward, two digits "FB" set them
- * separately, e.g. 43; other values keep the current ones; defaults 4 / 3) and tile assignment
- * (0 contiguous ranges per block, 1 round-robin; other values keep).
- * Returns 100*fwd + 10*bwd + interleave. */
-int advk_chain_tune(int min_blocks_per_sm, int interleave);
+/* 1 (default; environment ADVK_CHAIN_LEAN): chains whose warp stages all use zeros padding, linear
+ * interpolation and no pad values run the compile-time specialised per-stage kernels
+ * (csrc/advk_chain_lean.cuh); 0: the generic stage executor for everything (A/B timing, tests).  Returns the
+ * previous setting.  Results agree up to fp32 summation order.  The setting must not change between a
+ * forward call and the backward call that consumes its stash. */
+int advk_chain_set_lean(int enable);
 int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* stash_floats, size_t* scratch_floats);
 int advk_chain_apply_fwd(const advk_chain_desc* d, const float* src, const float* mask_src,
                          float* stash, float* out, float* mask_out, void* stream);

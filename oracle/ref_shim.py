@@ -14,6 +14,11 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("ADVCHAIN_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "advchain", "augmentor")):
+    # GPU box: the unmodified package mirrored by __graft_entry__.install_reference() (bench.py's reference arms)
+    _alt = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if os.path.isdir(os.path.join(_alt, "advchain", "augmentor")):
+        REFERENCE_ROOT = _alt
 
 
 def available():

@@ -57,3 +57,16 @@ CASES = {
     "c2d_anatomy": dict(d=2, size=[2, 1, 40, 48], chain=["morph", "affine"], n_iter=1, K=4, seed=41,
                         anatomy=True),
 }
+
+# Full-size cases = BASELINE.json's configurations at their stated sizes (run by make_golden_big.py).  The
+# inputs (volume, noise parameter) are regenerated from seeds and verified by fp64 checksums; outputs are
+# stored as strided samples (stride coprime with every tile size of the kernels) + fp64 checksums of the
+# whole tensor, so that a 128^3 case stays a few hundred KB.
+BIG_CASES = {
+    # BASELINE.json configs[1]: 2-D 8x1x256x256, full chain, 5 PGD steps
+    "c2_full256": dict(d=2, size=[8, 1, 256, 256], chain=FULL, n_iter=5, K=4, seed=61, stride=5, offset=2),
+    # BASELINE.json configs[2]: 3-D 2x1x128x128x64, full chain, 5 PGD steps
+    "c3_full128": dict(d=3, size=[2, 1, 128, 128, 64], chain=FULL, n_iter=5, K=4, seed=62, stride=5, offset=2),
+    # the metric line: 3-D 1x1x128^3, full chain, one PGD iteration
+    "m128_step": dict(d=3, size=[1, 1, 128, 128, 128], chain=FULL, n_iter=1, K=4, seed=63, stride=5, offset=2),
+}

@@ -421,6 +421,10 @@ CHAINS = [
     (3, [2, 1, 12, 20, 24], ["noise", "bias", "morph", "affine"], "zeros", "bilinear"),
     (3, [1, 1, 16, 12, 20], ["morph", "affine"], "border", "bilinear"),
     (3, [1, 2, 10, 14, 18], ["affine", "noise"], 0.5, "bilinear"),
+    (2, [2, 1, 36, 44], ["morph", "affine"], "zeros", "bilinear"),
+    (3, [1, 2, 14, 18, 22], ["affine", "morph", "noise"], "zeros", "bilinear"),
+    (3, [2, 1, 16, 16, 20], ["morph"], "zeros", "bilinear"),
+    (3, [1, 1, 12, 40, 70], ["bias", "affine"], "zeros", "bilinear"),
 ]
 
 
@@ -446,16 +450,20 @@ def _chain_solver(d, size, chain, pad, interp, fused):
 
 
 @pytest.mark.parametrize("d,size,chain,pad,interp", CHAINS)
-@pytest.mark.parametrize("coop", [1, 0])
+@pytest.mark.parametrize("mode", ["lean", "coop", "stage"])
 @pytest.mark.parametrize("k", [3, 4, 8])
-def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, coop, k):
+def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, mode, k):
     """The fused executor (advk_chain_apply_*) against the per-transform kernels on the same
     parameters: image chain + clamp, prediction warp-back, valid-region mask, and every parameter
     gradient -- for arbitrary stage orders, paddings and interpolation modes.  k = 4 and 8 classes
-    take the channel-packed prediction path (float4 intermediates), k = 3 the planar one."""
+    take the channel-packed prediction path (float4 intermediates), k = 3 the planar one.
+    mode: "lean" = the compile-time specialised per-stage kernels where the chain is eligible (zeros padding,
+    linear interpolation; default), "coop" / "stage" = the generic stage executor as one cooperative launch /
+    one launch per stage."""
     from advchain_b200 import _lib
     lib = _lib.load()
-    prev = lib.advk_chain_set_cooperative(coop)
+    prev = lib.advk_chain_set_cooperative(0 if mode == "stage" else 1)
+    prev_lean = lib.advk_chain_set_lean(1 if mode == "lean" else 0)
     try:
         torch.manual_seed(11)
         data = torch.rand(*size).to(_dev())
@@ -475,10 +483,13 @@ def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, c
             pred = sol.predict_backward(conv(adv))
             mask = sol.valid_region_mask(pred)
             (pred * gpred).sum().backward()
-            fused_launches = _lib.launch_count("chain_fwd") + _lib.launch_count("chain_fwd_stage")
+            lean_launches = _lib.launch_count("chain_img_fwd") + _lib.launch_count("chain_pk_fwd")
+            fused_launches = _lib.launch_count("chain_fwd") + _lib.launch_count("chain_fwd_stage") + lean_launches
             res.append((adv.detach(), pred.detach(), mask.detach().clone(),
-                        [t.param.grad.clone() for t in sol.chain_of_transforms], fused_launches))
+                        [t.param.grad.clone() for t in sol.chain_of_transforms], fused_launches, lean_launches))
         assert res[0][4] == 0 and res[1][4] > 0, "fused path did not run"
+        eligible = pad == "zeros" and interp == "bilinear"
+        assert (res[1][5] > 0) == (mode == "lean" and eligible), "lean kernels: ran %d launches" % res[1][5]
         assert rel_err(res[1][0], res[0][0]) < 2e-6
         assert rel_err(res[1][1], res[0][1]) < 2e-6
         assert (res[1][2] != res[0][2]).float().mean().item() < 1e-3
@@ -487,3 +498,4 @@ def test_fused_chain_matches_single_stage_kernels(d, size, chain, pad, interp, c
             assert rel_err(g1, g0) < tol, (t.get_name(), rel_err(g1, g0))
     finally:
         lib.advk_chain_set_cooperative(prev)
+        lib.advk_chain_set_lean(prev_lean)
