@@ -413,7 +413,9 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
     // VM_SRC (C == 1): the stashed source is float2 {value, mask} per voxel
     const float* s = lean_opaque(a.src + (VM_SRC ? 2 * nS : nS * a.C)) + (VM_SRC ? 2 : 1) * G.a000;
     const float* gd = lean_opaque(a.g_dst + nS * a.C);
-    float* gs = scatter ? lean_opaque(a.g_src + nS * a.C) + G.a000 : nullptr;
+    // (no ternary with nullptr here: it would turn the pointer generic and every RED into the three-way
+    // generic-address atomic sequence; a NULL g_src is never dereferenced)
+    float* gs = lean_opaque(a.g_src + nS * a.C) + G.a000;
     float ggx = 0.f, ggy = 0.f, ggz = 0.f;
     for (int c = 0; c < a.C; ++c, s += S, gd += S) {
       float go = ok ? gd[p] : 0.f;

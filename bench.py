@@ -14,9 +14,16 @@ Multi-GPU: one process per GPU (torchrun), every rank owns its own volumes (batc
 data-path collective) -> weak scaling; value = volume-iterations of all ranks /
 max-over-ranks time.
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port":
-the reference is pure Python on PyTorch ATen and `/root/reference` does not exist on the GPU box)
-on the host cores, rank 0 only.
+`--impl reference` times the reference's OWN code (the unmodified package mirrored under baseline/_ref by
+`__graft_entry__.build()`; kind "reference") on the box's host cores at the workload's FULL size -- no voxel
+scaling; as many of the K steps as fit a 150 s budget, at least one, reported as `steps` -- rank 0 only.  If
+baseline/_ref is absent the CPU restatement (oracle/, kind "port") is timed instead.
+`--impl reference-cuda` runs the same unmodified reference with device=cuda on the same B200 (PyTorch
+eager: the incumbent users run today); the b200 line carries that number as `cuda_eager_baseline`.
+
+Workloads: m128 (the metric; weak scaling, one 128^3 volume per GPU), c2 / c3 (BASELINE configs 2 and 3 on one
+GPU), c4 / c5 (BASELINE configs 4 and 5: FIXED global batch 256 / 16 split over the ranks -> strong scaling;
+`--exact-global` adds the three scalar all-reduces that make the shards reproduce the unsharded run).
 """
 import argparse
 import json
@@ -44,7 +51,11 @@ WORKLOADS = {
     "c4shard": (2, [32, 1, 256, 256], ["noise", "bias", "morph", "affine"]),
     "c5shard": (3, [2, 1, 256, 256, 128], ["morph", "affine"]),
     "tiny3d": (3, [1, 1, 32, 32, 32], ["noise", "bias", "morph", "affine"]),
+    # strong scaling: the size is the GLOBAL batch, split over the ranks (BASELINE.json configs 4 and 5)
+    "c4": (2, [256, 1, 256, 256], ["noise", "bias", "morph", "affine"]),
+    "c5": (3, [16, 1, 256, 256, 128], ["morph", "affine"]),
 }
+STRONG = ("c4", "c5")
 K_CLASSES = 4
 
 # Algorithmic 4-byte words per voxel moved by ONE launch of a kernel (SURVEY.md section 8d / DESIGN.md
@@ -64,7 +75,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--exact-global", action="store_true",
+                    help="multi-GPU: ShardContext (scalar all-reduces) so that the shards reproduce the unsharded run")
+    ap.add_argument("--no-cuda-baseline", action="store_true", help="skip the reference-on-CUDA (PyTorch eager) leg")
     ap.add_argument("--workload", default="m128", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the PGD loop eagerly (no CUDA graph)")
@@ -177,7 +191,7 @@ def ncu_traffic_bytes(kernel):
     try:
         with open(p) as f:
             t = json.load(f)
-        e = t.get(kernel)
+        e = t.get("by_bench_id", t).get(kernel)
         return None if e is None else float(e["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -223,13 +237,6 @@ def cpu_port_step_time(d, size, chain, steps=1, warmup=0, threads=None):
     return times
 
 
-def sample_size(d, size, div=2):
-    """The bounded CPU sample: the same workload with every spatial axis divided by `div` (1/div^d of
-    the voxels); throughput is scaled by the voxel ratio."""
-    sp = [max(16, s // div) for s in size[2:]]
-    return [size[0], size[1]] + sp
-
-
 def _nvox(size):
     n = size[0]
     for s in size[2:]:
@@ -237,44 +244,104 @@ def _nvox(size):
     return n
 
 
-REF_BUDGET_S = 180.0     # wall-clock bound of the reference arm's timed region
+REF_BUDGET_S = 150.0     # wall-clock bound of the reference arm's timed region
+
+
+def load_reference():
+    """The UNMODIFIED reference package (baseline/_ref, mirrored by __graft_entry__.install_reference(); in the
+    build container /root/reference itself), or None.  Test/bench infrastructure only: the product path never
+    imports it."""
+    try:
+        from oracle import ref_shim
+        if ref_shim.available():
+            return ref_shim.load()
+    except Exception as exc:                                  # pragma: no cover
+        sys.stderr.write("bench.py: reference not loadable (%s)\n" % (exc,))
+    return None
+
+
+def reference_stepper(aug, d, size, chain, device):
+    """One PGD inner-loop iteration of the reference's own solver (adv_compose_solver.py:289-405) on
+    synthetic data of the workload's shape; returns step()."""
+    cfgs = make_cfgs(d, size)
+    use_gpu = device.type == "cuda"
+    ts = []
+    for n in chain:
+        cls = {"noise": aug.AdvNoise, "bias": aug.AdvBias, "morph": aug.AdvMorph, "affine": aug.AdvAffine}[n]
+        ts.append(cls(spatial_dims=d, config_dict=cfgs[n], use_gpu=use_gpu, device=device))
+    sol = aug.ComposeAdversarialTransformSolver(
+        chain_of_transforms=ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+        use_gpu=use_gpu, if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+    torch.manual_seed(0)
+    data = torch.rand(*size).to(device)
+    conv = torch.nn.Conv2d if d == 2 else torch.nn.Conv3d
+    model = conv(size[1], K_CLASSES, 3, 1, 1).eval().to(device)
+    init_out = sol.get_init_output(model=model, data=data)
+    sol.init_random_transformation()
+    flags, steps = [True] * len(chain), [1.0] * len(chain)
+
+    def step():
+        sol.optimizing_transform(model=model, data=data, init_output=init_out, optimize_flags=flags,
+                                 n_iter=1, step_sizes=steps)
+    return step
+
+
+def small_size(d, size):
+    return [min(size[0], 2), size[1]] + [32] * d
+
+
+def time_cpu_arm(d, size, chain, steps, budget_s, prefer_reference=True):
+    """Times up to `steps` PGD iterations at FULL size on the host cores within `budget_s` (at least one).
+    -> (seconds per timed step list, kind, cores)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    aug = load_reference() if prefer_reference else None
+    cpu = torch.device("cpu")
+    if aug is not None:
+        kind = "reference"
+        warm = reference_stepper(aug, d, small_size(d, size), chain, cpu)
+        step = reference_stepper(aug, d, size, chain, cpu)
+    else:
+        kind = "port"
+        warm = lambda: cpu_port_step_time(d, small_size(d, size), chain, steps=1)     # noqa: E731
+        step = None
+    warm()                               # thread pools, lazy imports, oneDNN primitives: on a small volume
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max(1, steps):
+        t0 = time.perf_counter()
+        if step is not None:
+            step()
+        else:
+            cpu_port_step_time(d, size, chain, steps=1)
+        times.append(time.perf_counter() - t0)
+        spent = time.perf_counter() - t_start
+        if spent + max(times) > budget_s:
+            break
+    return times, kind, cores
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path, restated in oracle/ (kind "port"), on all host
-    cores.  Each step is one PGD inner-loop iteration on a BOUNDED sample of the workload: the same
-    chain on a sub-volume with every spatial axis divided by 2, 4, ... -- the largest one for which the
-    K timed steps are projected (from the warm-up) to finish within REF_BUDGET_S -- and the measured
-    iterations/s are scaled by the voxel ratio (CPU cost is linear in the voxel count at these sizes)."""
+    """`--impl reference`: the reference's own CPU implementation of the path at the workload's full size."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     d, size, chain = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    div = 2
-    ssz = sample_size(d, size, div)
-    warm = cpu_port_step_time(d, ssz, chain, steps=max(1, args.warmup), warmup=0, threads=cores)
-    per_step = min(warm)
-    while per_step * args.steps > REF_BUDGET_S and min(ssz[2:]) > 16:
-        div *= 2
-        nxt = sample_size(d, size, div)
-        if nxt == ssz:
-            break
-        per_step *= float(_nvox(nxt)) / float(_nvox(ssz))
-        ssz = nxt
-    ratio = float(_nvox(ssz)) / float(_nvox(size))
-    times = cpu_port_step_time(d, ssz, chain, steps=args.steps, warmup=(0 if div == 2 else max(1, args.warmup)),
-                               threads=cores)
+    times, kind, cores = time_cpu_arm(d, size, chain, args.steps, REF_BUDGET_S)
+    n = len(times)
     total = sum(times)
-    value = args.steps / total * ratio
-    sample = ("each step = 1 PGD inner-loop iteration of the CPU port on %s (%.4g of the voxels of %s); "
-              "iters/s scaled by that voxel ratio" % ("x".join(map(str, ssz)), ratio, "x".join(map(str, size))))
+    value = n / total
+    sample = ("%d PGD inner-loop iteration(s) of the %s on %s at FULL size (no voxel scaling), %d host threads; "
+              "%d of the %d requested steps fit the %.0f s budget; warm-up = 1 iteration on a %s volume"
+              % (n, "unmodified reference (baseline/_ref, CPU)" if kind == "reference" else "CPU port (oracle/)",
+                 "x".join(map(str, size)), cores, n, args.steps, REF_BUDGET_S, "x".join(map(str, small_size(d, size)))))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps / ratio,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "steps": n, "steps_requested": args.steps, "warmup": 1, "ms_per_step": 1e3 * total / n,
+        "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, d, size, chain),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -282,14 +349,67 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, d, size, chain):
-    return {"workload": "%s: %dD %s per GPU, chain %s, 1 PGD step per iteration, toy model Conv%dd(1,%d,3,1,1), "
-                        "loss mse+contour" % (args.workload, d, "x".join(map(str, size)), "->".join(chain), d,
-                                              K_CLASSES),
-            "per_gpu_size": size, "chain": chain, "n_gpus": args.gpus,
-            "l2": "per-step working set (field levels 2 signs x 9 x 32 MB at 128^3) exceeds the 126 MB L2; no flush",
-            "model_precision": "the toy model runs under PyTorch defaults (cuDNN may pick TF32 convolution "
-                               "kernels); every advk kernel computes in fp32"}
+def time_reference_cuda(d, size, chain, dev, steps=5, warmup=2):
+    """The unmodified reference with device=cuda (PyTorch eager on the same GPU). -> ms per iteration or None."""
+    aug = load_reference()
+    if aug is None:
+        return None
+    step = reference_stepper(aug, d, size, chain, dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_reference_cuda(args):
+    """`--impl reference-cuda`: the incumbent -- the reference's PyTorch-eager path on the same B200."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    d, size, chain = WORKLOADS[args.workload]
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "no CUDA device"}))
+        return 0
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    steps = max(1, min(args.steps, 20))
+    ms = time_reference_cuda(d, size, chain, dev, steps=steps, warmup=max(1, min(args.warmup, 3)))
+    if ms is None:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "baseline/_ref (mirror of the reference package) "
+                          "is not present; run __graft_entry__.build() where /root/reference exists"}))
+        return 0
+    print(json.dumps({
+        "impl": "reference-cuda", "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, d, size, chain),
+        "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager"}))
+    return 0
+
+
+def workload_config(args, d, size, chain, per_gpu=None):
+    strong = args.workload in STRONG
+    per_gpu = per_gpu or size
+    cfg = {"workload": "%s: %dD %s %s, chain %s, 1 PGD step per iteration, toy model Conv%dd(1,%d,3,1,1), "
+                       "loss mse+contour" % (args.workload, d, "x".join(map(str, size)),
+                                             "GLOBAL batch split over the GPUs" if strong else "per GPU",
+                                             "->".join(chain), d, K_CLASSES),
+           "per_gpu_size": per_gpu, "chain": chain, "n_gpus": args.gpus,
+           "l2": "no flush between iterations: the per-step working set (field levels alone: 2 signs x 10 fields x %d "
+                 "B/voxel = %.0f MB per GPU) %s the 126 MB L2"
+                 % (16 if d == 3 else 8, 2 * 10 * (16 if d == 3 else 8) * _nvox(per_gpu) / 1e6,
+                    "exceeds" if 2 * 10 * (16 if d == 3 else 8) * _nvox(per_gpu) / 1e6 > 126 else "FITS IN (not a valid timing size)"),
+           "model_precision": "the toy model runs under PyTorch defaults (cuDNN may pick TF32 convolution "
+                              "kernels); every advk kernel computes in fp32"}
+    if strong:
+        cfg["global_batch"] = size[0]
+        cfg["exact_global"] = bool(getattr(args, "exact_global", False))
+    return cfg
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -321,7 +441,16 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    d, size, chain = WORKLOADS[args.workload]
+    d, gsize, chain = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    size = list(gsize)
+    ctx = None
+    if strong:
+        from advchain_b200.augmentor.sharding import ShardContext, shard_slice
+        sl = shard_slice(gsize[0], rank, world)
+        size[0] = sl.stop - sl.start
+        if args.exact_global and world > 1:
+            ctx = ShardContext(gsize[0])
     sampler = ClockSampler(local) if rank == 0 else None     # runs beside everything; filtered to the timed window
     torch.manual_seed(1234 + rank)
     host_data = torch.rand(*size).pin_memory()
@@ -331,6 +460,7 @@ def run_b200(args):
     for p in model.parameters():
         p.requires_grad_(True)
     sol = build_solver(d, size, chain, dev)
+    sol.shard = ctx
     data = host_data.to(dev)
     init_out = sol.get_init_output(model, data)
     sol.init_random_transformation()
@@ -396,25 +526,38 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, resident):
+    REGIONS = 5
+
+    def timed(n, resident, regions=1):
+        """Times exactly n steps (barrier + synchronize on both sides, CUDA events, max over ranks).  With
+        regions > 1 the n steps are cut into that many back-to-back sub-regions by extra events on the stream
+        (no synchronisation in between). -> (total ms, [ms per step of every sub-region])"""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        regions = max(1, min(regions, n))
+        cuts = [round(i * n / regions) for i in range(regions + 1)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(regions + 1)]
+        evs[0].record()
         if not resident:
             e2e_begin()
-        for _ in range(n):
+        r = 1
+        for i in range(n):
             step(resident)
+            if i + 1 == cuts[r] and r < regions:
+                evs[r].record()
+                r += 1
         if not resident:
             e2e_end()
-        e1.record()
+        evs[regions].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = evs[0].elapsed_time(evs[regions])
+        per = [evs[i].elapsed_time(evs[i + 1]) / max(1, cuts[i + 1] - cuts[i]) for i in range(regions)]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms] + per, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            vals = t.tolist()
+            ms, per = float(vals[0]), [float(v) for v in vals[1:]]
         barrier()
-        return ms
+        return ms, per
 
     # ---- eager warm-up; two steps run with every kernel bracketed by CUDA events -> per-kernel
     # breakdown and the dominant kernel
@@ -438,7 +581,7 @@ def run_b200(args):
     _lib.launch_count(reset=True)
     if dom is not None:
         _lib.prof_configure(dom, 16384)
-    ms_eager = timed(eager_steps, True)
+    ms_eager, _ = timed(eager_steps, True)
     eager_launches = _lib.launch_count(reset=True) * args.steps // eager_steps
     dom_ms = _lib.prof_collect(16384).get(dom, []) if dom is not None else []
     _lib.prof_configure(None)
@@ -452,7 +595,7 @@ def run_b200(args):
     if sampler:
         sampler.wait_ready()                  # started before the warm-up; make sure it is producing
     w0 = time.time()
-    ms = timed(args.steps, True)
+    ms, region_ms = timed(args.steps, True, REGIONS)
     w1 = time.time()
     clocks = sampler.stop((w0, w1)) if sampler else None
     graph_used = use_graph and getattr(sol, "graph_replays", 0) == args.steps
@@ -460,17 +603,14 @@ def run_b200(args):
 
     # ---- timed region 2: end to end through the public API with host buffers
     timed(2, False)
-    ms_e2e = timed(args.steps, False)
+    ms_e2e, region_ms_e2e = timed(args.steps, False, REGIONS)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    nvox = 1
-    for s in size[2:]:
-        nvox *= s
-    nvox *= size[0]
+    nvox = _nvox(size)
     peak, peak_src = measured_peak_gbs()
     roof = None
     if dom_ms:
@@ -486,47 +626,92 @@ def run_b200(args):
                 "kernel_share_of_step": sum(dom_ms) / ms_eager if ms_eager > 0 else None,
                 "measured_in": "eager timed region of %d steps (CUDA events on the launching "
                                "stream; graph nodes cannot be bracketed)" % eager_steps}
-    # whole-step algorithmic bytes: full chain 102d+10C+5K+1 words / voxel
-    C = size[1]
-    if chain == ["noise", "bias", "morph", "affine"]:
-        words = 102 * d + 10 * C + 5 * K_CLASSES + 1
-    elif chain == ["morph", "affine"]:
-        words = 102 * d + 4 * C + 5 * K_CLASSES + 1
-    else:
-        words = None
-    value = world * args.steps / (ms * 1e-3)
+    # Roofline of the scopes SURVEY.md section 8d names: algorithmic words per voxel of the scope x 4 B x voxels
+    # per GPU / the time our kernels of that scope take per step (event breakdown of the eager steps above).
+    C, K = size[1], K_CLASSES
+    has_int = "noise" in chain or "bias" in chain
+    wA = (3 * C + d) if chain == ["noise", "bias", "morph", "affine"] else (2 * C + d)
+    wD = (4 * C + 2 * d) if has_int else (2 * C + 2 * d)
+    wB, wC_, wU = 2 * K + 3 * d + 1, 3 * K + 2 * d, (3 * C if "noise" in chain else 0)
+    w_field = 94 * d
+    words = wA + wB + wC_ + wD + wU + w_field        # full chain: 102d + 10C + 5K + 1
+    FIELD_KERNELS = ("ss_step", "ss_step_bwd", "smooth_fwd", "smooth_bwd", "init_phi0", "lowres_smooth",
+                     "adjoint_axis", "aos_to_planar", "unorm2", "steps_check")
+    APPLY_KERNELS = ("chain_img_fwd", "chain_img_bwd", "chain_pk_fwd", "chain_pk_bwd", "chain_fwd", "chain_bwd",
+                     "chain_fwd_stage", "chain_bwd_stage", "update", "sumsq", "lowfield_fwd", "lowfield_bwd",
+                     "adjoint_axis_f", "affine_theta_fwd", "affine_theta_bwd")
+
+    def scope(names, w):
+        t = sum(tot.get(k, 0.0) for k in names)
+        if t <= 0:
+            return None
+        gbs = w * 4.0 * nvox / (t * 1e-3) / 1e9
+        return {"ms_per_step": round(t, 4), "algo_bytes_per_step": w * 4.0 * nvox, "achieved": gbs, "frac": gbs / peak,
+                "kernels": [k for k in names if k in tot]}
+
+    scopes = {
+        "chain_apply_fwd_bwd_A+D": scope(("chain_img_fwd", "chain_img_bwd"), wA + wD),
+        "apply_total_A+B+C+D+U": scope(APPLY_KERNELS, wA + wB + wC_ + wD + wU),
+        "field_build_fwd_bwd": scope(FIELD_KERNELS, w_field),
+        "whole_step_advk_kernels": {"ms_per_step": round(sum(tot.values()), 4), "algo_bytes_per_step": words * 4.0 * nvox,
+                                    "achieved": words * 4.0 * nvox / (sum(tot.values()) * 1e-3) / 1e9,
+                                    "frac": words * 4.0 * nvox / (sum(tot.values()) * 1e-3) / 1e9 / peak},
+        "whole_step_incl_model_and_loss": {"ms_per_step": ms / args.steps, "algo_bytes_per_step": words * 4.0 * nvox,
+                                           "achieved": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9,
+                                           "frac": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "unit": "GB/s", "peak": peak,
+        "note": "per-scope time = CUDA-event time of our kernels of that scope in eager steps (graph nodes cannot be "
+                "bracketed); the last scope uses the CUDA-graph step time of `value`",
+    }
+    iters = (1 if strong else world) * args.steps          # strong scaling: one iteration covers the global batch
+    value = iters / (ms * 1e-3)
+    med = statistics.median(region_ms)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, d, size, chain),
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": host_data.numel() * 4, "d2h_bytes_per_step": 4},
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, d, gsize, chain, per_gpu=size),
+        "e2e": {"value": iters / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": host_data.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step_regions": [round(v, 4) for v in region_ms_e2e]},
         "gpu_launches": launches,
         "cuda_graph": bool(graph_used),
+        "ms_per_step_regions": [round(v, 4) for v in region_ms],
+        "ms_per_step_median_region": med,
+        "value_median_region": (1 if strong else world) / (med * 1e-3),
         "ms_per_step_eager": ms_eager / eager_steps,
         "clocks": clocks,
         "roofline": roof,
+        "roofline_scopes": scopes,
         "kernel_ms_per_step": {k: round(v, 4) for k, v in ranked},
         "advk_ms_per_step": round(sum(tot.values()), 4),
     }
-    if words is not None:
-        line["step_roofline"] = {
-            "algo_bytes_per_step": words * 4.0 * nvox, "unit": "GB/s",
-            "achieved_whole_step": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9,
-            "achieved_advk_kernels_only": words * 4.0 * nvox / (sum(tot.values()) * 1e-3) / 1e9,
-            "peak": peak}
+    line["step_roofline"] = {
+        "algo_bytes_per_step": words * 4.0 * nvox, "unit": "GB/s",
+        "achieved_whole_step": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9,
+        "achieved_advk_kernels_only": words * 4.0 * nvox / (sum(tot.values()) * 1e-3) / 1e9,
+        "peak": peak}
+    if not args.no_cuda_baseline and world == 1:
+        # the incumbent: the unmodified reference, device=cuda, PyTorch eager, same GPU, same run
+        try:
+            ms_ref = time_reference_cuda(d, size, chain, dev, steps=5, warmup=2)
+        except Exception as exc:                              # pragma: no cover
+            ms_ref = None
+            sys.stderr.write("bench.py: reference-on-CUDA leg failed: %s\n" % (exc,))
+        line["cuda_eager_baseline"] = None if ms_ref is None else {
+            "value": 1e3 / ms_ref, "unit": UNIT, "ms_per_step": ms_ref, "steps": 5, "warmup": 2,
+            "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager, same GPU",
+            "speedup_resident": value * ms_ref / 1e3}
+    else:
+        line["cuda_eager_baseline"] = None
     if not args.no_cpu_baseline and world == 1:
-        ssz = sample_size(d, size)
-        ratio = 1.0
-        for a, b in zip(ssz[2:], size[2:]):
-            ratio *= float(a) / float(b)
-        cores = os.cpu_count() or 1
-        ts = cpu_port_step_time(d, ssz, chain, steps=2, warmup=1, threads=cores)
+        # bounded CPU sample at FULL size: one iteration of the CPU port (the real reference needs ~4x longer:
+        # it builds every deformation field twice); `--impl reference` times the reference itself
+        times, kind, cores = time_cpu_arm(d, size, chain, 1, 30.0, prefer_reference=False)
         line["cpu_baseline"] = {
-            "value": len(ts) / sum(ts) * ratio, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "2 PGD inner-loop iterations of the CPU port (oracle/) on %s (%.4g of the voxels), "
-                      "iters/s scaled by the voxel ratio" % ("x".join(map(str, ssz)), ratio)}
+            "value": len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d PGD inner-loop iteration(s) of the CPU port (oracle/) on %s at FULL size (no scaling), "
+                      "%d host threads" % (len(times), "x".join(map(str, size)), cores)}
     else:
         line["cpu_baseline"] = None
     if args.profile_out:
@@ -542,6 +727,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda(args)
     return run_b200(args)
 
 
