@@ -165,6 +165,8 @@ class AdvMorph(AdvTransformBase):
         if self._fixed_steps is not None:
             # no host round trip: run with the captured count, let the device count rule violations
             n, viol = self._fixed_steps
+            if self.shard is not None:
+                self.shard.all_reduce_sum_(n2)          # quirk Q2: whole-batch norm, no host round trip
             _ops.call("advk_morph_steps_check", _ops.ptr(n2), int(n), int(self.num_steps), viol.data_ptr(),
                       _ops.stream())
             self._steps_cache = (weakref.ref(self.param), self.param._version, self._scale(), n)
@@ -196,6 +198,8 @@ class AdvMorph(AdvTransformBase):
             nb = self._nb_steps()
         field = _ops.MorphField.apply(p, self.data_size, self._morph_cfg(), sign * self._scale(), nb, norm_out)
         if norm_out is not None:
+            if self.shard is not None:
+                self.shard.all_reduce_sum_(norm_out)
             _ops.call("advk_morph_steps_check", _ops.ptr(norm_out), int(nb), int(self.num_steps), viol.data_ptr(),
                       _ops.stream())
             self._steps_cache = (weakref.ref(p), p._version, self._scale(), nb)

@@ -67,6 +67,12 @@ class ShardContext(object):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         return buf[0]
 
+    def all_reduce_sum_(self, buf):
+        """In-place SUM of a device tensor over the shards with no host round trip: the form the CUDA-graph
+        loop captures (an NCCL all-reduce is a capturable stream operation)."""
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        return buf
+
     # -- 3. 3-D step count ------------------------------------------------------------------
     def global_norm2(self, local_norm2):
         buf = local_norm2.detach().reshape(1).to(torch.float32).clone()

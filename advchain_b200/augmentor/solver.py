@@ -343,81 +343,86 @@ class ComposeAdversarialTransformSolver(object):
             if hasattr(t, "shard"):
                 t.shard = self.shard
         use_anatomy = anatomy_mask_images is not None and abs(anatomy_reg_weight) > 1e-32
-        if (self.use_cuda_graph and not use_anatomy and not self.debug and n_iter > 0 and data.is_cuda
-                and self._optimize_with_graph(model, data, init_output, optimize_flags, n_iter, step_sizes)):
-            return self._finish_loop(optimize_flags)
-        stop_flag = False if n_iter > 0 else True
+        graph_ok = self.use_cuda_graph and not self.debug and n_iter > 0 and data.is_cuda
+        anatomy = (anatomy_mask_images, anatomy_reg_weight) if use_anatomy else None
+        if use_anatomy and self.if_contains_geo_transform(self.chain_of_transforms):
+            assert anatomy_mask_images.size() == data.size(), "gt mask should be of the same size as input image "
         i_iter = 0
         one_time_iter = n_iter
         transforms = list(self.chain_of_transforms)
         data = data.detach()
+        stop_flag = False if n_iter > 0 else True
         while stop_flag is False:
-            model.zero_grad()
-            i_iter += 1
-            self.make_learnable_transformation(optimize_flags=optimize_flags,
-                                               chain_of_transforms=self.chain_of_transforms)
-            augmented_data = self.forward(data)
-            with _disable_tracking_bn_stats(model):
-                perturbed_output = self.get_net_output(model, augmented_data)
-            if self.if_contains_geo_transform(self.chain_of_transforms):
-                warped_back_prediction = self.predict_backward(perturbed_output)
-                mask = self.valid_region_mask(init_output)
-                dist = self.loss_fn(pred=warped_back_prediction, reference=init_output, mask=mask)
-                if use_anatomy:
-                    assert anatomy_mask_images.size() == data.size(), \
-                        "gt mask should be of the same size as input image "
-                    dist = dist + anatomy_reg_weight * self.compute_anatomy_misoverlapping_loss(
-                        anatomy_mask_images=anatomy_mask_images)
-            else:
-                dist = self.loss_fn(pred=perturbed_output, reference=init_output.detach())
-            if self.debug:
-                print('[inner loop], step {}: dist {}'.format(str(i_iter), dist.item()))
-            self.last_dist = dist.detach()
-            if self.shard is not None:   # the guard looks at the whole-batch loss, like the reference
-                self.last_dist = self.shard.global_scalar(dist)
-            if bool(torch.isfinite(self.last_dist)):            # the step's single host sync (NaN/Inf guard, :345)
-                self._backward_to_params(dist)
-                for flag, transform in zip(optimize_flags, self.chain_of_transforms):
-                    if flag:
-                        # quirk Q15 (adv_compose_solver.py:349-357): the reference indexes step_sizes with
-                        # a counter it never increments, so every transform is updated with step_sizes[0]
-                        try:
-                            step_size = step_sizes[0]
-                        except Exception:
-                            step_size = transform.get_step_size()
-                            logging.warning(f'use default step size:{step_size}')
-                        transform.optimize_parameters(step_size=step_size)
-            model.zero_grad()
-
-            if i_iter == n_iter:
-                transforms = []
-                for flag, transform in zip(optimize_flags, self.chain_of_transforms):
-                    if flag:
-                        transform.rescale_parameters()
-                        transform.eval()
-                    transforms.append(transform)
-                if self.if_contains_geo_transform(transforms) and use_anatomy:
-                    if abs(self.compute_anatomy_misoverlapping_loss(anatomy_mask_images)) <= volume_preserve_tolerance:
+            # iterations i_iter+1 .. n_iter (adv_compose_solver.py:308-368), as replays of a captured CUDA graph
+            # when enabled and capturable, else eagerly
+            k = n_iter - i_iter
+            if not (graph_ok and self._optimize_with_graph(model, data, init_output, optimize_flags, k, step_sizes,
+                                                           anatomy=anatomy)):
+                for _ in range(k):
+                    i_iter += 1
+                    self._eager_iteration(model, data, init_output, optimize_flags, step_sizes, anatomy, i_iter)
+            i_iter = n_iter
+            # last-iteration bookkeeping (:369-375) and the anatomy-preserving retry state machine (:376-400)
+            transforms = self._finish_loop(optimize_flags)
+            if self.if_contains_geo_transform(transforms) and use_anatomy:
+                if abs(self.compute_anatomy_misoverlapping_loss(anatomy_mask_images)) <= volume_preserve_tolerance:
+                    stop_flag = True
+                else:
+                    if i_iter >= 3 * one_time_iter:
                         stop_flag = True
+                        self.init_random_transformation(anatomy_mask_images=anatomy_mask_images,
+                                                        volume_preserve_tolerance=volume_preserve_tolerance)
                     else:
-                        if i_iter >= 3 * one_time_iter:
-                            stop_flag = True
+                        if i_iter == 2 * one_time_iter:
                             self.init_random_transformation(anatomy_mask_images=anatomy_mask_images,
                                                             volume_preserve_tolerance=volume_preserve_tolerance)
+                            n_iter += one_time_iter
                         else:
-                            if i_iter == 2 * one_time_iter:
-                                self.init_random_transformation(anatomy_mask_images=anatomy_mask_images,
-                                                                volume_preserve_tolerance=volume_preserve_tolerance)
-                                n_iter += one_time_iter
-                            else:
-                                n_iter += 1
-                        for flag, transform in zip(optimize_flags, self.chain_of_transforms):
-                            if flag:
-                                transform.train()
-                        transforms.append(transform)
-                else:
-                    stop_flag = True
+                            n_iter += 1
+                    transform = None
+                    for flag, transform in zip(optimize_flags, self.chain_of_transforms):
+                        if flag:
+                            transform.train()
+                    if transform is not None:
+                        transforms.append(transform)     # the reference appends the loop variable (:399)
+            else:
+                stop_flag = True
         return transforms
+
+    def _eager_iteration(self, model, data, init_output, optimize_flags, step_sizes, anatomy, i_iter):
+        """One pass of adv_compose_solver.py:308-368 with one host synchronisation (the NaN/Inf guard)."""
+        model.zero_grad()
+        self.make_learnable_transformation(optimize_flags=optimize_flags,
+                                           chain_of_transforms=self.chain_of_transforms)
+        augmented_data = self.forward(data)
+        with _disable_tracking_bn_stats(model):
+            perturbed_output = self.get_net_output(model, augmented_data)
+        if self.if_contains_geo_transform(self.chain_of_transforms):
+            warped_back_prediction = self.predict_backward(perturbed_output)
+            mask = self.valid_region_mask(init_output)
+            dist = self.loss_fn(pred=warped_back_prediction, reference=init_output, mask=mask)
+            if anatomy is not None:
+                dist = dist + anatomy[1] * self.compute_anatomy_misoverlapping_loss(anatomy_mask_images=anatomy[0])
+        else:
+            dist = self.loss_fn(pred=perturbed_output, reference=init_output.detach())
+        if self.debug:
+            print('[inner loop], step {}: dist {}'.format(str(i_iter), dist.item()))
+        self.last_dist = dist.detach()
+        if self.shard is not None:   # the guard looks at the whole-batch loss, like the reference
+            self.last_dist = self.shard.global_scalar(dist)
+        if bool(torch.isfinite(self.last_dist)):            # the step's single host sync (NaN/Inf guard, :345)
+            self._backward_to_params(dist)
+            for flag, transform in zip(optimize_flags, self.chain_of_transforms):
+                if flag:
+                    # quirk Q15 (adv_compose_solver.py:349-357): the reference indexes step_sizes with
+                    # a counter it never increments, so every transform is updated with step_sizes[0]
+                    try:
+                        step_size = step_sizes[0]
+                    except Exception:
+                        step_size = transform.get_step_size()
+                        logging.warning(f'use default step size:{step_size}')
+                    transform.optimize_parameters(step_size=step_size)
+        model.zero_grad()
 
     # ------------------------------------------------------------------ CUDA-graph PGD loop
     def _finish_loop(self, optimize_flags):
@@ -464,9 +469,14 @@ class ComposeAdversarialTransformSolver(object):
             warped = self.predict_backward(out)
             mask = self.valid_region_mask(st["init_output"])
             dist = self.loss_fn(pred=warped, reference=st["init_output"], mask=mask)
+            if st.get("anatomy") is not None:
+                # the thresholded round-trip score (:281-287, :329-338) has no gradient: it only shifts `dist`
+                dist = dist + st["anatomy_weight"] * self.compute_anatomy_misoverlapping_loss(st["anatomy"])
         else:
             dist = self.loss_fn(pred=out, reference=st["init_output"].detach())
         st["dist"].copy_(dist.detach().reshape(1))
+        if self.shard is not None:
+            self.shard.all_reduce_sum_(st["dist"])      # the guard looks at the whole-batch loss (captured NCCL op)
         self._backward_to_params(dist)
         for flag, t, buf in zip(st["flags"], chain, st["params"]):
             if flag:
@@ -482,6 +492,8 @@ class ComposeAdversarialTransformSolver(object):
             for j, t in enumerate(t_ for t_ in chain if isinstance(t_, AdvMorph) and t_.spatial_dims == 3):
                 buf = st["params"][chain.index(t)]
                 n2 = _ops.morph_unorm2(buf, t.data_size, t._morph_cfg(), t._scale())
+                if self.shard is not None:
+                    self.shard.all_reduce_sum_(n2)      # quirk Q2: the norm of the WHOLE batch decides the count
                 st["norm2"][j:j + 1].copy_(n2.reshape(1))
         model.zero_grad()
 
@@ -533,7 +545,8 @@ class ComposeAdversarialTransformSolver(object):
             graph = torch.cuda.CUDAGraph()
             from .. import _lib
             before = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            # (thread-local capture mode: the NCCL watchdog thread of an exact-global run may touch the runtime)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.shard is not None else "global"):
                 self._graph_iteration(model, st)
             entry = (graph, _lib.launch_count() - before)
             st["graphs"][(nsteps, want_norm)] = entry
@@ -550,7 +563,7 @@ class ComposeAdversarialTransformSolver(object):
                 t._steps_cache = None
         return entry
 
-    def _optimize_with_graph(self, model, data, init_output, optimize_flags, n_iter, step_sizes):
+    def _optimize_with_graph(self, model, data, init_output, optimize_flags, n_iter, step_sizes, anatomy=None):
         """Runs the n_iter PGD iterations as replays of captured CUDA graphs.  Returns False when the loop
         has to run eagerly (capture unsupported for this model, 3-D step count of the first iteration
         different from the one assumed).
@@ -562,8 +575,8 @@ class ComposeAdversarialTransformSolver(object):
         replays the graph captured for exactly that count, so a count that grows during a 5- or 10-step
         loop costs a capture the first time, not a redo."""
         chain = self.chain_of_transforms
-        if self.shard is not None:
-            return False                 # the scalar all-reduces of exact-global mode run eagerly
+        if anatomy is not None and not self.if_contains_geo_transform(chain):
+            anatomy = None               # the score is only evaluated for chains with a geometric transform
         for t in chain:
             if t.param is None:
                 t.init_parameters()
@@ -588,7 +601,9 @@ class ComposeAdversarialTransformSolver(object):
                tuple(tuple(t.param.shape) for t in chain), rng, self.use_fused_chain,
                tuple(self.divergence_types), tuple(self.divergence_weights), bool(self.is_gt),
                None if self.class_weights is None else tuple(self.class_weights),
-               tuple(self._config_fingerprint(t) for t in chain))
+               tuple(self._config_fingerprint(t) for t in chain),
+               None if anatomy is None else (tuple(anatomy[0].shape), float(anatomy[1])),
+               None if self.shard is None else (id(self.shard), self.shard.global_batch, self.shard.world_size))
         st = self._graphs.get(key)
         if isinstance(st, dict):
             objs = [r() for r in st["refs"]]
@@ -613,6 +628,8 @@ class ComposeAdversarialTransformSolver(object):
                       refs=[weakref.ref(model)] + [weakref.ref(t) for t in chain],
                       data=data.detach().clone(), init_output=init_output.detach().clone(),
                       params=[p.clone() for p in start],
+                      anatomy=None if anatomy is None else anatomy[0].detach().clone(),
+                      anatomy_weight=None if anatomy is None else float(anatomy[1]),
                       dist=torch.zeros(1, dtype=torch.float32, device=data.device),
                       viol=torch.zeros(1, dtype=torch.int32, device=data.device),
                       norm2=torch.zeros(max(len(morph3d), 1), dtype=torch.float32, device=data.device))
@@ -623,6 +640,8 @@ class ComposeAdversarialTransformSolver(object):
         # always refreshed: (data_ptr, _version, shape) does not identify a tensor -- a training loop makes a
         # new clean prediction every step, typically at the freed address of the previous one, version 0
         st["init_output"].copy_(init_output.detach())
+        if anatomy is not None:
+            st["anatomy"].copy_(anatomy[0].detach())
         for buf, p in zip(st["params"], start):
             buf.copy_(p)
         st["viol"].zero_()

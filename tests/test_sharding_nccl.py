@@ -29,7 +29,7 @@ def _build(d, size, dev):
                                              if_norm_image=True)
 
 
-def _worker(rank, world, port, d, gsize, q):
+def _worker(rank, world, port, d, gsize, q, graph=False, n_iter=1):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -52,21 +52,24 @@ def _worker(rank, world, port, d, gsize, q):
         lsize = [sl.stop - sl.start] + list(gsize[1:])
         sol = _build(d, lsize, dev)
         sol.shard = ctx
+        sol.use_cuda_graph = graph            # exact-global mode inside the captured iteration (NCCL in the graph)
+        sol.graph_capture_after = 0
         x = data[sl].to(dev)
         init = sol.get_init_output(conv, x)
         for t, p in zip(sol.chain_of_transforms, start):
             t.init_parameters()
             t.param = p[sl].to(dev).clone()
-        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True] * 4, n_iter=1,
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True] * 4, n_iter=n_iter,
                                  step_sizes=[1.0] * 4)
         res = {"rank": rank, "slice": (sl.start, sl.stop), "dist": float(sol.last_dist),
+               "replays": getattr(sol, "graph_replays", 0), "redos": getattr(sol, "graph_redos", 0),
                "params": [t.param.detach().cpu() for t in sol.chain_of_transforms]}
         if rank == 0:                                          # the unsharded loop on one GPU
             xf = data.to(dev)
             initf = full.get_init_output(conv, xf)
             for t, p in zip(full.chain_of_transforms, start):
                 t.param = p.to(dev).clone()
-            full.optimizing_transform(model=conv, data=xf, init_output=initf, optimize_flags=[True] * 4, n_iter=1,
+            full.optimizing_transform(model=conv, data=xf, init_output=initf, optimize_flags=[True] * 4, n_iter=n_iter,
                                       step_sizes=[1.0] * 4)
             res["full_dist"] = float(full.last_dist)
             res["full_params"] = [t.param.detach().cpu() for t in full.chain_of_transforms]
@@ -76,8 +79,9 @@ def _worker(rank, world, port, d, gsize, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("graph,n_iter", [(False, 1), (True, 1), (True, 2)])
 @pytest.mark.parametrize("d,gsize", [(2, [4, 1, 48, 64]), (3, [2, 1, 24, 24, 32])])
-def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize):
+def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize, graph, n_iter):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     import torch.multiprocessing as mp
@@ -85,7 +89,7 @@ def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, d, gsize, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, d, gsize, q, graph, n_iter)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]
@@ -94,6 +98,8 @@ def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize):
         assert p.exitcode == 0
     results.sort(key=lambda r: r["rank"])
     ref = results[0]
+    if graph:                                 # the sharded loop really ran as graph replays on every rank
+        assert all(r["replays"] == n_iter and r["redos"] == 0 for r in results), [(r["replays"], r["redos"]) for r in results]
     # the all-reduced loss of the shards is the whole-batch loss
     for r in results:
         assert abs(r["dist"] - ref["full_dist"]) <= 2e-5 * abs(ref["full_dist"]), (r["dist"], ref["full_dist"])
@@ -101,5 +107,6 @@ def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize):
     for i, name in enumerate(names):
         got = torch.cat([r["params"][i] for r in results], 0)
         want = ref["full_params"][i]
-        tol = 0.25 if name == "affine" else 2e-3          # sign step of the affine parameters may flip at |g| ~ 0
+        tol = 0.25 if name == "affine" else (2e-3 if n_iter == 1 else 5e-2)   # affine: sign steps may flip at |g| ~ 0;
+        # two free-running steps amplify fp32-atomic-order differences
         assert float((got - want).norm() / want.norm()) < tol, name
