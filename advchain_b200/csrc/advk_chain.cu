@@ -983,6 +983,24 @@ static int lean_sms() {
   return sms;
 }
 
+// Resident CTAs per SM the lean adjoint kernels are compiled for (their register budget).  Measured at 128^3
+// (gpurun_out/r02g, ncu, us per launch; 0 = no target, the compiler's own choice of 77-102 registers):
+//                              0      2      3      4
+//   field  warp, C = 1        52.4   60.2   44.3   38.3     -> 4 (64 registers, 8-24 bytes of spill)
+//   affine warp, C = 1        89.9    -     84.2   99.8     -> 3
+//   field  warp, packed K=4   63.1   75.4   64.0   66.1     -> 0
+//   affine warp, packed K=4  121.0    -    125.2  136.2     -> 0
+// ADVK_LEAN_MINB overrides all four (experiments).
+static int g_lean_minb = -2;
+static int lean_minb(bool field, bool pack) {
+  if (g_lean_minb == -2) {
+    const char* e = getenv("ADVK_LEAN_MINB");
+    g_lean_minb = e ? atoi(e) : -1;
+  }
+  if (g_lean_minb >= 0) return g_lean_minb;
+  return pack ? 0 : (field ? 4 : 3);
+}
+
 template <int DIM, bool FIELD>
 static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaStream_t st) {
   const bool last = (k == P.n - 1);
@@ -994,14 +1012,23 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
   // the theta gradient is reduced per block: a block walks several tiles so that the per-sample atomics stay few
   unsigned grid = (unsigned)P.n_tiles;
   if (!FIELD && s.g_theta) { const unsigned cap = (unsigned)lean_sms() * 16u; if (grid > cap) grid = cap; }
+  const int minb = lean_minb(FIELD, P.pack != 0);
+#define ADVK_LB(KID, KERN, B1, B2)                                                                       \
+  do {                                                                                                   \
+    if (minb >= 4) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 4><<<grid, 256, 0, st>>>(a)));             \
+    else if (minb == 3) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 3><<<grid, 256, 0, st>>>(a)));        \
+    else if (minb == 2) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 2><<<grid, 256, 0, st>>>(a)));        \
+    else ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 0><<<grid, 256, 0, st>>>(a)));                       \
+  } while (0)
   if (!P.pack) {
-    if (s.src_vm) ADVK_LAUNCH(K_chain_img_bwd, st, (lean_warp_bwd_kernel<DIM, FIELD, true><<<grid, 256, 0, st>>>(a)));
-    else ADVK_LAUNCH(K_chain_img_bwd, st, (lean_warp_bwd_kernel<DIM, FIELD, false><<<grid, 256, 0, st>>>(a)));
+    if (s.src_vm) ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, true, 0);
+    else ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, false, 0);
   } else {
     if (k == 0) a.src = P.src_packed;
-    if (!last) ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_warp_bwd_pk_kernel<DIM, FIELD, true><<<grid, 256, 0, st>>>(a)));
-    else ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_warp_bwd_pk_kernel<DIM, FIELD, false><<<grid, 256, 0, st>>>(a)));
+    if (!last) ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, true, 0);
+    else ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, false, 0);
   }
+#undef ADVK_LB
 }
 
 template <int DIM>

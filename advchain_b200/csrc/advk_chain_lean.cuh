@@ -374,8 +374,8 @@ __device__ __forceinline__ int lean_key(const LGeo<DIM>& G, bool ok) {
   return ok ? ((G.a000 << 2) | (G.dyo ? 1 : 0) | (G.dzo ? 2 : 0)) : -1;
 }
 
-template <int DIM, bool FIELD, bool VM_SRC>
-__global__ void __launch_bounds__(256)
+template <int DIM, bool FIELD, bool VM_SRC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
   typedef typename FieldT<DIM>::type T;
   constexpr int NG = DIM * (DIM + 1);
@@ -469,8 +469,8 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
 
 // channel-packed adjoint: the stashed source and g_src (scatter target) are always packed;
 // GD_PK: layout of the upstream gradient (planar = the user's g_out at the last stage)
-template <int DIM, bool FIELD, bool GD_PK>
-__global__ void __launch_bounds__(256)
+template <int DIM, bool FIELD, bool GD_PK, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
   typedef typename FieldT<DIM>::type T;
   constexpr int NG = DIM * (DIM + 1);

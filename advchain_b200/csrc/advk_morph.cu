@@ -274,6 +274,16 @@ static void launch_init_phi0(const MorphCfg& c, const Dims& g, const float* u_lr
   }
 }
 
+// grid_sample(base, c, border) along one axis: linear interpolation of the linspace.
+__device__ __forceinline__ float compose_axis(float c, int size, float step, float& mult) {
+  float i = gs_index(c, size, ADVK_PAD_BORDER, mult);
+  float f = floorf(i);
+  int i0 = (int)f;
+  float v = base_coord_s(i0, size, step) * ((f + 1.f) - i);
+  if (i0 + 1 < size) v += base_coord_s(i0 + 1, size, step) * (i - f);
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // One squaring step: out(p) = sample(in, at in(p)), border padding, align_corners=True.
 template <int DIM>
@@ -319,9 +329,14 @@ ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM
 
 // Same step with no validity predicates (see ss_step_bwd_lean_kernel: under border padding a corner
 // outside the volume has weight exactly 0, so it is redirected to corner 0 of its axis and adds s * 0).
-template <int DIM>
+//
+// EMIT_R (the LAST step of a 3-D build): also writes r = compose_with_base(phi_n - phi_0 + base) - base, the
+// input of the full-resolution Gaussian (quirk Q1; smooth_in<DIM, 0> is the same arithmetic), so that the
+// smoothing kernel stages ONE field by TMA and evaluates no input map at its halo voxels.
+template <int DIM, bool EMIT_R>
 __global__ void __launch_bounds__(256, 8)
-ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
+ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out,
+                    const typename V<DIM>::T* __restrict__ phi0, typename V<DIM>::T* __restrict__ rout) {
   typedef typename V<DIM>::T T;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
   if (p >= g.S) return;
@@ -351,6 +366,21 @@ ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename 
     }
   }
   (out + nb)[p] = V<DIM>::make(ox, oy, oz);
+  if (EMIT_R) {
+    const T q = __ldg(opaque_ptr(phi0 + nb) + p);
+    int x, y, z;
+    voxel_xyz(g, (unsigned)p, x, y, z);
+    float m;
+    const float bx = base_coord_s(x, g.W, g.stW), by = base_coord_s(y, g.H, g.stH);
+    const float rx = compose_axis((ox - q.x) + bx, g.W, g.stW, m) - bx;
+    const float ry = compose_axis((oy - q.y) + by, g.H, g.stH, m) - by;
+    float rz = 0.f;
+    if (DIM == 3) {
+      const float bz = base_coord_s(z, g.D, g.stD);
+      rz = compose_axis((oz - V<DIM>::z(q)) + bz, g.D, g.stD, m) - bz;
+    }
+    (opaque_ptr(rout + nb))[p] = V<DIM>::make(rx, ry, rz);
+  }
 }
 
 // Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
@@ -525,13 +555,14 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
   }
 }
 
-// advk_morph_tune / ADVK_SSB_MODE: 0 = the lean kernels (default), 1 = the plain predecessors
-// (predicated forward step, one-RED-per-corner adjoint with memset nodes).
+// advk_morph_tune / ADVK_SSB_MODE: bit 0 = the plain predecessors of the lean squaring-step kernels
+// (predicated forward step, one-RED-per-corner adjoint with memset nodes); bit 1 = the two-launch predecessor
+// (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh).  Default 0.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 1) : 0;
+    g_ssb_mode = e ? (atoi(e) & 3) : 0;
   }
   return g_ssb_mode;
 }
@@ -562,16 +593,6 @@ struct SmoothArgs {
   typename V<DIM>::T* out;
   float w[KT];
 };
-
-// grid_sample(base, c, border) along one axis: linear interpolation of the linspace.
-__device__ __forceinline__ float compose_axis(float c, int size, float step, float& mult) {
-  float i = gs_index(c, size, ADVK_PAD_BORDER, mult);
-  float f = floorf(i);
-  int i0 = (int)f;
-  float v = base_coord_s(i0, size, step) * ((f + 1.f) - i);
-  if (i0 + 1 < size) v += base_coord_s(i0 + 1, size, step) * (i - f);
-  return v;
-}
 
 template <int DIM, int MODE>
 __device__ __forceinline__ void smooth_in(const SmoothArgs<DIM>& a, const Dims& g, i64 idx, int z,
@@ -778,6 +799,10 @@ static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const
   }
 }
 
+}  // namespace advk
+#include "advk_smooth_tma.cuh"
+namespace advk {
+
 // ---------------------------------------------------------------------------------------
 // Adjoint of the align_corners=False linear upsample along ONE axis, gather form (deterministic).
 // in  viewed as [outer][n_in ][inner] elements of T, out as [outer][n_out][inner];
@@ -929,11 +954,16 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   if (norm2_out) cudaMemsetAsync(norm2_out, 0, sizeof(float), st);
   launch_init_phi0<DIM>(c, g, u_lr, inv2n, L, norm2_out, st);     // sum |u|^2 as a by-product when asked for
   const bool lean = (ssb_mode() & 1) == 0;
+  // 3-D: the last step also writes the smoothing input r into the scratch level, for the TMA-staged Gaussian
+  const bool fused = DIM == 3 && lean && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
   for (int k = 1; k <= nb; ++k) {
-    if (lean) ADVK_LAUNCH(K_ss_step, st, ss_step_lean_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
+    if (lean && fused && k == nb)
+      ADVK_LAUNCH(K_ss_step, st, (ss_step_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
+    else if (lean) ADVK_LAUNCH(K_ss_step, st, (ss_step_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
     else ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
   }
-  launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
+  if (!(fused && launch_smooth_tma<0>(g, c, L + (nb + 1) * F, nullptr, nullptr, nullptr, field_out, st)))
+    launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
   return check_launch("morph_field_fwd");
 }
 
@@ -957,7 +987,9 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   T* g_off = (T*)scratch;
   T* buf[2] = {g_off + F, g_off + 2 * F};
   // (9)+(8)+(7): clamp mask, Gaussian (self-adjoint), compose-with-base border mask -> g_off = dL/d(off)
-  launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, g_off + 3 * F, st);
+  const bool fused = DIM == 3 && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
+  if (!(fused && launch_smooth_tma<1>(g, c, g_field, field_out, L + nb * F, L, g_off, st)))
+    launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, g_off + 3 * F, st);
   // dL/dphi_n = g_off ; walk the squaring steps back, ping-ponging between two buffers that are
   // zeroed by memset nodes (g_off is kept for the Q1 subtraction below)
   const bool self_zero = (ssb_mode() & 1) == 0;       // the lean adjoint zeroes the buffer it consumed
@@ -1000,7 +1032,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 1;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 3;
   return prev;
 }
 

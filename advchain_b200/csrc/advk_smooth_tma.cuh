@@ -1,0 +1,314 @@
+// advk_smooth_tma.cuh -- 3-D full-resolution Gaussian of the field build (adv_morph.py:377-389, 484-488) as ONE
+// launch: xy tiles marching in z, input planes staged by TMA.  Included by advk_morph.cu (uses KT, KR,
+// SmoothArgs, smooth_out).
+//
+// The reference's smoothing is nn.Conv3d(groups=3, kernel 9^3, padding 4): ZERO padding.  A TMA box load
+// (cp.async.bulk.tensor.5d, tensor = [N][D][H][W][4 floats]) fills the part of a box that lies outside the
+// tensor with zeros, so a haloed plane tile costs one instruction of one thread, no bounds arithmetic, and the
+// halo is the convolution's padding exactly.  A CTA owns a 32 x 16 tile of (x, y) and a run of z planes:
+//     producer (thread 0): keeps 2-3 plane tiles in flight on an mbarrier ring (arrive.expect_tx + TMA);
+//     x pass: 6 warps, one thread per (row, 4 consecutive outputs): 12 LDS.128 of the float4 tile -> 108 FMA
+//             (rows are 41 float4 apart = 4 banks mod 32, so a quarter-warp's 8 rows hit 8 different bank groups);
+//     y pass: every thread owns one column and 2 rows: 10 LDS.32 per component from the planar x-pass result;
+//     z pass: in registers, scatter form -- a new xy-smoothed plane adds w[8-m] * t to the 9 output planes it
+//             belongs to, the oldest accumulator is complete and leaves through the output map; the plane loop is
+//             unrolled by 9 so that the accumulator ring is addressed statically (no register shifts).
+// One __syncthreads per plane (the x-pass result is double-buffered).  The input is ONE field: forward, the
+// compose-with-base offsets r, written by the last squaring step; backward, g_field -- the gradient with
+// respect to the UNCLAMPED field, which every consumer of the field has already masked by the clamp range
+// (the warps clamp on load: advk_warp_field_bwd, the chain adjoints; torch.clamp in user code), so the mask
+// the two-launch version applies once more (idempotent) is not repeated here.  The float4 round trip through
+// HBM between the xy and z launches and the 90-instruction input map at every halo voxel are gone.
+#pragma once
+#include <cuda.h>   // CUtensorMap and the encoder's prototype only: the entry point is fetched through the runtime
+
+namespace advk {
+
+constexpr int FT_TX = 32, FT_TY = 16, FT_THREADS = 256;
+constexpr int FT_BW = FT_TX + 2 * KR + 1;      // 41 columns: one more than needed, for the bank-friendly row stride
+constexpr int FT_BH = FT_TY + 2 * KR;          // 24 rows
+constexpr int FT_TILE_BYTES = FT_BW * FT_BH * 16;   // 15744 = 123 * 128
+constexpr int FT_TMP_LD = FT_TX + 4;           // 36 floats: row stride of the planar x-pass result (4 banks mod 32)
+constexpr int FT_TMP_FLOATS = 3 * FT_BH * FT_TMP_LD;
+static_assert(FT_TILE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+
+template <int MODE> struct FtCfg {
+  static constexpr int NT = 1;                 // tiles per stage
+  static constexpr int NS = 3;                 // stages in flight
+  static constexpr int SMEM = NS * NT * FT_TILE_BYTES + 2 * FT_TMP_FLOATS * 4 + NS * 8;
+};
+
+struct FtArgs {
+  Dims g;
+  SmoothArgs<3> a;
+  int zc, nzc;          // output planes per CTA, CTAs per sample along z
+};
+
+__device__ __forceinline__ unsigned ft_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ft_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FT_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FT_DONE_%=;\n"
+      "bra FT_WAIT_%=;\n"
+      "FT_DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ft_tma_load(unsigned dst, const CUtensorMap* map, int x, int y, int z, int n, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"((unsigned long long)map), "r"(0), "r"(x), "r"(y), "r"(z), "r"(n), "r"(bar) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ FtArgs q) {
+  constexpr int NT = FtCfg<MODE>::NT, NS = FtCfg<MODE>::NS;
+  extern __shared__ __align__(128) unsigned char ft_smem[];
+  const float4* s_in = reinterpret_cast<const float4*>(ft_smem);                  // [NS][NT][BH][BW]
+  float* s_tmp = reinterpret_cast<float*>(ft_smem + NS * NT * FT_TILE_BYTES);     // [2][3][BH][TMP_LD]
+  const unsigned bar0 = ft_smem_u32(ft_smem + NS * NT * FT_TILE_BYTES + 2 * FT_TMP_FLOATS * 4);
+  const unsigned in0 = ft_smem_u32(ft_smem);
+  const Dims& g = q.g;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * FT_TX, y0 = blockIdx.y * FT_TY;
+  const int n = blockIdx.z / q.nzc, zb = (blockIdx.z - n * q.nzc) * q.zc;
+  const int zend = min(zb + q.zc, g.D);
+  const int np = (zend - zb) + 2 * KR;            // input planes zb-KR .. zend+KR-1 (those outside the volume are zeros)
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) ft_mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // plane i lives in stage i % NS; only planes inside the volume are loaded (and waited for)
+  auto issue = [&](int i) {
+    const int zi = zb - KR + i;
+    if (zi < 0 || zi >= g.D) return;
+    const int s = i % NS;
+    const unsigned bar = bar0 + 8 * s;
+    ft_mbar_expect(bar, NT * FT_TILE_BYTES);
+    ft_tma_load(in0 + (s * NT) * FT_TILE_BYTES, &mapA, x0 - KR, y0 - KR, zi, n, bar);
+    if (NT == 2) ft_tma_load(in0 + (s * NT + 1) * FT_TILE_BYTES, &mapB, x0 - KR, y0 - KR, zi, n, bar);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < NS && i < np; ++i) issue(i);
+  }
+  float w[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) w[k] = q.a.w[k];
+  // x-pass task of this thread (warps 0..5): row = 8 * (warp % 3) + (lane % 8), outputs 4 * run .. + 3
+  const int wrp = tid >> 5, lane = tid & 31;
+  const int xrow = 8 * (wrp % 3) + (lane & 7), xrun = (wrp / 3) * 4 + (lane >> 3);
+  // y/z-pass positions of this thread: column tx, rows 2 * yg and 2 * yg + 1
+  const int tx = lane, yg = wrp;
+  float acc[2][3][KT];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int m = 0; m < KT; ++m) acc[j][c][m] = 0.f;
+  unsigned phases = 0;
+  const i64 HW = (i64)g.H * g.W;
+  const int gx = x0 + tx, gy0 = y0 + 2 * yg;
+  // output map, per-thread constants: base coordinates of the column / the two rows, border-clip bounds
+  const float bx = base_coord_s(gx, g.W, g.stW);
+  const float by[2] = {base_coord_s(gy0, g.H, g.stH), base_coord_s(gy0 + 1, g.H, g.stH)};
+  const float mxW = (float)(g.W - 1), mxH = (float)(g.H - 1), mxD = (float)(g.D - 1);
+  const bool okx = gx < g.W;
+  const bool oky[2] = {okx && gy0 < g.H, okx && gy0 + 1 < g.H};
+  const i64 obase = (i64)n * g.S + (i64)gy0 * g.W + gx;
+  for (int base = 0; base < np; base += KT) {
+#pragma unroll
+    for (int u = 0; u < KT; ++u) {
+      const int i = base + u;
+      if (i >= np) break;
+      const int zi = zb - KR + i;
+      const bool live = zi >= 0 && zi < g.D;            // block-uniform
+      float t[2][3];
+      if (live) {
+        const int s = i % NS;
+        ft_mbar_wait(bar0 + 8 * s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        float* tmp = s_tmp + (i & 1) * FT_TMP_FLOATS;
+        if (wrp < 6) {
+          const float4* rowA = s_in + ((s * NT) * FT_BH + xrow) * FT_BW + 4 * xrun;
+          float o[3][4];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[c][j] = 0.f;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) {
+            const float4 v = rowA[e];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = e - j;
+              if (k >= 0 && k < KT) { o[0][j] += w[k] * v.x; o[1][j] += w[k] * v.y; o[2][j] += w[k] * v.z; }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<float4*>(tmp + (c * FT_BH + xrow) * FT_TMP_LD + 4 * xrun) =
+                make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        }
+        __syncthreads();                  // x-pass result complete; stage s has been read by everybody
+      }
+      // stage i % NS is free either way (a plane outside the volume never occupied it)
+      if (tid == 0 && i + NS < np) issue(i + NS);
+      if (live) {
+        const float* tmp = s_tmp + (i & 1) * FT_TMP_FLOATS;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float in[10];
+#pragma unroll
+          for (int e = 0; e < 10; ++e) in[e] = tmp[(c * FT_BH + 2 * yg + e) * FT_TMP_LD + tx];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) sacc += w[k] * in[j + k];
+            t[j][c] = sacc;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) t[j][c] = 0.f;
+      }
+      // z pass: plane zi is tap k of output plane zi + KR - k; ring slot of output plane zo is (zo - zb + KR) % KT
+      // ... written with the slot of output (zi - KR + m) = (u + m) % KT, static after unrolling
+      if (live) {
+#pragma unroll
+        for (int m = 0; m < KT; ++m) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[j][c][(u + m) % KT] += w[KT - 1 - m] * t[j][c];
+        }
+      }
+      if (i >= 2 * KR) {                  // output plane zo = zi - KR is complete: slot u
+        const int zo = zi - KR;
+        const float bz = base_coord_s(zo, g.D, g.stD);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (!oky[j]) continue;
+          const i64 idx = obase + (i64)zo * HW + (i64)j * g.W;
+          const float s0 = acc[j][0][u], s1 = acc[j][1][u], s2 = acc[j][2][u];
+          if (MODE == 0) {
+            q.a.out[idx] = make_float4(s0 + bx, s1 + by[j], s2 + bz, 0.f);          // field = G (*) r + base
+          } else {
+            // border-clip mask of the compose-with-base grid_sample (smooth_out<3, 1>: gs_index, border padding):
+            // the gradient passes where the pixel coordinate of phi_n - phi_0 + base lies strictly inside
+            const float4 pn = __ldg(q.a.C + idx), p0 = __ldg(q.a.D + idx);
+            const float px = (((pn.x - p0.x) + bx + 1.f) / 2.f) * mxW;
+            const float py = (((pn.y - p0.y) + by[j] + 1.f) / 2.f) * mxH;
+            const float pz = (((pn.z - p0.z) + bz + 1.f) / 2.f) * mxD;
+            q.a.out[idx] = make_float4((px > 0.f && px < mxW) ? s0 : 0.f, (py > 0.f && py < mxH) ? s1 : 0.f,
+                                       (pz > 0.f && pz < mxD) ? s2 : 0.f, 0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[j][c][u] = 0.f;      // slot u now collects output plane zi + KR + 1
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+
+typedef CUresult (*ft_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static ft_encode_fn ft_encoder() {
+  static ft_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (ft_encode_fn)p;
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// tensor map of one interleaved 3-D field [N][D][H][W] x float4, box = one haloed plane tile
+static bool ft_make_map(const Dims& g, const void* field, CUtensorMap* map) {
+  ft_encode_fn enc = ft_encoder();
+  if (!enc || ((uintptr_t)field & 15)) return false;
+  const cuuint64_t dims[5] = {4, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.N};
+  const cuuint64_t strides[4] = {16, 16ull * g.W, 16ull * g.W * g.H, 16ull * (cuuint64_t)g.S};
+  const cuuint32_t box[5] = {4, (cuuint32_t)FT_BW, (cuuint32_t)FT_BH, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(field), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int ft_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+  }
+  return sms;
+}
+
+// Launches the fused smoothing; returns false (nothing launched) when TMA cannot be used -- the caller then
+// runs the two-launch kernels.  inA: the field the Gaussian is applied to (forward: r; backward: g_field),
+// inB: backward only, the field whose clamp range masks inA.
+template <int MODE>
+static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA, const void* inB, const void* C,
+                              const void* D, void* out, cudaStream_t st) {
+  static int ready = -1;
+  if (ready < 0)
+    ready = cudaFuncSetAttribute(smooth3d_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 FtCfg<MODE>::SMEM) == cudaSuccess ? 1 : 0;
+  if (!ready) { (void)cudaGetLastError(); return false; }
+  CUtensorMap mapA, mapB;
+  if (!ft_make_map(g, inA, &mapA)) return false;
+  mapB = mapA;      // (second operand slot: unused since the backward stages one field)
+  FtArgs q;
+  q.g = g;
+  q.a.A = (const float4*)inA; q.a.B = (const float4*)inB; q.a.C = (const float4*)C; q.a.D = (const float4*)D;
+  q.a.out = (float4*)out;
+  for (int i = 0; i < KT; ++i) q.a.w[i] = c.w[i];
+  const int tx = (g.W + FT_TX - 1) / FT_TX, ty = (g.H + FT_TY - 1) / FT_TY;
+  // z runs: as many CTAs as fit the machine at once (2 per SM), never shorter than 8 planes (halo = 8)
+  const i64 tiles = (i64)tx * ty * g.N;
+  i64 chunks = (2LL * ft_sms()) / tiles;
+  if (chunks < 1) chunks = 1;
+  int zc = (int)((g.D + chunks - 1) / chunks);
+  if (zc < 8) zc = 8;
+  if (zc > g.D) zc = g.D;
+  q.zc = zc; q.nzc = (g.D + zc - 1) / zc;
+  if ((i64)g.N * q.nzc > 65535) return false;
+  dim3 grid(tx, ty, (unsigned)(g.N * q.nzc));
+  ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
+              (smooth3d_tma_kernel<MODE><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+  return true;
+}
+
+}  // namespace advk

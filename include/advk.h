@@ -150,17 +150,24 @@ int advk_morph_field_fwd(const advk_geom* g, const advk_morph_cfg* cfg, const fl
                          float scale, int nb_steps, float* u_lr, void* levels, void* field_out,
                          float* norm2_out, void* stream);
 /* scratch: 5 fields of N*S elements (4 are used); lr_scratch: advk_morph_lr_scratch_floats() floats.
- * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out. */
+ * g_v: N x d x lr, written. g_field: gradient w.r.t. field_out, i.e. w.r.t. the UNCLAMPED field: a
+ * consumer that clamps the field on load (every warp of this library; torch.clamp in user code) has already
+ * zeroed it outside the clamp range (adv_morph.py:489-490). */
 size_t advk_morph_lr_scratch_floats(const advk_geom* g, const advk_morph_cfg* cfg);
 int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float scale, int nb_steps,
                          const void* levels, const void* field_out, const void* g_field,
                          void* scratch, float* lr_scratch, float* g_v, void* stream);
-/* Kernel variant of the squaring steps (A/B timing and tests): 0 = the lean kernels (default: no
- * validity predicates -- an outside corner has weight 0 under border padding and is redirected to an inside
- * one --, x hand-off by weight before the RED, the adjoint zeroes the ping-pong buffer it consumed);
- * 1 = the plain predecessors (predicated forward step; one RED per corner, memset nodes).  Environment
- * ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries; returns the
- * previous mask. */
+/* Kernel variants of the field build (A/B timing and tests), a bit mask; 0 = defaults.
+ *   bit 0: the plain predecessors of the lean squaring-step kernels (predicated forward step; one RED per
+ *          corner, memset nodes).  Default: no validity predicates -- an outside corner has weight 0 under
+ *          border padding and is redirected to an inside one --, x hand-off by weight before the RED, the
+ *          adjoint zeroes the ping-pong buffer it consumed.
+ *   bit 1: the two-launch predecessor (xy tile kernel + z column kernel) of the 3-D full-resolution Gaussian.
+ *          Default: ONE launch per direction, plane tiles staged by TMA (cp.async.bulk.tensor, out-of-bounds
+ *          zero fill = the convolution's zero padding) on an mbarrier ring; forward, the last squaring step
+ *          writes the Gaussian's input itself.
+ * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
+ * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
 
 /* ---- AdvNoise / AdvBias: intensity stage ------------------------------------------------

@@ -207,11 +207,12 @@ MORPH_TIE_TOL = 1e-2
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
 @pytest.mark.parametrize("support", ["interior", "full"])
-@pytest.mark.parametrize("tile", [0, 1])
+@pytest.mark.parametrize("tile", [0, 1, 2])
 def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
     """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp.
-    `tile` is the advk_morph_tune mask: 0 the lean squaring-step kernels (default), 1 their plain
-    predecessors (predicated forward step, one RED per corner + memset nodes)."""
+    `tile` is the advk_morph_tune mask: 0 the defaults (lean squaring-step kernels; 3-D: TMA-staged one-launch
+    Gaussian fed by the last squaring step), bit 0 the plain squaring-step predecessors (predicated forward
+    step, one RED per corner + memset nodes), bit 1 the two-launch predecessor of the 3-D Gaussian."""
     from advchain_b200 import _lib
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()
