@@ -40,6 +40,12 @@ class ShardContext(object):
         self.world_size = dist.get_world_size(group)
         self.local = shard_slice(self.global_batch, self.rank, self.world_size)
 
+    def close(self):
+        """Call before `dist.destroy_process_group()`: captured PGD iterations hold this group's NCCL
+        all-reduces, and the communicator cannot be destroyed while those CUDA graphs are alive."""
+        from .solver import release_graphs
+        release_graphs()
+
     @property
     def local_batch(self):
         return self.local.stop - self.local.start

@@ -33,6 +33,20 @@ _FUSABLE = (AdvNoise, AdvBias, AdvMorph, AdvAffine)
 _GRAPH_CACHE = collections.OrderedDict()
 _GRAPH_CACHE_MAX = 8
 _GRAPH_SEEN = {}
+_ATEXIT = []
+
+
+def release_graphs():
+    """Destroys every captured PGD iteration (the process-wide cache).  MUST run before the NCCL process group of
+    an exact-global run is destroyed: a communicator whose all-reduces were captured cannot be torn down while
+    the graphs that reference it are alive (ncclCommDestroy waits for them: the process would hang at exit).
+    `ShardContext.close()` and an atexit hook call it; call it yourself before `dist.destroy_process_group()`."""
+    import gc
+    _GRAPH_CACHE.clear()
+    _GRAPH_SEEN.clear()
+    gc.collect()
+    if torch.cuda.is_available() and torch.cuda.is_initialized():
+        torch.cuda.synchronize()
 
 
 class ComposeAdversarialTransformSolver(object):
@@ -545,6 +559,10 @@ class ComposeAdversarialTransformSolver(object):
             graph = torch.cuda.CUDAGraph()
             from .. import _lib
             before = _lib.launch_count()
+            if self.shard is not None and not _ATEXIT:
+                import atexit
+                atexit.register(release_graphs)       # graphs that captured NCCL work go before the communicator
+                _ATEXIT.append(True)
             # (thread-local capture mode: the NCCL watchdog thread of an exact-global run may touch the runtime)
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.shard is not None else "global"):
                 self._graph_iteration(model, st)

@@ -922,6 +922,18 @@ static void lean_fill_int(const Program& P, const Stage& s, bool last, LeanInt& 
   a.g_dst = s.g_dst; a.g_src = s.g_src; a.g_delta = s.g_delta; a.g_up = s.g_up;
 }
 
+// bias stage with an upsampled field -> the row-wise intensity kernel (ADVK_LEAN_INT_ROWS=0: the per-voxel one)
+static bool lean_int_rows(const Program& P, const Stage& s) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ADVK_LEAN_INT_ROWS"); on = (e && e[0] == '0') ? 0 : 1; }
+  const i64 gz = (i64)P.g.N * P.g.D;
+  return on && s.order != 0 && s.b.upsample && s.b.lW <= LIR_MAX && gz <= 65535 && P.g.S < 0x7fffffffLL;
+}
+template <int DIM>
+static dim3 lean_int_grid(const Program& P) {
+  return dim3(1, (unsigned)((P.g.H + 7) / 8), (unsigned)(DIM == 3 ? P.g.N * P.g.D : P.g.N));
+}
+
 template <int DIM, bool FIELD>
 static void lean_launch_warp_fwd(const Program& P, const Stage& s, int k, cudaStream_t st) {
   const bool last = (k == P.n - 1);
@@ -965,7 +977,8 @@ static int lean_fwd(Program& P, cudaStream_t st) {
     if (s.kind == ADVK_STAGE_INTENSITY) {
       LeanInt a;
       lean_fill_int(P, s, k == P.n - 1, a);
-      ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_kernel<DIM, false><<<grid, 256, 0, st>>>(a)));
+      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_rows_kernel<DIM, false><<<lean_int_grid<DIM>(P), 256, 0, st>>>(a)));
+      else ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_kernel<DIM, false><<<grid, 256, 0, st>>>(a)));
     } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_fwd<DIM, true>(P, s, k, st);
     else lean_launch_warp_fwd<DIM, false>(P, s, k, st);
   }
@@ -1046,7 +1059,8 @@ static int lean_bwd(Program& P, cudaStream_t st) {
     if (s.kind == ADVK_STAGE_INTENSITY) {
       LeanInt a;
       lean_fill_int(P, s, last, a);
-      ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_kernel<DIM, true><<<grid, 256, 0, st>>>(a)));
+      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_rows_kernel<DIM, true><<<lean_int_grid<DIM>(P), 256, 0, st>>>(a)));
+      else ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_kernel<DIM, true><<<grid, 256, 0, st>>>(a)));
     } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_bwd<DIM, true>(P, s, k, st);
     else lean_launch_warp_bwd<DIM, false>(P, s, k, st);
   }

@@ -8,6 +8,7 @@
 // is  low = (A_D (x) A_H (x) A_W) cp  -- a few hundred FMAs per low-res voxel -- and the full-res
 // bias is evaluated on the fly per voxel (linear upsample + exp + clip) without ever being stored.
 #include "advk_intensity.cuh"
+#include "advk_adjoint.cuh"
 
 namespace advk {
 
@@ -238,9 +239,12 @@ extern "C" int advk_bias_upsample_adjoint(const advk_geom* gg, const advk_bias_c
     ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot, 256), 256, 0, st>>>(a, s1, g.N, g.D, b.lD, (i64)g.H * g.W, b.sD));
     a = s1; s1 += tot;
   }
-  i64 tot2 = (i64)g.N * b.lD * b.lH * g.W;
-  ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot2, 256), 256, 0, st>>>(a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH));
-  i64 tot3 = (i64)g.N * b.lD * b.lH * b.lW;
-  ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot3, 256), 256, 0, st>>>(s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW));
+  // the last two axes in one launch (advk_adjoint.cuh); per-axis kernels when a row does not fit shared memory
+  if (!launch_adjoint_hw<float>(K_adjoint_axis_f, a, nullptr, 1.f, g_low, (i64)g.N * b.lD, g.H, g.W, b.lH, b.lW, b.sH, b.sW, st)) {
+    i64 tot2 = (i64)g.N * b.lD * b.lH * g.W;
+    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot2, 256), 256, 0, st>>>(a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH));
+    i64 tot3 = (i64)g.N * b.lD * b.lH * b.lW;
+    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot3, 256), 256, 0, st>>>(s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW));
+  }
   return check_launch("bias_upsample_adjoint");
 }

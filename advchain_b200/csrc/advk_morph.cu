@@ -13,6 +13,7 @@
 // load and every backward scatter ONE vector reduction (REDG.E.ADD.F32x2/x4).
 #include <stdlib.h>
 #include "advk_common.cuh"
+#include "advk_adjoint.cuh"
 
 namespace advk {
 
@@ -1016,9 +1017,12 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
     a = s1; a2 = nullptr; b = nullptr; vs = 1.f;
     s1 += (i64)g.N * c.Dl * g.H * g.W;
   }
-  launch_adjoint_axis<T>(a, a2, b, vs, s1, (i64)g.N * c.Dl, g.H, c.Hl, g.W, c.sH, st);
   T* s2 = s1 + (i64)g.N * c.Dl * c.Hl * g.W;
-  launch_adjoint_axis<T>(s1, nullptr, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
+  // the last two axes in one launch (advk_adjoint.cuh); per-axis kernels when a row does not fit shared memory
+  if (a2 || !launch_adjoint_hw<T>(K_adjoint_axis, a, b, vs, s2, (i64)g.N * c.Dl, g.H, g.W, c.Hl, c.Wl, c.sH, c.sW, st)) {
+    launch_adjoint_axis<T>(a, a2, b, vs, s1, (i64)g.N * c.Dl, g.H, c.Hl, g.W, c.sH, st);
+    launch_adjoint_axis<T>(s1, nullptr, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
+  }
   float* planar = (float*)(s2 + (i64)g.N * lr);
   ADVK_LAUNCH(K_aos_to_planar, st, aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr));
   int NC = g.N * DIM;

@@ -69,8 +69,8 @@ __device__ __forceinline__ void ft_tma_load(unsigned dst, const CUtensorMap* map
       ::"r"(dst), "l"((unsigned long long)map), "r"(0), "r"(x), "r"(y), "r"(z), "r"(n), "r"(bar) : "memory");
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(FT_THREADS, MINB)
 smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ FtArgs q) {
   constexpr int NT = FtCfg<MODE>::NT, NS = FtCfg<MODE>::NS;
@@ -138,6 +138,17 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int zi = zb - KR + i;
       const bool live = zi >= 0 && zi < g.D;            // block-uniform
       float t[2][3];
+      // backward: the two fields of the output map are requested a whole plane of work ahead of their use
+      float4 pn[2], p0[2];
+      if (MODE == 1 && i >= 2 * KR) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (oky[j]) {
+            const i64 idx = obase + (i64)(zi - KR) * HW + (i64)j * g.W;
+            pn[j] = __ldg(q.a.C + idx); p0[j] = __ldg(q.a.D + idx);
+          }
+        }
+      }
       if (live) {
         const int s = i % NS;
         ft_mbar_wait(bar0 + 8 * s, (phases >> s) & 1u);
@@ -213,10 +224,9 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           } else {
             // border-clip mask of the compose-with-base grid_sample (smooth_out<3, 1>: gs_index, border padding):
             // the gradient passes where the pixel coordinate of phi_n - phi_0 + base lies strictly inside
-            const float4 pn = __ldg(q.a.C + idx), p0 = __ldg(q.a.D + idx);
-            const float px = (((pn.x - p0.x) + bx + 1.f) / 2.f) * mxW;
-            const float py = (((pn.y - p0.y) + by[j] + 1.f) / 2.f) * mxH;
-            const float pz = (((pn.z - p0.z) + bz + 1.f) / 2.f) * mxD;
+            const float px = (((pn[j].x - p0[j].x) + bx + 1.f) / 2.f) * mxW;
+            const float py = (((pn[j].y - p0[j].y) + by[j] + 1.f) / 2.f) * mxH;
+            const float pz = (((pn[j].z - p0[j].z) + bz + 1.f) / 2.f) * mxD;
             q.a.out[idx] = make_float4((px > 0.f && px < mxW) ? s0 : 0.f, (py > 0.f && py < mxH) ? s1 : 0.f,
                                        (pz > 0.f && pz < mxD) ? s2 : 0.f, 0.f);
           }
@@ -282,10 +292,17 @@ static int ft_sms() {
 template <int MODE>
 static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA, const void* inB, const void* C,
                               const void* D, void* out, cudaStream_t st) {
-  static int ready = -1;
-  if (ready < 0)
-    ready = cudaFuncSetAttribute(smooth3d_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 FtCfg<MODE>::SMEM) == cudaSuccess ? 1 : 0;
+  // resident CTAs per SM the kernel is compiled for: 2 (112-119 registers) or 3 (80 registers, ~10 of them
+  // spilled); ADVK_FT_MINB selects (A/B)
+  static int ready = -1, minb = 2;
+  if (ready < 0) {
+    const char* e = getenv("ADVK_FT_MINB");
+    minb = (e && atoi(e) == 3) ? 3 : 2;
+    ready = (cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  FtCfg<MODE>::SMEM) == cudaSuccess &&
+             cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  FtCfg<MODE>::SMEM) == cudaSuccess) ? 1 : 0;
+  }
   if (!ready) { (void)cudaGetLastError(); return false; }
   CUtensorMap mapA, mapB;
   if (!ft_make_map(g, inA, &mapA)) return false;
@@ -296,9 +313,9 @@ static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA,
   q.a.out = (float4*)out;
   for (int i = 0; i < KT; ++i) q.a.w[i] = c.w[i];
   const int tx = (g.W + FT_TX - 1) / FT_TX, ty = (g.H + FT_TY - 1) / FT_TY;
-  // z runs: as many CTAs as fit the machine at once (2 per SM), never shorter than 8 planes (halo = 8)
+  // z runs: as many CTAs as fit the machine at once, never shorter than 8 planes (halo = 8)
   const i64 tiles = (i64)tx * ty * g.N;
-  i64 chunks = (2LL * ft_sms()) / tiles;
+  i64 chunks = ((i64)minb * ft_sms()) / tiles;
   if (chunks < 1) chunks = 1;
   int zc = (int)((g.D + chunks - 1) / chunks);
   if (zc < 8) zc = 8;
@@ -306,8 +323,12 @@ static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA,
   q.zc = zc; q.nzc = (g.D + zc - 1) / zc;
   if ((i64)g.N * q.nzc > 65535) return false;
   dim3 grid(tx, ty, (unsigned)(g.N * q.nzc));
-  ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
-              (smooth3d_tma_kernel<MODE><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+  if (minb == 3)
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
+                (smooth3d_tma_kernel<MODE, 3><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+  else
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
+                (smooth3d_tma_kernel<MODE, 2><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
   return true;
 }
 

@@ -414,6 +414,12 @@ def workload_config(args, d, size, chain, per_gpu=None):
 
 # ----------------------------------------------------------------------------------- GPU arm
 
+def _release_graphs():
+    """Captured iterations of an exact-global run hold NCCL work: they go before the process group does."""
+    from advchain_b200.augmentor.solver import release_graphs
+    release_graphs()
+
+
 def build_solver(d, size, chain, dev):
     from advchain_b200.augmentor import (AdvAffine, AdvBias, AdvMorph, AdvNoise,
                                          ComposeAdversarialTransformSolver)
@@ -607,6 +613,7 @@ def run_b200(args):
 
     if rank != 0:
         if world > 1:
+            _release_graphs()
             dist.destroy_process_group()
         return 0
 
@@ -718,7 +725,9 @@ def run_b200(args):
         with open(args.profile_out, "w") as f:
             json.dump({"breakdown_ms_per_step": dict(ranked), "line": line}, f, indent=1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        _release_graphs()
         dist.destroy_process_group()
     return 0
 

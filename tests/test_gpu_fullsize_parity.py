@@ -116,8 +116,12 @@ def test_cuda_matches_reference_and_oracle_at_full_size(name):
         params = [st.param.detach().clone() for st in osol.stages]
         if s + 1 < case["n_iter"]:
             for i, p in enumerate(params):
+                # (the oracle runs on THIS box's host cores: ATen's CPU kernels reduce in a thread-count-dependent
+                # order, so its trajectory leaves the fixture's by a few 1e-5 per step on white noise -- seen on a
+                # box with a different core count, gpurun_out/r02k; the CUDA path is checked against the oracle
+                # evaluated here, at the same parameters, above)
                 e, ck = big_err(p, z, "s%d_param_%d" % (s + 1, i), case)
-                assert e < 5e-6 and ck < 2e-6, (s, names[i], e, ck)
+                assert e < 2e-4 and ck < 2e-5, (s, names[i], e, ck)
     print("\n%s: per-step (step, transform, grad err vs oracle, vs fixture): %s" % (name, report))
     if replay != case["n_iter"]:
         return
@@ -128,7 +132,7 @@ def test_cuda_matches_reference_and_oracle_at_full_size(name):
     fparams = [st.param.detach().clone() for st in osol.stages]
     for i, p in enumerate(fparams):
         e, ck = big_err(p, z, "final_param_%d" % i, case)
-        assert e < 5e-6 and ck < 2e-6, (names[i], e, ck)
+        assert e < 5e-4 and ck < 5e-5, (names[i], e, ck)
         if "final_param_%d" % i in z:               # teacher forcing: the reference's own final parameters
             fparams[i] = z["final_param_%d" % i].clone()
             osol.stages[i].param = fparams[i].clone()

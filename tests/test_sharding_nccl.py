@@ -76,6 +76,9 @@ def _worker(rank, world, port, d, gsize, q, graph=False, n_iter=1):
         q.put(res)
         dist.barrier()
     finally:
+        ctx_close = locals().get("ctx")
+        if ctx_close is not None:
+            ctx_close.close()                 # captured NCCL all-reduces go before the communicator
         dist.destroy_process_group()
 
 
@@ -92,9 +95,9 @@ def test_two_gpu_shards_reproduce_the_unsharded_loop(d, gsize, graph, n_iter):
     procs = [ctx.Process(target=_worker, args=(r, world, port, d, gsize, q, graph, n_iter)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
+    results = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     results.sort(key=lambda r: r["rank"])
     ref = results[0]
