@@ -52,19 +52,21 @@ adjoint_hw_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T*
   int plo, phi;
   ahw_support(j, H, sH, plo, phi);
   const bool hb = (b != nullptr);
-  for (int x = lane; x < W; x += 32) {
-    T s;
-    ahw_zero(s);
-    for (int p = plo + wrp; p <= phi; p += 8) {
-      const float w = ahw_weight(p, j, Hl, sH);
-      if (w != 0.f) {
-        const i64 q = (o * H + p) * W + x;
-        T av = a[q];
-        if (hb) av = ahw_sub(av, b[q]);
-        ahw_fma(s, w, av);
-      }
+  // (rows outer, columns inner and unrolled: a warp's loads of one row are independent of each other, so they
+  // are all in flight together instead of one latency per (row, column chunk))
+  for (int x = lane; x < W; x += 32) ahw_zero(colsum[wrp * W + x]);
+  for (int p = plo + wrp; p <= phi; p += 8) {
+    const float w = ahw_weight(p, j, Hl, sH);
+    if (w == 0.f) continue;
+    const i64 rowq = (o * H + p) * W;
+#pragma unroll 4
+    for (int x = lane; x < W; x += 32) {
+      T av = __ldg(a + rowq + x);
+      if (hb) av = ahw_sub(av, __ldg(b + rowq + x));
+      T s = colsum[wrp * W + x];
+      ahw_fma(s, w, av);
+      colsum[wrp * W + x] = s;
     }
-    colsum[wrp * W + x] = s;
   }
   __syncthreads();
   for (int jl = wrp; jl < Wl; jl += 8) {

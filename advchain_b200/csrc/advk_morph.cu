@@ -558,14 +558,55 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
 
 // advk_morph_tune / ADVK_SSB_MODE: bit 0 = the plain predecessors of the lean squaring-step kernels
 // (predicated forward step, one-RED-per-corner adjoint with memset nodes); bit 1 = the two-launch predecessor
-// (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh).  Default 0.
+// (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh); bit 2 = the lean
+// adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd).  Default 0.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 3) : 0;
+    g_ssb_mode = e ? (atoi(e) & 7) : 0;
   }
   return g_ssb_mode;
+}
+
+// A side stream per device for work that can run BESIDE the calling stream (the zeroing of scatter targets):
+// forked and joined with events only, so it is legal under stream capture and never synchronises the host.
+struct SideStream {
+  cudaStream_t s;
+  cudaEvent_t ev[16];
+  int next;
+  cudaEvent_t event() { cudaEvent_t e = ev[next]; next = (next + 1) & 15; return e; }
+  // memset `p` on the side stream after everything enqueued on `st` so far; returns the event to wait for
+  cudaEvent_t zero_beside(cudaStream_t st, void* p, size_t bytes) {
+    cudaEvent_t a = event(), b = event();
+    cudaEventRecord(a, st);
+    cudaStreamWaitEvent(s, a, 0);
+    cudaMemsetAsync(p, 0, bytes, s);
+    cudaEventRecord(b, s);
+    return b;
+  }
+};
+static SideStream* side_stream(cudaStream_t st) {
+  static SideStream* tab[64] = {nullptr};
+  static bool failed[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || failed[dev]) return nullptr;
+  if (!tab[dev]) {
+    // creating a stream is not a capturable operation: a first use inside a capture keeps the in-kernel
+    // zeroing (the solver's graph loop runs an eager warm-up iteration before it captures)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    SideStream* n = new SideStream();
+    n->next = 0;
+    bool ok = cudaStreamCreateWithFlags(&n->s, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreateWithFlags(&n->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); failed[dev] = true; delete n; return nullptr; }
+    tab[dev] = n;
+  }
+  return tab[dev];
 }
 
 template <int DIM>
@@ -991,16 +1032,40 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
   const bool fused = DIM == 3 && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
   if (!(fused && launch_smooth_tma<1>(g, c, g_field, field_out, L + nb * F, L, g_off, st)))
     launch_smooth<DIM, 1>(g, c, g_field, field_out, L + nb * F, L, g_off, g_off + 3 * F, st);
-  // dL/dphi_n = g_off ; walk the squaring steps back, ping-ponging between two buffers that are
-  // zeroed by memset nodes (g_off is kept for the Q1 subtraction below)
-  const bool self_zero = (ssb_mode() & 1) == 0;       // the lean adjoint zeroes the buffer it consumed
-  if (self_zero) cudaMemsetAsync(buf[0], 0, sizeof(T) * F * (nb > 1 ? 2 : 1), st);
+  // dL/dphi_n = g_off ; walk the squaring steps back through scatter targets that must be zero on entry
+  // (g_off is kept for the Q1 subtraction below)
+  const bool self_zero = (ssb_mode() & 1) == 0;       // the lean adjoint can zero the buffer it consumed
+  SideStream* ss = (self_zero && (ssb_mode() & 4) == 0 && nb >= 3) ? side_stream(st) : nullptr;
   T* cur = g_off;
-  for (int k = nb; k >= 1; --k) {
-    T* nxt = buf[(nb - k) & 1];
-    if (!self_zero) cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
-    launch_ss_step_bwd<DIM>(g, L + (k - 1) * F, cur, nxt, cur != g_off, st);
-    cur = nxt;
+  if (ss) {
+    // THREE targets in rotation, zeroed by memsets on a side stream: launch j reads B[(j-1)%3] and scatters into
+    // B[j%3]; once it has run, its input is dead and is zeroed BESIDE launch j+1 for launch j+2.  The adjoint
+    // kernels sit at ~30 % of the DRAM bandwidth (they are bound by L1<->L2 requests), so the 32 MB memset hides
+    // behind them; zeroing inside the kernel costs 4.7 us of every launch (ss_step_bwd_lean<.., true> vs
+    // <.., false>: 44.3 vs 39.6 us at 128^3).  Forks and joins are events: capturable, nothing is synchronised.
+    T* B[3] = {g_off + F, g_off + 2 * F, g_off + 3 * F};
+    cudaEvent_t pending[3] = {nullptr, nullptr, nullptr};
+    cudaMemsetAsync(B[0], 0, sizeof(T) * F * 2, st);
+    pending[2] = ss->zero_beside(st, B[2], sizeof(T) * F);           // (also orders it after the smoothing's scratch use)
+    for (int j = 0; j < nb; ++j) {
+      const int k = nb - j;
+      T* nxt = B[j % 3];
+      if (pending[j % 3]) { cudaStreamWaitEvent(st, pending[j % 3], 0); pending[j % 3] = nullptr; }
+      launch_ss_step_bwd<DIM>(g, L + (k - 1) * F, cur, nxt, false, st);
+      if (j >= 1 && j + 2 < nb) pending[(j - 1) % 3] = ss->zero_beside(st, B[(j - 1) % 3], sizeof(T) * F);
+      cur = nxt;
+    }
+    for (int i = 0; i < 3; ++i)
+      if (pending[i]) cudaStreamWaitEvent(st, pending[i], 0);       // every side-stream branch joins before we return
+  } else {
+    // two targets: zeroed by the lean kernel itself (the buffer it consumed) or, plain kernels, by memset nodes
+    if (self_zero) cudaMemsetAsync(buf[0], 0, sizeof(T) * F * (nb > 1 ? 2 : 1), st);
+    for (int k = nb; k >= 1; --k) {
+      T* nxt = buf[(nb - k) & 1];
+      if (!self_zero) cudaMemsetAsync(nxt, 0, sizeof(T) * F, st);
+      launch_ss_step_bwd<DIM>(g, L + (k - 1) * F, cur, nxt, cur != g_off, st);
+      cur = nxt;
+    }
   }
   const T* curS = cur;
   const T* curJ = nullptr;
@@ -1036,7 +1101,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 3;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 7;
   return prev;
 }
 

@@ -31,11 +31,12 @@ constexpr int FT_TILE_BYTES = FT_BW * FT_BH * 16;   // 15744 = 123 * 128
 constexpr int FT_TMP_LD = FT_TX + 4;           // 36 floats: row stride of the planar x-pass result (4 banks mod 32)
 constexpr int FT_TMP_FLOATS = 3 * FT_BH * FT_TMP_LD;
 static_assert(FT_TILE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+static_assert(KT % 3 == 0, "the plane loop is unrolled by KT: stage = u % 3 must be static");
 
 template <int MODE> struct FtCfg {
   static constexpr int NT = 1;                 // tiles per stage
   static constexpr int NS = 3;                 // stages in flight
-  static constexpr int SMEM = NS * NT * FT_TILE_BYTES + 2 * FT_TMP_FLOATS * 4 + NS * 8;
+  static constexpr int SMEM = NS * NT * FT_TILE_BYTES + NS * FT_TMP_FLOATS * 4 + NS * 8;
 };
 
 struct FtArgs {
@@ -69,15 +70,19 @@ __device__ __forceinline__ void ft_tma_load(unsigned dst, const CUtensorMap* map
       ::"r"(dst), "l"((unsigned long long)map), "r"(0), "r"(x), "r"(y), "r"(z), "r"(n), "r"(bar) : "memory");
 }
 
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(FT_THREADS, MINB)
+// PPT = output rows per thread: 2 -> 256 threads (8 warps), 1 -> 512 threads (16 warps; half the accumulator
+// registers per thread, twice the warps per SM to hide the shared-memory and FMA latencies)
+template <int MODE, int PPT>
+__global__ void __launch_bounds__(FT_THREADS * 2 / PPT, 2)
 smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ FtArgs q) {
   constexpr int NT = FtCfg<MODE>::NT, NS = FtCfg<MODE>::NS;
+  constexpr int XO = 2 * PPT;                   // consecutive outputs of one x-pass task
+  constexpr int XW = 6 * (2 / PPT);             // warps that carry x-pass tasks: 24 rows x (32 / XO) runs / 32
   extern __shared__ __align__(128) unsigned char ft_smem[];
   const float4* s_in = reinterpret_cast<const float4*>(ft_smem);                  // [NS][NT][BH][BW]
-  float* s_tmp = reinterpret_cast<float*>(ft_smem + NS * NT * FT_TILE_BYTES);     // [2][3][BH][TMP_LD]
-  const unsigned bar0 = ft_smem_u32(ft_smem + NS * NT * FT_TILE_BYTES + 2 * FT_TMP_FLOATS * 4);
+  float* s_tmp = reinterpret_cast<float*>(ft_smem + NS * NT * FT_TILE_BYTES);     // [NS][3][BH][TMP_LD]
+  const unsigned bar0 = ft_smem_u32(ft_smem + NS * NT * FT_TILE_BYTES + NS * FT_TMP_FLOATS * 4);
   const unsigned in0 = ft_smem_u32(ft_smem);
   const Dims& g = q.g;
   const int tid = threadIdx.x;
@@ -92,43 +97,49 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // plane i lives in stage i % NS; only planes inside the volume are loaded (and waited for)
-  auto issue = [&](int i) {
+  // plane i lives in stage i % NS.  Planes outside the volume are requested like the others: the whole box is
+  // out of bounds, TMA fills it with zeros without touching memory, and the stage / phase of a plane stays a
+  // pure function of i (static after unrolling the plane loop by KT = 3 * NS)
+  auto issue = [&](int i, int s) {
     const int zi = zb - KR + i;
-    if (zi < 0 || zi >= g.D) return;
-    const int s = i % NS;
     const unsigned bar = bar0 + 8 * s;
     ft_mbar_expect(bar, NT * FT_TILE_BYTES);
     ft_tma_load(in0 + (s * NT) * FT_TILE_BYTES, &mapA, x0 - KR, y0 - KR, zi, n, bar);
     if (NT == 2) ft_tma_load(in0 + (s * NT + 1) * FT_TILE_BYTES, &mapB, x0 - KR, y0 - KR, zi, n, bar);
   };
   if (tid == 0) {
-    for (int i = 0; i < NS && i < np; ++i) issue(i);
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+      if (i < np) issue(i, i);
   }
   float w[KT];
 #pragma unroll
   for (int k = 0; k < KT; ++k) w[k] = q.a.w[k];
-  // x-pass task of this thread (warps 0..5): row = 8 * (warp % 3) + (lane % 8), outputs 4 * run .. + 3
+  // x-pass task of this thread (warps 0 .. XW-1): row = 8 * (warp % 3) + (lane % 8), outputs XO * run .. + XO - 1
   const int wrp = tid >> 5, lane = tid & 31;
   const int xrow = 8 * (wrp % 3) + (lane & 7), xrun = (wrp / 3) * 4 + (lane >> 3);
-  // y/z-pass positions of this thread: column tx, rows 2 * yg and 2 * yg + 1
+  // y/z-pass positions of this thread: column tx, rows PPT * yg .. + PPT - 1
   const int tx = lane, yg = wrp;
-  float acc[2][3][KT];
+  float acc[PPT][3][KT];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < PPT; ++j)
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int m = 0; m < KT; ++m) acc[j][c][m] = 0.f;
-  unsigned phases = 0;
+  unsigned kpar = 0;          // parity of base / KT: stage s is on its (base / NS + u / NS)-th use
   const i64 HW = (i64)g.H * g.W;
-  const int gx = x0 + tx, gy0 = y0 + 2 * yg;
-  // output map, per-thread constants: base coordinates of the column / the two rows, border-clip bounds
+  const int gx = x0 + tx, gy0 = y0 + PPT * yg;
+  // output map, per-thread constants: base coordinates of the column / the rows, border-clip bounds
   const float bx = base_coord_s(gx, g.W, g.stW);
-  const float by[2] = {base_coord_s(gy0, g.H, g.stH), base_coord_s(gy0 + 1, g.H, g.stH)};
+  float by[PPT];
+  bool oky[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    by[j] = base_coord_s(gy0 + j, g.H, g.stH);
+    oky[j] = gx < g.W && gy0 + j < g.H;
+  }
   const float mxW = (float)(g.W - 1), mxH = (float)(g.H - 1), mxD = (float)(g.D - 1);
-  const bool okx = gx < g.W;
-  const bool oky[2] = {okx && gy0 < g.H, okx && gy0 + 1 < g.H};
   const i64 obase = (i64)n * g.S + (i64)gy0 * g.W + gx;
   for (int base = 0; base < np; base += KT) {
 #pragma unroll
@@ -137,76 +148,69 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (i >= np) break;
       const int zi = zb - KR + i;
       const bool live = zi >= 0 && zi < g.D;            // block-uniform
-      float t[2][3];
+      float t[PPT][3];
       // backward: the two fields of the output map are requested a whole plane of work ahead of their use
-      float4 pn[2], p0[2];
+      float4 pn[PPT], p0[PPT];
       if (MODE == 1 && i >= 2 * KR) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < PPT; ++j) {
           if (oky[j]) {
             const i64 idx = obase + (i64)(zi - KR) * HW + (i64)j * g.W;
             pn[j] = __ldg(q.a.C + idx); p0[j] = __ldg(q.a.D + idx);
           }
         }
       }
+      const int s = u % NS;             // == i % NS (base is a multiple of KT = 3 * NS): static after unrolling
+      ft_mbar_wait(bar0 + 8 * s, (kpar ^ (unsigned)(u / NS)) & 1u);
       if (live) {
-        const int s = i % NS;
-        ft_mbar_wait(bar0 + 8 * s, (phases >> s) & 1u);
-        phases ^= 1u << s;
-        float* tmp = s_tmp + (i & 1) * FT_TMP_FLOATS;
-        if (wrp < 6) {
-          const float4* rowA = s_in + ((s * NT) * FT_BH + xrow) * FT_BW + 4 * xrun;
-          float o[3][4];
+        float* tmp = s_tmp + s * FT_TMP_FLOATS;
+        if (wrp < XW) {
+          const float4* rowA = s_in + ((s * NT) * FT_BH + xrow) * FT_BW + XO * xrun;
+          float o[3][XO];
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[c][j] = 0.f;
+            for (int j = 0; j < XO; ++j) o[c][j] = 0.f;
 #pragma unroll
-          for (int e = 0; e < 12; ++e) {
+          for (int e = 0; e < XO + 2 * KR; ++e) {
             const float4 v = rowA[e];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < XO; ++j) {
               const int k = e - j;
               if (k >= 0 && k < KT) { o[0][j] += w[k] * v.x; o[1][j] += w[k] * v.y; o[2][j] += w[k] * v.z; }
             }
           }
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            *reinterpret_cast<float4*>(tmp + (c * FT_BH + xrow) * FT_TMP_LD + 4 * xrun) =
-                make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+          for (int c = 0; c < 3; ++c) {
+            float* d = tmp + (c * FT_BH + xrow) * FT_TMP_LD + XO * xrun;
+            if (XO == 4) *reinterpret_cast<float4*>(d) = make_float4(o[c][0], o[c][1], o[c][2], o[c][XO - 1]);
+            else *reinterpret_cast<float2*>(d) = make_float2(o[c][0], o[c][1]);
+          }
         }
-        __syncthreads();                  // x-pass result complete; stage s has been read by everybody
       }
-      // stage i % NS is free either way (a plane outside the volume never occupied it)
-      if (tid == 0 && i + NS < np) issue(i + NS);
+      __syncthreads();                    // x-pass result complete; stage s has been read (or skipped) by everybody
+      if (tid == 0 && i + NS < np) issue(i + NS, s);
       if (live) {
-        const float* tmp = s_tmp + (i & 1) * FT_TMP_FLOATS;
+        const float* tmp = s_tmp + s * FT_TMP_FLOATS;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float in[10];
+          float in[PPT + 2 * KR];
 #pragma unroll
-          for (int e = 0; e < 10; ++e) in[e] = tmp[(c * FT_BH + 2 * yg + e) * FT_TMP_LD + tx];
+          for (int e = 0; e < PPT + 2 * KR; ++e) in[e] = tmp[(c * FT_BH + PPT * yg + e) * FT_TMP_LD + tx];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < PPT; ++j) {
             float sacc = 0.f;
 #pragma unroll
             for (int k = 0; k < KT; ++k) sacc += w[k] * in[j + k];
             t[j][c] = sacc;
           }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) t[j][c] = 0.f;
-      }
-      // z pass: plane zi is tap k of output plane zi + KR - k; ring slot of output plane zo is (zo - zb + KR) % KT
-      // ... written with the slot of output (zi - KR + m) = (u + m) % KT, static after unrolling
-      if (live) {
+        // z pass: plane zi is tap KT-1-m of output plane zi - KR + m, whose ring slot (u + m) % KT is static after
+        // unrolling
 #pragma unroll
         for (int m = 0; m < KT; ++m) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < PPT; ++j)
 #pragma unroll
             for (int c = 0; c < 3; ++c) acc[j][c][(u + m) % KT] += w[KT - 1 - m] * t[j][c];
         }
@@ -215,7 +219,7 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int zo = zi - KR;
         const float bz = base_coord_s(zo, g.D, g.stD);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < PPT; ++j) {
           if (!oky[j]) continue;
           const i64 idx = obase + (i64)zo * HW + (i64)j * g.W;
           const float s0 = acc[j][0][u], s1 = acc[j][1][u], s2 = acc[j][2][u];
@@ -233,10 +237,11 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < PPT; ++j)
 #pragma unroll
         for (int c = 0; c < 3; ++c) acc[j][c][u] = 0.f;      // slot u now collects output plane zi + KR + 1
     }
+    kpar ^= 1u;                           // KT / NS = 3 uses of every stage per block of KT planes: odd
   }
 }
 
@@ -292,15 +297,14 @@ static int ft_sms() {
 template <int MODE>
 static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA, const void* inB, const void* C,
                               const void* D, void* out, cudaStream_t st) {
-  // resident CTAs per SM the kernel is compiled for: 2 (112-119 registers) or 3 (80 registers, ~10 of them
-  // spilled); ADVK_FT_MINB selects (A/B)
-  static int ready = -1, minb = 2;
+  // rows per thread: 1 (512 threads, 32 warps per SM) or 2 (256 threads, 16 warps per SM); ADVK_FT_PPT selects
+  static int ready = -1, ppt = 1;
   if (ready < 0) {
-    const char* e = getenv("ADVK_FT_MINB");
-    minb = (e && atoi(e) == 3) ? 3 : 2;
-    ready = (cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const char* e = getenv("ADVK_FT_PPT");
+    ppt = (e && atoi(e) == 2) ? 2 : 1;
+    ready = (cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   FtCfg<MODE>::SMEM) == cudaSuccess &&
-             cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+             cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   FtCfg<MODE>::SMEM) == cudaSuccess) ? 1 : 0;
   }
   if (!ready) { (void)cudaGetLastError(); return false; }
@@ -315,7 +319,7 @@ static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA,
   const int tx = (g.W + FT_TX - 1) / FT_TX, ty = (g.H + FT_TY - 1) / FT_TY;
   // z runs: as many CTAs as fit the machine at once, never shorter than 8 planes (halo = 8)
   const i64 tiles = (i64)tx * ty * g.N;
-  i64 chunks = ((i64)minb * ft_sms()) / tiles;
+  i64 chunks = (2LL * ft_sms()) / tiles;
   if (chunks < 1) chunks = 1;
   int zc = (int)((g.D + chunks - 1) / chunks);
   if (zc < 8) zc = 8;
@@ -323,12 +327,12 @@ static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA,
   q.zc = zc; q.nzc = (g.D + zc - 1) / zc;
   if ((i64)g.N * q.nzc > 65535) return false;
   dim3 grid(tx, ty, (unsigned)(g.N * q.nzc));
-  if (minb == 3)
-    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
-                (smooth3d_tma_kernel<MODE, 3><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
-  else
+  if (ppt == 2)
     ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
                 (smooth3d_tma_kernel<MODE, 2><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+  else
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
+                (smooth3d_tma_kernel<MODE, 1><<<grid, 2 * FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
   return true;
 }
 

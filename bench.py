@@ -485,6 +485,8 @@ def run_b200(args):
     free_evt = [torch.cuda.Event(), torch.cuda.Event()]
     host_loss2 = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
     loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_dev = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
+    down_stream = torch.cuda.Stream()          # the loss goes down on its own stream: the next step does not queue behind the copy
     e2e_state = {"i": 0, "losses": 0}
 
     def upload(i):
@@ -506,9 +508,12 @@ def run_b200(args):
         upload(i + 1)                                      # next step's volume, overlapped with this step
         sol.optimizing_transform(model=model, data=dbuf[b], init_output=init_out, optimize_flags=flags,
                                  n_iter=1, step_sizes=steps_sz)
+        loss_dev[b].copy_(sol.last_dist.reshape(1))        # (the solver's own scalar is overwritten by the next step)
         free_evt[b].record(cur)
-        host_loss2[b].copy_(sol.last_dist.reshape(1), non_blocking=True)
-        loss_evt[b].record(cur)
+        with torch.cuda.stream(down_stream):
+            down_stream.wait_event(free_evt[b])
+            host_loss2[b].copy_(loss_dev[b], non_blocking=True)
+            loss_evt[b].record(down_stream)
         if i > 0:                                          # read the previous step's loss on the host
             loss_evt[b ^ 1].synchronize()
             e2e_state["losses"] += 1 if float(host_loss2[b ^ 1][0]) == float(host_loss2[b ^ 1][0]) else 0

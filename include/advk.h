@@ -166,6 +166,9 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  *          Default: ONE launch per direction, plane tiles staged by TMA (cp.async.bulk.tensor, out-of-bounds
  *          zero fill = the convolution's zero padding) on an mbarrier ring; forward, the last squaring step
  *          writes the Gaussian's input itself.
+ *   bit 2: the lean adjoint zeroes the scatter target it consumed itself (two targets).  Default: three targets
+ *          in rotation, zeroed by memsets on a library-owned side stream beside the next launch (event fork /
+ *          join: capturable, no host synchronisation).
  * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
  * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);

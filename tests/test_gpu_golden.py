@@ -200,6 +200,53 @@ def test_anatomy_preserving_branch_matches_reference():
         assert float((p1 - p0).norm() / p0.norm()) < tol, t.get_name()
 
 
+def test_anatomy_branch_runs_as_graph_replays():
+    """The anatomy-preserving branch inside the CUDA-graph loop (adv_compose_solver.py:329-338 captured in the
+    iteration, the retry state machine :376-400 around the replays): same loss and parameters as the eager
+    loop; a negative tolerance forces the retries (n_iter + 1 ... up to 3 x n_iter iterations, re-initialisation at
+    2 x n_iter), every one of them a replay."""
+    dev = torch.device("cuda:0")
+    meta, z = load_golden("c2d_anatomy")
+    case = meta["case"]
+    model = make_model(case, z, dev)
+    data, init_out = z["data"].to(dev), z["init_output"].to(dev)
+    amask = z["anatomy_mask"].to(dev)
+    res = []
+    for graph in (False, True):
+        sol = cuda_solver(case, dev)
+        sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0
+        chain = sol.chain_of_transforms
+        for i, t in enumerate(chain):
+            t.init_parameters()
+            t.param = z["p0_%d" % i].to(dev)
+        sol.optimizing_transform(model=model, data=data, init_output=init_out, optimize_flags=[True] * len(chain),
+                                 n_iter=case["n_iter"], step_sizes=meta["steps"], anatomy_mask_images=amask,
+                                 anatomy_reg_weight=50, volume_preserve_tolerance=1.0)
+        if graph:
+            assert getattr(sol, "graph_replays", 0) == case["n_iter"], getattr(sol, "graph_replays", 0)
+        res.append(([t.param.detach().clone() for t in chain], float(sol.last_dist)))
+    assert abs(res[0][1] - res[1][1]) <= 2e-2 * abs(res[0][1]) + 0.11      # a few voxels of the thresholded mask may flip
+    for a, b, t in zip(res[0][0], res[1][0], cuda_solver(case, dev).chain_of_transforms):
+        tol = 1e-3 if t.get_name() != "affine" else 0.25
+        assert rel_err(b, a) < tol, (t.get_name(), rel_err(b, a))
+    # negative tolerance: the score never passes, the loop retries (:383-400) -- all iterations are replays
+    sol = cuda_solver(case, dev)
+    sol.use_cuda_graph = True
+    sol.graph_capture_after = 0
+    chain = sol.chain_of_transforms
+    for i, t in enumerate(chain):
+        t.init_parameters()
+        t.param = z["p0_%d" % i].to(dev)
+    torch.manual_seed(3)
+    out = sol.optimizing_transform(model=model, data=data, init_output=init_out, optimize_flags=[True] * len(chain),
+                                   n_iter=2, step_sizes=meta["steps"], anatomy_mask_images=amask,
+                                   anatomy_reg_weight=50, volume_preserve_tolerance=-1.0)
+    assert len(out) >= len(chain)
+    assert getattr(sol, "graph_replays", 0) >= 2 * 3, getattr(sol, "graph_replays", 0)
+    assert all(torch.isfinite(t.param).all() for t in chain)
+
+
 def test_graph_loop_follows_the_3d_step_count():
     """adv_morph.py:159-162: in 3-D the number of squaring steps follows the norm of the velocity field,
     which grows during the PGD loop.  The graph loop reads that norm between replays and replays the graph
