@@ -297,11 +297,12 @@ static int ft_sms() {
 template <int MODE>
 static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA, const void* inB, const void* C,
                               const void* D, void* out, cudaStream_t st) {
-  // rows per thread: 1 (512 threads, 32 warps per SM) or 2 (256 threads, 16 warps per SM); ADVK_FT_PPT selects
-  static int ready = -1, ppt = 1;
+  // rows per thread: 2 (256 threads, 16 warps per SM; default) or 1 (512 threads, 32 warps per SM: 56 % more
+  // instructions per voxel, measured slower: 39.9 / 53.8 vs 32.7 / 40.1 us, gpurun_out/r02o); ADVK_FT_PPT selects
+  static int ready = -1, ppt = 2;
   if (ready < 0) {
     const char* e = getenv("ADVK_FT_PPT");
-    ppt = (e && atoi(e) == 2) ? 2 : 1;
+    ppt = (e && atoi(e) == 1) ? 1 : 2;
     ready = (cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   FtCfg<MODE>::SMEM) == cudaSuccess &&
              cudaFuncSetAttribute(smooth3d_tma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
