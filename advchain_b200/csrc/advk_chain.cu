@@ -60,6 +60,7 @@ struct Program {
   i64 n_tiles;
   int lean;         // runs the specialised per-stage kernels (advk_chain_lean.cuh)
   const float* user_src; float* src_packed;   // lean + pack: the chain input and its packed copy (stash)
+  float* g_coord;   // adjoint, lean: per-voxel coordinate gradient of an affine stage (tail of `scratch`)
   Stage st[MAX_STAGES];
 };
 
@@ -850,6 +851,7 @@ static bool build_program(const advk_chain_desc* d, Program& P, const float* src
     }
   }
   P.user_src = src;
+  P.g_coord = nullptr;
   P.src_packed = (P.pack && stash) ? cursor : nullptr;
   P.lean = lean_eligible(P) ? 1 : 0;
   if (P.lean && P.C == 1 && !P.pack) {
@@ -1014,6 +1016,30 @@ static int lean_minb(bool field, bool pack) {
   return pack ? 0 : (field ? 4 : 3);
 }
 
+// The theta gradient of an affine stage.  Split: the adjoint kernel writes dL/d(coordinate) per voxel into the tail
+// of `scratch` and lean_theta_reduce_kernel sums it; in-kernel: the adjoint kernel carries the d(d+1) accumulators
+// itself.  Measured at 128^3 (live CUDA events per iteration, gpurun_out/r02r): channel-packed K = 4 chain adjoint
+// 214.9 -> 177.3 us with the split, C = 1 image chain adjoint 128.9 -> 135.4 us (its affine stage is bound by the
+// sectors a rotated line of scalar REDs touches, 6.5 M against 1.9 M for the field stage, not by registers).
+// ADVK_LEAN_THETA: 0 = never split, 1 = packed chains only (default), 2 = always.
+static int g_lean_theta = -1;
+static bool lean_theta_split(bool pack) {
+  if (g_lean_theta < 0) {
+    const char* e = getenv("ADVK_LEAN_THETA");
+    g_lean_theta = e ? atoi(e) : 1;
+  }
+  return g_lean_theta >= 2 || (g_lean_theta == 1 && pack);
+}
+static int g_lean_minb_aff = -2;
+static int lean_minb_affine(bool pack) {      // register budget of the split affine adjoints (ADVK_LEAN_MINB_AFFINE)
+  if (g_lean_minb_aff == -2) {
+    const char* e = getenv("ADVK_LEAN_MINB_AFFINE");
+    g_lean_minb_aff = e ? atoi(e) : -1;
+  }
+  if (g_lean_minb_aff >= 0) return g_lean_minb_aff;
+  return pack ? 3 : 4;        // 80 / 62 registers, no spill (unconstrained: 124 / 73)
+}
+
 template <int DIM, bool FIELD>
 static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaStream_t st) {
   const bool last = (k == P.n - 1);
@@ -1022,26 +1048,43 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
   a.src = s.src; a.g_dst = s.g_dst; a.g_src = s.g_src; a.phi = s.phi; a.theta = s.theta;
   a.g_phi = s.g_phi; a.g_theta = s.g_theta;
   a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
-  // the theta gradient is reduced per block: a block walks several tiles so that the per-sample atomics stay few
   unsigned grid = (unsigned)P.n_tiles;
-  if (!FIELD && s.g_theta) { const unsigned cap = (unsigned)lean_sms() * 16u; if (grid > cap) grid = cap; }
-  const int minb = lean_minb(FIELD, P.pack != 0);
-#define ADVK_LB(KID, KERN, B1, B2)                                                                       \
+  const bool split = !FIELD && s.g_theta && P.g_coord && lean_theta_split(P.pack != 0);
+  if (split) { a.g_phi = P.g_coord; a.g_theta = nullptr; }
+  // in-kernel theta reduction (predecessor): a block walks several tiles so that the per-sample atomics stay few
+  else if (!FIELD && s.g_theta) { const unsigned cap = (unsigned)lean_sms() * 16u; if (grid > cap) grid = cap; }
+  const int minb = split ? lean_minb_affine(P.pack != 0) : lean_minb(FIELD, P.pack != 0);
+  constexpr bool TA = !FIELD;                 // only affine stages have an in-kernel-accumulating variant
+#define ADVK_LB1(KID, KERN, B1, ACC)                                                                     \
   do {                                                                                                   \
-    if (minb >= 4) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 4><<<grid, 256, 0, st>>>(a)));             \
-    else if (minb == 3) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 3><<<grid, 256, 0, st>>>(a)));        \
-    else if (minb == 2) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 2><<<grid, 256, 0, st>>>(a)));        \
-    else ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 0><<<grid, 256, 0, st>>>(a)));                       \
+    if (minb >= 4) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 4, ACC><<<grid, 256, 0, st>>>(a)));        \
+    else if (minb == 3) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 3, ACC><<<grid, 256, 0, st>>>(a)));   \
+    else if (minb == 2) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 2, ACC><<<grid, 256, 0, st>>>(a)));   \
+    else ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 0, ACC><<<grid, 256, 0, st>>>(a)));                  \
+  } while (0)
+#define ADVK_LB(KID, KERN, B1)                                                                           \
+  do {                                                                                                   \
+    if (TA && !split && s.g_theta) ADVK_LB1(KID, KERN, B1, TA);                                          \
+    else ADVK_LB1(KID, KERN, B1, false);                                                                 \
   } while (0)
   if (!P.pack) {
-    if (s.src_vm) ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, true, 0);
-    else ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, false, 0);
+    if (s.src_vm) ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, true);
+    else ADVK_LB(K_chain_img_bwd, lean_warp_bwd_kernel, false);
   } else {
     if (k == 0) a.src = P.src_packed;
-    if (!last) ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, true, 0);
-    else ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, false, 0);
+    if (!last) ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, true);
+    else ADVK_LB(K_chain_pk_bwd, lean_warp_bwd_pk_kernel, false);
   }
 #undef ADVK_LB
+#undef ADVK_LB1
+  if (split) {
+    // ~4 CTAs per SM over the whole batch; every CTA ends in d(d+1) atomics on its sample's gradient
+    unsigned gx = (unsigned)((lean_sms() * 4 + P.g.N - 1) / P.g.N);
+    if (gx > (unsigned)P.tps) gx = (unsigned)P.tps;
+    if (gx < 1) gx = 1;
+    const KernelId kid = P.pack ? K_chain_pk_bwd : K_chain_img_bwd;
+    ADVK_LAUNCH(kid, st, (lean_theta_reduce_kernel<DIM><<<dim3(gx, (unsigned)P.g.N), 256, 0, st>>>(P.g, P.g_coord, s.g_theta)));
+  }
 }
 
 template <int DIM>
@@ -1128,7 +1171,11 @@ extern "C" int advk_chain_workspace_floats(const advk_chain_desc* d, size_t* sta
     *stash_floats = (size_t)((i64)(d->n_stages - 1) * ncs + ((d->want_mask && warps > 1) ? (i64)(warps - 1) * ns : 0) +
                              (may_pack ? ncs : 0));
   // one slot per stage boundary, plus one for the packed gradient of the chain input (packed mode)
-  if (scratch_floats) *scratch_floats = (size_t)((i64)d->n_stages * ncs);
+  // ... and, behind them, 4 floats per voxel for the coordinate gradient of an affine stage (lean kernels)
+  bool affine = false;
+  for (int k = 0; k < d->n_stages; ++k)
+    if (d->stages[k].kind == ADVK_STAGE_WARP_AFFINE) affine = true;
+  if (scratch_floats) *scratch_floats = (size_t)((i64)d->n_stages * ncs + (affine ? 4 * ns : 0));
   return ADVK_OK;
 }
 
@@ -1164,6 +1211,7 @@ extern "C" int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out
   if (first == P.n) return ADVK_OK;       // nothing requested
   P.first_bwd = first;
   if (first < P.n - 1 || (P.pack && g_src)) ADVK_REQUIRE(scratch != nullptr, "scratch is NULL");
+  P.g_coord = scratch ? scratch + (i64)P.n * slot : nullptr;   // behind the n stage slots (advk_chain_workspace_floats)
   for (int k = P.n - 1; k >= first; --k) {
     Stage& s = P.st[k];
     s.g_dst = (k == P.n - 1) ? g_out : scratch + (i64)k * slot;

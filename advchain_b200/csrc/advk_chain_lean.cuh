@@ -445,7 +445,7 @@ __device__ __forceinline__ int lean_key(const LGeo<DIM>& G, bool ok) {
   return ok ? ((G.a000 << 2) | (G.dyo ? 1 : 0) | (G.dzo ? 2 : 0)) : -1;
 }
 
-template <int DIM, bool FIELD, bool VM_SRC, int MINB>
+template <int DIM, bool FIELD, bool VM_SRC, int MINB, bool THACC = false>
 __global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
   typedef typename FieldT<DIM>::type T;
@@ -454,7 +454,7 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
   const unsigned FULL = 0xffffffffu;
   __shared__ float red[12 * 32];
   const int lane = threadIdx.x & 31;
-  const bool want_theta = !FIELD && a.g_theta != nullptr;
+  const bool want_theta = THACC && !FIELD && a.g_theta != nullptr;
   const bool scatter = a.g_src != nullptr;
   const int S = (int)a.g.S;
   float acc[NG];
@@ -531,8 +531,11 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
     ggx *= (float)(a.g.W - 1) / 2.f; ggy *= (float)(a.g.H - 1) / 2.f; ggz *= (float)(a.g.D - 1) / 2.f;
     if (FIELD) {
       if (a.g_phi) lean_store_gphi<DIM>(a.g_phi, nS + p, ggx, ggy, ggz, rx, ry, rz);
-    } else if (want_theta) {
-      lean_theta_acc<DIM>(acc, ggx, ggy, ggz, bx, by, bz);
+    } else if (THACC) {
+      if (want_theta) lean_theta_acc<DIM>(acc, ggx, ggy, ggz, bx, by, bz);
+    } else if (a.g_phi) {                        // affine stage: dL/d(coordinate) for lean_theta_reduce_kernel
+      if (DIM == 2) reinterpret_cast<float2*>(a.g_phi)[nS + p] = make_float2(ggx, ggy);
+      else reinterpret_cast<float4*>(a.g_phi)[nS + p] = make_float4(ggx, ggy, ggz, 0.f);
     }
   }
   if (want_theta && cur_n >= 0) lean_theta_flush<DIM>(acc, red, a.g_theta, cur_n);
@@ -540,7 +543,7 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
 
 // channel-packed adjoint: the stashed source and g_src (scatter target) are always packed;
 // GD_PK: layout of the upstream gradient (planar = the user's g_out at the last stage)
-template <int DIM, bool FIELD, bool GD_PK, int MINB>
+template <int DIM, bool FIELD, bool GD_PK, int MINB, bool THACC = false>
 __global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
   typedef typename FieldT<DIM>::type T;
@@ -549,7 +552,7 @@ lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
   const unsigned FULL = 0xffffffffu;
   __shared__ float red[12 * 32];
   const int lane = threadIdx.x & 31;
-  const bool want_theta = !FIELD && a.g_theta != nullptr;
+  const bool want_theta = THACC && !FIELD && a.g_theta != nullptr;
   const bool scatter = a.g_src != nullptr;
   const int S = (int)a.g.S;
   const int CG = a.C >> 2;
@@ -644,11 +647,46 @@ lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
     ggx *= (float)(a.g.W - 1) / 2.f; ggy *= (float)(a.g.H - 1) / 2.f; ggz *= (float)(a.g.D - 1) / 2.f;
     if (FIELD) {
       if (a.g_phi) lean_store_gphi<DIM>(a.g_phi, nS + p, ggx, ggy, ggz, rx, ry, rz);
-    } else if (want_theta) {
-      lean_theta_acc<DIM>(acc, ggx, ggy, ggz, bx, by, bz);
+    } else if (THACC) {
+      if (want_theta) lean_theta_acc<DIM>(acc, ggx, ggy, ggz, bx, by, bz);
+    } else if (a.g_phi) {                        // affine stage: dL/d(coordinate) for lean_theta_reduce_kernel
+      if (DIM == 2) reinterpret_cast<float2*>(a.g_phi)[nS + p] = make_float2(ggx, ggy);
+      else reinterpret_cast<float4*>(a.g_phi)[nS + p] = make_float4(ggx, ggy, ggz, 0.f);
     }
   }
   if (want_theta && cur_n >= 0) lean_theta_flush<DIM>(acc, red, a.g_theta, cur_n);
+}
+
+// theta gradient of an affine stage from the per-voxel coordinate gradient the adjoint kernel left in `gc`
+// (float2 / float4 per voxel): g_theta[n] += sum_p gc(p) (x) [base(p), 1]  (adv_affine.py:316-324 through
+// F.affine_grid's adjoint).  The adjoint kernels used to carry these d(d+1) accumulators themselves: 100
+// registers, two resident CTAs per SM and a block reduction behind every CTA made the affine adjoints twice as
+// slow as the field adjoints of the same stencil (125.7 vs 65.1 us packed, 91.3 vs 39.6 us C = 1 at 128^3,
+// gpurun_out/r02q); a streaming pass over 16 bytes per voxel costs less than the difference.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+lean_theta_reduce_kernel(Dims g, const void* __restrict__ gc, float* __restrict__ g_theta) {
+  constexpr int NG = DIM * (DIM + 1);
+  __shared__ float red[12 * 32];
+  const int n = blockIdx.y;
+  const int S = (int)g.S;
+  const i64 nS = (i64)n * g.S;
+  float acc[NG];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) acc[i] = 0.f;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < S; p += gridDim.x * 256) {
+    int x, y, z;
+    voxel_xyz(g, (unsigned)p, x, y, z);
+    const float bx = base_coord_s(x, g.W, g.stW, 0.f), by = base_coord_s(y, g.H, g.stH, 0.f);
+    if (DIM == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(gc) + nS + p);
+      lean_theta_acc<DIM>(acc, v.x, v.y, 0.f, bx, by, 0.f);
+    } else {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(gc) + nS + p);
+      lean_theta_acc<DIM>(acc, v.x, v.y, v.z, bx, by, base_coord_s(z, g.D, g.stD, 0.f));
+    }
+  }
+  lean_theta_flush<DIM>(acc, red, g_theta, n);
 }
 
 // planar [N*C][S] -> packed [N*CG][S] float4 (the chain input of the prediction path, once per pass)

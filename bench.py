@@ -349,22 +349,34 @@ def run_reference(args):
     return 0
 
 
-def time_reference_cuda(d, size, chain, dev, steps=5, warmup=2):
-    """The unmodified reference with device=cuda (PyTorch eager on the same GPU). -> ms per iteration or None."""
+def time_reference_cuda(d, size, chain, dev, steps=5, warmup=3):
+    """The unmodified reference with device=cuda (PyTorch eager on the same GPU). -> (ms per iteration, detail) or
+    (None, None).  Timed under both settings of torch.backends.cudnn.benchmark (the reference's Gaussian and the toy
+    model are cuDNN convolutions: PyTorch's default is False, this file sets True for the user model) and the
+    FASTER one is reported as the incumbent; one run measured 146 ms and another 1 356 ms per iteration with the
+    flag on (gpurun_out/r02f, r02q), so a single setting is not a fair baseline."""
     aug = load_reference()
     if aug is None:
-        return None
-    step = reference_stepper(aug, d, size, chain, dev)
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+        return None, None
+    saved = torch.backends.cudnn.benchmark
+    detail = {}
+    try:
+        for flag in (False, True):
+            torch.backends.cudnn.benchmark = flag
+            step = reference_stepper(aug, d, size, chain, dev)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            detail["cudnn_benchmark_%s" % flag] = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.benchmark = saved
+    return min(detail.values()), detail
 
 
 def run_reference_cuda(args):
@@ -379,7 +391,7 @@ def run_reference_cuda(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     steps = max(1, min(args.steps, 20))
-    ms = time_reference_cuda(d, size, chain, dev, steps=steps, warmup=max(1, min(args.warmup, 3)))
+    ms, detail = time_reference_cuda(d, size, chain, dev, steps=steps, warmup=max(1, min(args.warmup, 3)))
     if ms is None:
         print(json.dumps({"impl": "reference-cuda", "unavailable": "baseline/_ref (mirror of the reference package) "
                           "is not present; run __graft_entry__.build() where /root/reference exists"}))
@@ -388,7 +400,8 @@ def run_reference_cuda(args):
         "impl": "reference-cuda", "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": steps,
         "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, d, size, chain),
-        "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager"}))
+        "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager",
+        "ms_per_step_by_setting": detail}))
     return 0
 
 
@@ -706,13 +719,15 @@ def run_b200(args):
     if not args.no_cuda_baseline and world == 1:
         # the incumbent: the unmodified reference, device=cuda, PyTorch eager, same GPU, same run
         try:
-            ms_ref = time_reference_cuda(d, size, chain, dev, steps=5, warmup=2)
+            ms_ref, ref_detail = time_reference_cuda(d, size, chain, dev, steps=5, warmup=3)
         except Exception as exc:                              # pragma: no cover
-            ms_ref = None
+            ms_ref, ref_detail = None, None
             sys.stderr.write("bench.py: reference-on-CUDA leg failed: %s\n" % (exc,))
         line["cuda_eager_baseline"] = None if ms_ref is None else {
-            "value": 1e3 / ms_ref, "unit": UNIT, "ms_per_step": ms_ref, "steps": 5, "warmup": 2,
-            "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager, same GPU",
+            "value": 1e3 / ms_ref, "unit": UNIT, "ms_per_step": ms_ref, "steps": 5, "warmup": 3,
+            "ms_per_step_by_setting": ref_detail,
+            "kind": "unmodified reference (baseline/_ref), device=cuda, PyTorch eager, same GPU; the faster of "
+                    "torch.backends.cudnn.benchmark off / on",
             "speedup_resident": value * ms_ref / 1e3}
     else:
         line["cuda_eager_baseline"] = None

@@ -11,6 +11,8 @@ for v in "${VS[@]}"; do
   python - <<PY
 import json
 d = json.load(open("$O/${TAG}_ab_$i.json"))
+k = d["kernel_ms_per_step"]
+print("   ", {n: k.get(n) for n in ("chain_pk_bwd", "chain_img_bwd", "chain_pk_fwd", "chain_img_fwd", "smooth_fwd", "smooth_bwd", "loss_contour", "loss_contour_adj", "loss_softmax", "loss_grad")})
 print("[%s]" % "$v", "value %.1f it/s  %.4f ms | e2e %.1f | advk %.4f | regions %s | e2e regions %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["advk_ms_per_step"], d["ms_per_step_regions"], d["e2e"]["ms_per_step_regions"]))
 PY
   i=$((i+1))
