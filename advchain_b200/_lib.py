@@ -72,6 +72,8 @@ SIGNATURES = {
     "advk_launch_count": (C.c_ulonglong, [_I, _I]),
     "advk_prof_configure": (_I, [_I, _I]),
     "advk_prof_collect": (_I, [C.POINTER(_I), C.POINTER(_F), _I]),
+    "advk_prof_group_runs": (_I, [_I]),
+    "advk_prof_collect_runs": (_I, [C.POINTER(_I), C.POINTER(_F), C.POINTER(_I), _I]),
     "advk_affine_theta_fwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P]),
     "advk_affine_theta_bwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P, _P]),
     "advk_warp_affine_fwd": (_I, [_G, _I, _P, _P, _I, _I, _P, _P, _P]),
@@ -196,6 +198,25 @@ def prof_configure(kernel="all", capacity=8192):
     """Bracket launches of `kernel` ("all", None = off, or a kernel name) with CUDA events."""
     kid = -2 if kernel is None else (-1 if kernel == "all" else kernel_names().index(kernel))
     call("advk_prof_configure", kid, capacity)
+
+
+def prof_group_runs(enable):
+    """Bracket a run of back-to-back launches of the profiled kernel once (see include/advk.h). -> previous setting"""
+    return bool(load().advk_prof_group_runs(1 if enable else 0))
+
+
+def prof_collect_runs(capacity=8192):
+    """-> {kernel name: [(ms, launches covered), ...]} for the records since the last collect."""
+    lib = load()
+    ids, ms, cnt = (_I * capacity)(), (_F * capacity)(), (_I * capacity)()
+    n = lib.advk_prof_collect_runs(ids, ms, cnt, capacity)
+    if n < 0:
+        raise RuntimeError("advk_prof_collect_runs failed: %s" % lib.advk_last_error().decode())
+    names = kernel_names()
+    out = {}
+    for i in range(n):
+        out.setdefault(names[ids[i]], []).append((float(ms[i]), int(cnt[i])))
+    return out
 
 
 def prof_collect(capacity=8192):

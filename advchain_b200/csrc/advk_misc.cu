@@ -36,13 +36,28 @@ static int g_prof_kid = -2;           // -2 off, -1 all kernels, >=0 one kernel 
 static int g_prof_cap = 0, g_prof_used = 0;
 static cudaEvent_t* g_prof_ev = nullptr;   // 2 events per record
 static int* g_prof_ids = nullptr;
+static int* g_prof_cnt = nullptr;          // launches covered by a record (> 1 only when runs are grouped)
+// advk_prof_group_runs: a run of back-to-back launches of the profiled kernel on one stream (the 8 adjoint
+// squaring steps of a field build) is bracketed ONCE -- an event pair around every 40 us launch adds its own
+// 2-4 us to each record
+static int g_prof_group = 0, g_prof_open = -1;
+static cudaStream_t g_prof_open_st = nullptr;
 
 Prof::Prof(int kid, cudaStream_t s) : slot(-1), st(s) {
   if (kid >= 0 && kid < K_COUNT) ++g_launches[kid];
-  if (g_prof_kid == -2 || (g_prof_kid >= 0 && g_prof_kid != kid) || g_prof_used >= g_prof_cap) return;
+  if (g_prof_kid == -2) return;
+  if (g_prof_kid >= 0 && g_prof_kid != kid) { g_prof_open = -1; return; }     // another kernel ends the run
+  if (g_prof_group && g_prof_kid >= 0 && g_prof_open >= 0 && g_prof_open_st == s) {
+    slot = g_prof_open;                       // same run: keep its start event, move its end event
+    ++g_prof_cnt[slot];
+    return;
+  }
+  if (g_prof_used >= g_prof_cap) { g_prof_open = -1; return; }
   slot = g_prof_used++;
   g_prof_ids[slot] = kid;
+  g_prof_cnt[slot] = 1;
   cudaEventRecord(g_prof_ev[2 * slot], st);
+  if (g_prof_group && g_prof_kid >= 0) { g_prof_open = slot; g_prof_open_st = s; }
 }
 Prof::~Prof() {
   if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st);
@@ -167,22 +182,38 @@ extern "C" unsigned long long advk_launch_count(int kid, int reset) {
     }
   return t;
 }
+extern "C" int advk_prof_collect(int* kernel_ids, float* ms, int max_records);
 extern "C" int advk_prof_configure(int kid, int capacity) {
   ADVK_REQUIRE(kid >= -2 && kid < K_COUNT && capacity >= 0, "bad kernel id / capacity");
   for (int i = 0; i < 2 * g_prof_cap; ++i) cudaEventDestroy(g_prof_ev[i]);
-  delete[] g_prof_ev; delete[] g_prof_ids;
-  g_prof_ev = nullptr; g_prof_ids = nullptr; g_prof_cap = 0; g_prof_used = 0; g_prof_kid = -2;
+  delete[] g_prof_ev; delete[] g_prof_ids; delete[] g_prof_cnt;
+  g_prof_ev = nullptr; g_prof_ids = nullptr; g_prof_cnt = nullptr; g_prof_cap = 0; g_prof_used = 0; g_prof_kid = -2;
+  g_prof_open = -1;
   if (kid == -2 || capacity == 0) return ADVK_OK;
   g_prof_ev = new cudaEvent_t[2 * (size_t)capacity];
   g_prof_ids = new int[capacity];
+  g_prof_cnt = new int[capacity];
   for (int i = 0; i < 2 * capacity; ++i)
     if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return check_launch("prof_configure");
   g_prof_cap = capacity;
   g_prof_kid = kid;
   return ADVK_OK;
 }
+extern "C" int advk_prof_group_runs(int enable) {
+  const int prev = g_prof_group;
+  g_prof_group = enable ? 1 : 0;
+  g_prof_open = -1;
+  return prev;
+}
+extern "C" int advk_prof_collect_runs(int* kernel_ids, float* ms, int* launches, int max_records) {
+  int n = g_prof_used < max_records ? g_prof_used : max_records;
+  if (launches)
+    for (int i = 0; i < n; ++i) launches[i] = g_prof_cnt[i];
+  return advk_prof_collect(kernel_ids, ms, max_records);
+}
 extern "C" int advk_prof_collect(int* kernel_ids, float* ms, int max_records) {
   int n = g_prof_used < max_records ? g_prof_used : max_records;
+  g_prof_open = -1;
   for (int i = 0; i < n; ++i) {
     if (cudaEventSynchronize(g_prof_ev[2 * i + 1]) != cudaSuccess ||
         cudaEventElapsedTime(&ms[i], g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) != cudaSuccess) {

@@ -88,12 +88,16 @@ int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_byt
  *   (-1: every kernel, -2: off) with a pair of CUDA events recorded on the launching stream, up to
  *   `capacity` records.  advk_prof_collect synchronises on the recorded events, writes
  *   (kernel id, milliseconds) per record to the host arrays, resets the record list and returns
- *   the number of records (<0 on error). */
+ *   the number of records (<0 on error).  advk_prof_group_runs(1): when ONE kernel is profiled, a run of
+ *   back-to-back launches of it on one stream is bracketed by one event pair (returns the previous
+ *   setting); advk_prof_collect_runs additionally returns the launches each record covers. */
 int advk_kernel_count(void);
 const char* advk_kernel_name(int kid);
 unsigned long long advk_launch_count(int kid, int reset);
 int advk_prof_configure(int kid, int capacity);
 int advk_prof_collect(int* kernel_ids, float* ms, int max_records);  /* host ptrs */
+int advk_prof_group_runs(int enable);
+int advk_prof_collect_runs(int* kernel_ids, float* ms, int* launches, int max_records);  /* host ptrs */
 
 /* ---- AdvAffine: parameters -> matrices -------------------------------------------------
  * replaces gen_batch_affine_matrix (adv_affine.py:210-273: Hardtanh, cos/sin, stack, matmul)
