@@ -73,6 +73,7 @@ SIGNATURES = {
     "advk_prof_configure": (_I, [_I, _I]),
     "advk_prof_collect": (_I, [C.POINTER(_I), C.POINTER(_F), _I]),
     "advk_prof_group_runs": (_I, [_I]),
+    "advk_set_pdl": (_I, [_I]),
     "advk_prof_collect_runs": (_I, [C.POINTER(_I), C.POINTER(_F), C.POINTER(_I), _I]),
     "advk_affine_theta_fwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P]),
     "advk_affine_theta_bwd": (_I, [C.POINTER(AffineCfg), _P, _F, _I, _P, _P, _P, _P]),

@@ -44,6 +44,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 adjoint_hw_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out, int H, int W,
                   int Hl, int Wl, float sH, float sW) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   extern __shared__ float4 ahw_smem4[];
   T* colsum = reinterpret_cast<T*>(ahw_smem4);            // [8][W]
   const int j = blockIdx.x;
@@ -93,7 +94,7 @@ static bool launch_adjoint_hw(int kid, const T* a, const T* b, float vs, T* out,
   const size_t smem = sizeof(T) * 8 * (size_t)W;
   if (smem > 48 * 1024 || outer > 65535 || outer < 1) return false;
   dim3 grid((unsigned)Hl, (unsigned)outer);
-  ADVK_LAUNCH(kid, st, (adjoint_hw_kernel<T><<<grid, 256, smem, st>>>(a, b, vs, out, H, W, Hl, Wl, sH, sW)));
+  ADVK_LAUNCH(kid, st, (launch_pdl((adjoint_hw_kernel<T>), grid, 256, smem, st, a, b, vs, out, H, W, Hl, Wl, sH, sW)));
   return true;
 }
 

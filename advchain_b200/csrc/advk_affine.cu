@@ -69,6 +69,7 @@ __device__ __forceinline__ void build_theta(const AffineCfg& c, const float* p, 
 template <int DIM>
 __global__ void affine_theta_fwd_kernel(AffineCfg c, const float* __restrict__ param, float pscale,
                                         int N, float* __restrict__ theta, float* __restrict__ theta_inv) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   constexpr int NP = DIM == 2 ? 5 : 9;
   constexpr int NT = DIM * (DIM + 1);
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +92,7 @@ __global__ void affine_theta_bwd_kernel(AffineCfg c, const float* __restrict__ p
                                         int N, const float* __restrict__ g_theta,
                                         const float* __restrict__ g_theta_inv,
                                         float* __restrict__ g_param) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   constexpr int NP = DIM == 2 ? 5 : 9;
   constexpr int NT = DIM * (DIM + 1);
   constexpr int R = DIM + 1;
@@ -198,8 +200,8 @@ extern "C" int advk_affine_theta_fwd(const advk_affine_cfg* cfg, const float* pa
   ADVK_REQUIRE(param && theta && N >= 1, "null pointer / bad N");
   cudaStream_t st = (cudaStream_t)stream;
   int thr = 64, blk = (N + thr - 1) / thr;
-  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_fwd, st, affine_theta_fwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv));
-  else ADVK_LAUNCH(K_affine_theta_fwd, st, affine_theta_fwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, theta, theta_inv));
+  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_fwd, st, launch_pdl((affine_theta_fwd_kernel<2>), blk, thr, 0, st, c, param, pscale, N, theta, theta_inv));
+  else ADVK_LAUNCH(K_affine_theta_fwd, st, launch_pdl((affine_theta_fwd_kernel<3>), blk, thr, 0, st, c, param, pscale, N, theta, theta_inv));
   return check_launch("affine_theta_fwd");
 }
 
@@ -211,7 +213,7 @@ extern "C" int advk_affine_theta_bwd(const advk_affine_cfg* cfg, const float* pa
   ADVK_REQUIRE(param && g_param && N >= 1 && (g_theta || g_theta_inv), "null pointer / bad N");
   cudaStream_t st = (cudaStream_t)stream;
   int thr = 64, blk = (N + thr - 1) / thr;
-  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_bwd, st, affine_theta_bwd_kernel<2><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param));
-  else ADVK_LAUNCH(K_affine_theta_bwd, st, affine_theta_bwd_kernel<3><<<blk, thr, 0, st>>>(c, param, pscale, N, g_theta, g_theta_inv, g_param));
+  if (cfg->d == 2) ADVK_LAUNCH(K_affine_theta_bwd, st, launch_pdl((affine_theta_bwd_kernel<2>), blk, thr, 0, st, c, param, pscale, N, g_theta, g_theta_inv, g_param));
+  else ADVK_LAUNCH(K_affine_theta_bwd, st, launch_pdl((affine_theta_bwd_kernel<3>), blk, thr, 0, st, c, param, pscale, N, g_theta, g_theta_inv, g_param));
   return check_launch("affine_theta_bwd");
 }

@@ -946,7 +946,7 @@ static void lean_launch_warp_fwd(const Program& P, const Stage& s, int k, cudaSt
   const dim3 grid(blocks_for(P.g.S, 256), P.g.N);
   const int mm = s.mdst ? (s.msrc ? 2 : 1) : 0;
   if (!P.pack) {
-#define ADVK_LF(MM, VS, VD) ADVK_LAUNCH(K_chain_img_fwd, st, (lean_warp_fwd_kernel<DIM, FIELD, MM, VS, VD><<<grid, 256, 0, st>>>(a)))
+#define ADVK_LF(MM, VS, VD) ADVK_LAUNCH(K_chain_img_fwd, st, (launch_pdl((lean_warp_fwd_kernel<DIM, FIELD, MM, VS, VD>), grid, 256, 0, st, a)))
     if (s.src_vm && s.dst_vm) ADVK_LF(2, true, true);
     else if (s.src_vm) ADVK_LF(2, true, false);
     else if (s.dst_vm && mm == 2) ADVK_LF(2, false, true);
@@ -957,7 +957,7 @@ static void lean_launch_warp_fwd(const Program& P, const Stage& s, int k, cudaSt
 #undef ADVK_LF
   } else {
     if (k == 0) a.src = P.src_packed;            // the packed copy of the chain input
-#define ADVK_LF(MM, DP) ADVK_LAUNCH(K_chain_pk_fwd, st, (lean_warp_fwd_pk_kernel<DIM, FIELD, MM, DP><<<grid, 256, 0, st>>>(a)))
+#define ADVK_LF(MM, DP) ADVK_LAUNCH(K_chain_pk_fwd, st, (launch_pdl((lean_warp_fwd_pk_kernel<DIM, FIELD, MM, DP>), grid, 256, 0, st, a)))
 #define ADVK_LF2(DP) do { if (mm == 0) ADVK_LF(0, DP); else if (mm == 1) ADVK_LF(1, DP); else ADVK_LF(2, DP); } while (0)
     if (s.dst_pk) ADVK_LF2(true);
     else ADVK_LF2(false);
@@ -972,15 +972,15 @@ static int lean_fwd(Program& P, cudaStream_t st) {
   if (P.pack) {
     if (!P.src_packed) { set_error("chain_apply_fwd: stash is NULL"); return ADVK_ERR_ARG; }
     const dim3 gp(blocks_for(P.g.S, 256), (unsigned)(P.g.N * (P.C >> 2)));
-    ADVK_LAUNCH(K_chain_pk_fwd, st, (lean_pack_kernel<<<gp, 256, 0, st>>>(P.user_src, reinterpret_cast<float4*>(P.src_packed), (int)P.g.S)));
+    ADVK_LAUNCH(K_chain_pk_fwd, st, (launch_pdl((lean_pack_kernel), gp, 256, 0, st, P.user_src, reinterpret_cast<float4*>(P.src_packed), (int)P.g.S)));
   }
   for (int k = 0; k < P.n; ++k) {
     const Stage& s = P.st[k];
     if (s.kind == ADVK_STAGE_INTENSITY) {
       LeanInt a;
       lean_fill_int(P, s, k == P.n - 1, a);
-      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_rows_kernel<DIM, false><<<lean_int_grid<DIM>(P), 256, 0, st>>>(a)));
-      else ADVK_LAUNCH(K_chain_img_fwd, st, (lean_intensity_kernel<DIM, false><<<grid, 256, 0, st>>>(a)));
+      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_fwd, st, (launch_pdl((lean_intensity_rows_kernel<DIM, false>), lean_int_grid<DIM>(P), 256, 0, st, a)));
+      else ADVK_LAUNCH(K_chain_img_fwd, st, (launch_pdl((lean_intensity_kernel<DIM, false>), grid, 256, 0, st, a)));
     } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_fwd<DIM, true>(P, s, k, st);
     else lean_launch_warp_fwd<DIM, false>(P, s, k, st);
   }
@@ -1057,10 +1057,10 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
   constexpr bool TA = !FIELD;                 // only affine stages have an in-kernel-accumulating variant
 #define ADVK_LB1(KID, KERN, B1, ACC)                                                                     \
   do {                                                                                                   \
-    if (minb >= 4) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 4, ACC><<<grid, 256, 0, st>>>(a)));        \
-    else if (minb == 3) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 3, ACC><<<grid, 256, 0, st>>>(a)));   \
-    else if (minb == 2) ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 2, ACC><<<grid, 256, 0, st>>>(a)));   \
-    else ADVK_LAUNCH(KID, st, (KERN<DIM, FIELD, B1, 0, ACC><<<grid, 256, 0, st>>>(a)));                  \
+    if (minb >= 4) ADVK_LAUNCH(KID, st, (launch_pdl((KERN<DIM, FIELD, B1, 4, ACC>), grid, 256, 0, st, a)));        \
+    else if (minb == 3) ADVK_LAUNCH(KID, st, (launch_pdl((KERN<DIM, FIELD, B1, 3, ACC>), grid, 256, 0, st, a)));   \
+    else if (minb == 2) ADVK_LAUNCH(KID, st, (launch_pdl((KERN<DIM, FIELD, B1, 2, ACC>), grid, 256, 0, st, a)));   \
+    else ADVK_LAUNCH(KID, st, (launch_pdl((KERN<DIM, FIELD, B1, 0, ACC>), grid, 256, 0, st, a)));                  \
   } while (0)
 #define ADVK_LB(KID, KERN, B1)                                                                           \
   do {                                                                                                   \
@@ -1083,7 +1083,7 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
     if (gx > (unsigned)P.tps) gx = (unsigned)P.tps;
     if (gx < 1) gx = 1;
     const KernelId kid = P.pack ? K_chain_pk_bwd : K_chain_img_bwd;
-    ADVK_LAUNCH(kid, st, (lean_theta_reduce_kernel<DIM><<<dim3(gx, (unsigned)P.g.N), 256, 0, st>>>(P.g, P.g_coord, s.g_theta)));
+    ADVK_LAUNCH(kid, st, (launch_pdl((lean_theta_reduce_kernel<DIM>), dim3(gx, (unsigned)P.g.N), 256, 0, st, P.g, P.g_coord, s.g_theta)));
   }
 }
 
@@ -1102,15 +1102,15 @@ static int lean_bwd(Program& P, cudaStream_t st) {
     if (s.kind == ADVK_STAGE_INTENSITY) {
       LeanInt a;
       lean_fill_int(P, s, last, a);
-      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_rows_kernel<DIM, true><<<lean_int_grid<DIM>(P), 256, 0, st>>>(a)));
-      else ADVK_LAUNCH(K_chain_img_bwd, st, (lean_intensity_kernel<DIM, true><<<grid, 256, 0, st>>>(a)));
+      if (lean_int_rows(P, s)) ADVK_LAUNCH(K_chain_img_bwd, st, (launch_pdl((lean_intensity_rows_kernel<DIM, true>), lean_int_grid<DIM>(P), 256, 0, st, a)));
+      else ADVK_LAUNCH(K_chain_img_bwd, st, (launch_pdl((lean_intensity_kernel<DIM, true>), grid, 256, 0, st, a)));
     } else if (s.kind == ADVK_STAGE_WARP_FIELD) lean_launch_warp_bwd<DIM, true>(P, s, k, st);
     else lean_launch_warp_bwd<DIM, false>(P, s, k, st);
   }
   const Stage& f = P.st[P.first_bwd];
   if (P.pack && f.g_src_user && f.g_src) {
     const dim3 gu(blocks_for(P.g.S, 256), (unsigned)(P.g.N * (P.C >> 2)));
-    ADVK_LAUNCH(K_chain_pk_bwd, st, (lean_unpack_kernel<<<gu, 256, 0, st>>>(reinterpret_cast<const float4*>(f.g_src), f.g_src_user, (int)P.g.S)));
+    ADVK_LAUNCH(K_chain_pk_bwd, st, (launch_pdl((lean_unpack_kernel), gu, 256, 0, st, reinterpret_cast<const float4*>(f.g_src), f.g_src_user, (int)P.g.S)));
   }
   return check_launch("chain_apply_bwd (lean)");
 }

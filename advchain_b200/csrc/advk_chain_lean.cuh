@@ -142,6 +142,7 @@ __device__ __forceinline__ void lean_mask_out(const LeanFwd& a, const LGeo<DIM>&
 template <int DIM, bool FIELD, int MASKM, bool VM_SRC, bool VM_DST>
 __global__ void __launch_bounds__(256)
 lean_warp_fwd_kernel(const __grid_constant__ LeanFwd a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename FieldT<DIM>::type T;
   static_assert(!VM_SRC || MASKM == 2, "an interleaved source carries the mask to gather");
   static_assert(!VM_DST || MASKM != 0, "an interleaved destination needs a mask");
@@ -214,6 +215,7 @@ lean_warp_fwd_kernel(const __grid_constant__ LeanFwd a) {
 template <int DIM, bool FIELD, int MASKM, bool DST_PK>
 __global__ void __launch_bounds__(256)
 lean_warp_fwd_pk_kernel(const __grid_constant__ LeanFwd a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename FieldT<DIM>::type T;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= a.g.S) return;
@@ -261,6 +263,7 @@ struct LeanInt {
 template <int DIM, bool BWD>
 __global__ void __launch_bounds__(256)
 lean_intensity_kernel(const __grid_constant__ LeanInt a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= a.g.S) return;
   const int n = blockIdx.y;
@@ -305,6 +308,7 @@ constexpr int LIR_MAX = 128;
 template <int DIM, bool BWD>
 __global__ void __launch_bounds__(256)
 lean_intensity_rows_kernel(const __grid_constant__ LeanInt a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float rowbuf[8][LIR_MAX];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int z = (DIM == 3) ? blockIdx.z % a.g.D : 0;
@@ -448,6 +452,7 @@ __device__ __forceinline__ int lean_key(const LGeo<DIM>& G, bool ok) {
 template <int DIM, bool FIELD, bool VM_SRC, int MINB, bool THACC = false>
 __global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename FieldT<DIM>::type T;
   constexpr int NG = DIM * (DIM + 1);
   constexpr int NZ = DIM == 3 ? 2 : 1;
@@ -546,6 +551,7 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
 template <int DIM, bool FIELD, bool GD_PK, int MINB, bool THACC = false>
 __global__ void __launch_bounds__(256, MINB)
 lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename FieldT<DIM>::type T;
   constexpr int NG = DIM * (DIM + 1);
   constexpr int NZ = DIM == 3 ? 2 : 1;
@@ -666,6 +672,7 @@ lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
 template <int DIM>
 __global__ void __launch_bounds__(256)
 lean_theta_reduce_kernel(Dims g, const void* __restrict__ gc, float* __restrict__ g_theta) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   constexpr int NG = DIM * (DIM + 1);
   __shared__ float red[12 * 32];
   const int n = blockIdx.y;
@@ -692,6 +699,7 @@ lean_theta_reduce_kernel(Dims g, const void* __restrict__ gc, float* __restrict_
 // planar [N*C][S] -> packed [N*CG][S] float4 (the chain input of the prediction path, once per pass)
 __global__ void __launch_bounds__(256)
 lean_pack_kernel(const float* __restrict__ src, float4* __restrict__ dst, int S) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= S) return;
   const i64 gb = (i64)blockIdx.y * S;
@@ -702,6 +710,7 @@ lean_pack_kernel(const float* __restrict__ src, float4* __restrict__ dst, int S)
 // packed [N*CG][S] float4 -> planar [N*C][S]
 __global__ void __launch_bounds__(256)
 lean_unpack_kernel(const float4* __restrict__ src, float* __restrict__ dst, int S) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= S) return;
   const i64 gb = (i64)blockIdx.y * S;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/advk.h"
 
 namespace advk {
@@ -72,6 +73,44 @@ inline FastDiv make_fastdiv(unsigned d) {
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
   return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+).  One PGD iteration is a chain of ~75 dependent launches, most of them
+// 5-40 us long: with plain stream order every boundary costs the drain of the last wave plus the launch latency
+// of the next grid.  Every kernel of this library starts with
+//     pdl_wait();      griddepcontrol.wait: returns once the grids this one depends on have COMPLETED and their
+//                      memory is visible -- nothing of the predecessor is read or overwritten before it
+//     pdl_trigger();   griddepcontrol.launch_dependents: the next grid may be scheduled as soon as every CTA of
+//                      this one has started (its CTAs then sit in the slots the last wave leaves free, blocked in
+//                      their own pdl_wait, and run the moment this grid is done)
+// and is launched through launch_pdl with cudaLaunchAttributeProgrammaticStreamSerialization.  Both instructions
+// are no-ops in a grid launched without the attribute (advk_set_pdl(0) / ADVK_PDL=0, cooperative launches, user
+// kernels in between).  A kernel launched by launch_pdl MUST call pdl_wait() before it touches global memory:
+// tests/test_host_logic.py checks that over the sources.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();     // advk_misc.cu
+void pdl_disable();     // a launch with the attribute was refused: plain launches from here on
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+  if (rc != cudaSuccess && cfg.numAttrs && (rc == cudaErrorNotSupported || rc == cudaErrorInvalidValue)) {
+    (void)cudaGetLastError();
+    pdl_disable();
+    cfg.numAttrs = 0;
+    rc = cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+  }
+  return rc;
 }
 #endif
 

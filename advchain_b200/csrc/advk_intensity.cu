@@ -16,6 +16,7 @@ namespace advk {
 template <int DIM>
 __global__ void lowfield_fwd_kernel(BiasCfg b, int N, const float* __restrict__ cp, float s,
                                     float* __restrict__ low) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   i64 L = (i64)b.lD * b.lH * b.lW;
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (i64)N * L) return;
@@ -39,6 +40,7 @@ __global__ void lowfield_fwd_kernel(BiasCfg b, int N, const float* __restrict__ 
 template <int DIM>
 __global__ void __launch_bounds__(256)
 lowfield_bwd_kernel(BiasCfg b, int N, const float* __restrict__ g_low, float s, float* __restrict__ g_cp) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[32];
   i64 ncp = (i64)b.nD * b.nH * b.nW;
   i64 L = (i64)b.lD * b.lH * b.lW;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(256)
 intensity_fwd_kernel(Dims g, int C, int order, const float* __restrict__ x, const float* __restrict__ delta,
                      float ns, const float* __restrict__ low, BiasCfg b, int use_ig, float ig,
                      float* __restrict__ out, float* __restrict__ bias_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
@@ -89,6 +92,7 @@ intensity_bwd_kernel(Dims g, int C, int order, const float* __restrict__ g_out, 
                      const float* __restrict__ delta, float ns, const float* __restrict__ low, BiasCfg b,
                      int use_ig, float ig, float* __restrict__ g_x, float* __restrict__ g_delta,
                      float* __restrict__ g_up) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
@@ -113,6 +117,7 @@ intensity_bwd_kernel(Dims g, int C, int order, const float* __restrict__ g_out, 
 __global__ void __launch_bounds__(256)
 adjoint_axis_f_kernel(const float* __restrict__ a, float* __restrict__ out, i64 outer, int n_in, int n_out,
                       i64 inner, float scale) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= outer * n_out * inner) return;
   i64 i = idx % inner;
@@ -143,8 +148,8 @@ extern "C" int advk_bias_lowfield_fwd(const advk_bias_cfg* cfg, int N, const flo
   ADVK_REQUIRE(cp && low && N >= 1, "null pointer");
   i64 tot = (i64)N * b.lD * b.lH * b.lW;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d == 2) ADVK_LAUNCH(K_lowfield_fwd, st, lowfield_fwd_kernel<2><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low));
-  else ADVK_LAUNCH(K_lowfield_fwd, st, lowfield_fwd_kernel<3><<<blocks_for(tot, 128), 128, 0, st>>>(b, N, cp, cp_scale, low));
+  if (d == 2) ADVK_LAUNCH(K_lowfield_fwd, st, launch_pdl((lowfield_fwd_kernel<2>), blocks_for(tot, 128), 128, 0, st, b, N, cp, cp_scale, low));
+  else ADVK_LAUNCH(K_lowfield_fwd, st, launch_pdl((lowfield_fwd_kernel<3>), blocks_for(tot, 128), 128, 0, st, b, N, cp, cp_scale, low));
   return check_launch("bias_lowfield_fwd");
 }
 
@@ -163,8 +168,8 @@ extern "C" int advk_bias_lowfield_bwd(const advk_bias_cfg* cfg, int N, const flo
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(g_cp, 0, sizeof(float) * blocks, st);
   dim3 grid(blocks, split);
-  if (d == 2) ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<2><<<grid, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
-  else ADVK_LAUNCH(K_lowfield_bwd, st, lowfield_bwd_kernel<3><<<grid, 256, 0, st>>>(b, N, g_low, cp_scale, g_cp));
+  if (d == 2) ADVK_LAUNCH(K_lowfield_bwd, st, launch_pdl((lowfield_bwd_kernel<2>), grid, 256, 0, st, b, N, g_low, cp_scale, g_cp));
+  else ADVK_LAUNCH(K_lowfield_bwd, st, launch_pdl((lowfield_bwd_kernel<3>), grid, 256, 0, st, b, N, g_low, cp_scale, g_cp));
   return check_launch("bias_lowfield_bwd");
 }
 
@@ -184,9 +189,9 @@ extern "C" int advk_intensity_fwd(const advk_geom* gg, int C, int order, const f
   dim3 grid(blocks_for(g.S, 256), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    ADVK_LAUNCH(K_intensity_fwd, st, intensity_fwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
+    ADVK_LAUNCH(K_intensity_fwd, st, launch_pdl((intensity_fwd_kernel<2>), grid, 256, 0, st, g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
   else
-    ADVK_LAUNCH(K_intensity_fwd, st, intensity_fwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
+    ADVK_LAUNCH(K_intensity_fwd, st, launch_pdl((intensity_fwd_kernel<3>), grid, 256, 0, st, g, C, order, x, delta, noise_scale, low, b, use_ignore, ignore_value, out, bias_out));
   return check_launch("intensity_fwd");
 }
 
@@ -206,9 +211,9 @@ extern "C" int advk_intensity_bwd(const advk_geom* gg, int C, int order, const f
   dim3 grid(blocks_for(g.S, 256), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (gg->d == 2)
-    ADVK_LAUNCH(K_intensity_bwd, st, intensity_bwd_kernel<2><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
+    ADVK_LAUNCH(K_intensity_bwd, st, launch_pdl((intensity_bwd_kernel<2>), grid, 256, 0, st, g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
   else
-    ADVK_LAUNCH(K_intensity_bwd, st, intensity_bwd_kernel<3><<<grid, 256, 0, st>>>(g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
+    ADVK_LAUNCH(K_intensity_bwd, st, launch_pdl((intensity_bwd_kernel<3>), grid, 256, 0, st, g, C, order, g_out, x, delta, noise_scale, low, b, use_ignore, ignore_value, g_x, g_delta, g_up));
   return check_launch("intensity_bwd");
 }
 
@@ -236,15 +241,15 @@ extern "C" int advk_bias_upsample_adjoint(const advk_geom* gg, const advk_bias_c
   float* s1 = scratch;
   if (gg->d == 3) {
     i64 tot = (i64)g.N * b.lD * g.H * g.W;
-    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot, 256), 256, 0, st>>>(a, s1, g.N, g.D, b.lD, (i64)g.H * g.W, b.sD));
+    ADVK_LAUNCH(K_adjoint_axis_f, st, launch_pdl((adjoint_axis_f_kernel), blocks_for(tot, 256), 256, 0, st, a, s1, g.N, g.D, b.lD, (i64)g.H * g.W, b.sD));
     a = s1; s1 += tot;
   }
   // the last two axes in one launch (advk_adjoint.cuh); per-axis kernels when a row does not fit shared memory
   if (!launch_adjoint_hw<float>(K_adjoint_axis_f, a, nullptr, 1.f, g_low, (i64)g.N * b.lD, g.H, g.W, b.lH, b.lW, b.sH, b.sW, st)) {
     i64 tot2 = (i64)g.N * b.lD * b.lH * g.W;
-    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot2, 256), 256, 0, st>>>(a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH));
+    ADVK_LAUNCH(K_adjoint_axis_f, st, launch_pdl((adjoint_axis_f_kernel), blocks_for(tot2, 256), 256, 0, st, a, s1, (i64)g.N * b.lD, g.H, b.lH, g.W, b.sH));
     i64 tot3 = (i64)g.N * b.lD * b.lH * b.lW;
-    ADVK_LAUNCH(K_adjoint_axis_f, st, adjoint_axis_f_kernel<<<blocks_for(tot3, 256), 256, 0, st>>>(s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW));
+    ADVK_LAUNCH(K_adjoint_axis_f, st, launch_pdl((adjoint_axis_f_kernel), blocks_for(tot3, 256), 256, 0, st, s1, g_low, (i64)g.N * b.lD * b.lH, g.W, b.lW, 1, b.sW));
   }
   return check_launch("bias_upsample_adjoint");
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256)
 loss_softmax_kernel(i64 S, int N, int Krt, const float* __restrict__ out, const float* __restrict__ ref,
                     const float* __restrict__ mask, int is_gt, int want_kl, float* __restrict__ E,
                     float* __restrict__ pred, double* __restrict__ acc) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[64];
   const int K = KC > 0 ? KC : Krt;
   constexpr int KA = KC > 0 ? KC : 1;
@@ -157,6 +158,7 @@ template <int DIM>
 __global__ void __launch_bounds__(LT_X * LT_Y)
 loss_contour_kernel(Dims g, int K, int nzc, const float* __restrict__ E, const float* __restrict__ mask,
                     float* __restrict__ R, double* __restrict__ acc) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float tile[2][LT_Y + 2][LT_X + 2];
   __shared__ float red[32];
   const int tx = threadIdx.x % LT_X, ty = threadIdx.x / LT_X;
@@ -219,6 +221,7 @@ loss_contour_kernel(Dims g, int K, int nzc, const float* __restrict__ E, const f
 template <int DIM>
 __global__ void __launch_bounds__(LT_X * LT_Y)
 loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float tile[2][2][LT_Y + 2][LT_X + 2];
   const int tx = threadIdx.x % LT_X, ty = threadIdx.x / LT_X;
   const int zc = blockIdx.z % nzc;
@@ -261,6 +264,7 @@ loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, flo
 
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont, float a_kl,
                                      float* __restrict__ loss) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   loss[0] = (float)((double)a_mse * acc[0] + (double)a_cont * acc[1] + (double)a_kl * acc[2]);
 }
 
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(256)
 loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __restrict__ pred,
                  const float* __restrict__ mask, float a_mse, float a_cont, float a_kl, int is_gt,
                  const float* __restrict__ upstream, float* __restrict__ g_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int K = KC > 0 ? KC : Krt;
   constexpr int KA = KC > 0 ? KC : 1;
   const int n = blockIdx.y;
@@ -373,7 +378,7 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
   dim3 grid(blocks_for(g.S, 256), g.N);
   const int wkl = w_kl != 0.f ? 1 : 0;
-#define ADVK_SOFTMAX(KC) ADVK_LAUNCH(K_loss_softmax, st, loss_softmax_kernel<KC><<<grid, 256, 0, st>>>(g.S, g.N, K, output, reference, mask, is_gt, wkl, E, pred, acc))
+#define ADVK_SOFTMAX(KC) ADVK_LAUNCH(K_loss_softmax, st, launch_pdl((loss_softmax_kernel<KC>), grid, 256, 0, st, g.S, g.N, K, output, reference, mask, is_gt, wkl, E, pred, acc))
   switch (K) {
     case 2: ADVK_SOFTMAX(2); break;
     case 3: ADVK_SOFTMAX(3); break;
@@ -386,10 +391,10 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   if (K > 1 && w_contour != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
-    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<2><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
-    else ADVK_LAUNCH(K_loss_contour, st, loss_contour_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, E, mask, R, acc));
+    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
+    else ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<3>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
   }
-  ADVK_LAUNCH(K_loss_finalize, st, loss_finalize_kernel<<<1, 1, 0, st>>>(acc, a_mse, a_cont, a_kl, loss));
+  ADVK_LAUNCH(K_loss_finalize, st, launch_pdl((loss_finalize_kernel), 1, 1, 0, st, acc, a_mse, a_cont, a_kl, loss));
   return check_launch("consistency_loss_fwd");
 }
 
@@ -411,11 +416,11 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   if (a_cont != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
-    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<2><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
-    else ADVK_LAUNCH(K_loss_contour_adj, st, loss_contour_adj_kernel<3><<<grid2, LT_X * LT_Y, 0, st>>>(g, K, nzc, R, g_output));
+    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour_adj, st, launch_pdl((loss_contour_adj_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, R, g_output));
+    else ADVK_LAUNCH(K_loss_contour_adj, st, launch_pdl((loss_contour_adj_kernel<3>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, R, g_output));
   }
   dim3 grid(blocks_for(g.S, 256), g.N);
-#define ADVK_LGRAD(KC) ADVK_LAUNCH(K_loss_grad, st, loss_grad_kernel<KC><<<grid, 256, 0, st>>>(g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output))
+#define ADVK_LGRAD(KC) ADVK_LAUNCH(K_loss_grad, st, launch_pdl((loss_grad_kernel<KC>), grid, 256, 0, st, g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output))
   switch (K) {
     case 2: ADVK_LGRAD(2); break;
     case 3: ADVK_LGRAD(3); break;

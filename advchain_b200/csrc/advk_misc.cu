@@ -66,6 +66,7 @@ Prof::~Prof() {
 // sum of squares per sample, accumulated in double across blocks
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, size_t per, double* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[32];
   const int n = blockIdx.y;
   const float* src = g + (size_t)n * per;
@@ -81,6 +82,7 @@ sumsq_kernel(const float* __restrict__ g, size_t per, double* __restrict__ out) 
 __global__ void __launch_bounds__(256)
 update_kernel(float* param, const float* grad, float step, int mode, size_t per,
               const double* __restrict__ ss, const float* __restrict__ guard) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   // NaN/Inf guard of the PGD loop (adv_compose_solver.py:345-346) evaluated on the device: a
   // non-finite loss leaves the parameters untouched, without a host round trip
   if (guard) {
@@ -110,6 +112,7 @@ update_kernel(float* param, const float* grad, float step, int mode, size_t per,
 __global__ void __launch_bounds__(256)
 small_update_kernel(float* param, const float* grad, float step, int mode, int per,
                     const float* __restrict__ guard) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[32];
   __shared__ float s_inv;
   if (guard) {
@@ -142,17 +145,20 @@ small_update_kernel(float* param, const float* grad, float step, int mode, int p
 }
 
 __global__ void clamp_kernel(const float* __restrict__ x, float lo, float hi, float* __restrict__ out, size_t n) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = fminf(fmaxf(x[i], lo), hi);
 }
 __global__ void clamp_bwd_kernel(const float* __restrict__ go, const float* __restrict__ x, float lo, float hi,
                                  float* __restrict__ gx, size_t n) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = x[i];
     gx[i] = (v >= lo && v <= hi) ? go[i] : 0.f;
   }
 }
 __global__ void nonzero_kernel(float* __restrict__ x, size_t n) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] = (x[i] != 0.f) ? 1.f : 0.f;
 }
@@ -172,6 +178,22 @@ extern "C" const char* advk_last_error(void) { return g_err; }
 extern "C" int advk_kernel_count(void) { return K_COUNT; }
 extern "C" const char* advk_kernel_name(int kid) {
   return g_kernel_names[(kid >= 0 && kid < K_COUNT) ? kid : K_COUNT];
+}
+static int g_pdl = -1;
+namespace advk {
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ADVK_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+void pdl_disable() { g_pdl = 0; }
+}  // namespace advk
+extern "C" int advk_set_pdl(int enable) {
+  const int prev = advk::pdl_enabled() ? 1 : 0;
+  g_pdl = enable ? 1 : 0;
+  return prev;
 }
 extern "C" unsigned long long advk_launch_count(int kid, int reset) {
   unsigned long long t = 0;
@@ -245,6 +267,7 @@ extern "C" int advk_device_info(int* sm_count, int* cc_major, int* cc_minor, siz
 // violation when the smallest n >= 8 with sqrt(norm2)/2^n <= 0.5 differs from `nb_steps`.
 __global__ void steps_check_kernel(const float* __restrict__ norm2, int nb_steps, int min_steps,
                                    int* __restrict__ violations) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   float nrm = sqrtf(norm2[0]);
   int n = min_steps;
   while (nrm / exp2f((float)n) > 0.5f && n < 64) ++n;
@@ -255,7 +278,7 @@ extern "C" int advk_morph_steps_check(const float* norm2, int nb_steps, int min_
                                       void* stream) {
   ADVK_REQUIRE(norm2 && violations, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  ADVK_LAUNCH(K_steps_check, st, steps_check_kernel<<<1, 1, 0, st>>>(norm2, nb_steps, min_steps, violations));
+  ADVK_LAUNCH(K_steps_check, st, launch_pdl((steps_check_kernel), 1, 1, 0, st, norm2, nb_steps, min_steps, violations));
   return check_launch("morph_steps_check");
 }
 
@@ -271,7 +294,7 @@ extern "C" int advk_pgd_update_guarded(float* param, const float* grad, float st
   ADVK_REQUIRE(mode >= 0 && mode <= 3, "bad mode");
   cudaStream_t st = (cudaStream_t)stream;
   if (per_sample <= 8192) {
-    ADVK_LAUNCH(K_update, st, small_update_kernel<<<N, 256, 0, st>>>(param, grad, step, mode, (int)per_sample, guard));
+    ADVK_LAUNCH(K_update, st, launch_pdl((small_update_kernel), N, 256, 0, st, param, grad, step, mode, (int)per_sample, guard));
     return check_launch("pgd_update");
   }
   size_t b = (per_sample + 255) / 256;
@@ -280,28 +303,28 @@ extern "C" int advk_pgd_update_guarded(float* param, const float* grad, float st
   if (mode == ADVK_UPD_L2_ASCENT || mode == ADVK_UPD_L2_POWER) {
     ADVK_REQUIRE(sumsq != nullptr, "sumsq scratch is NULL");
     cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
-    ADVK_LAUNCH(K_sumsq, st, sumsq_kernel<<<grid, 256, 0, st>>>(grad, per_sample, sumsq));
+    ADVK_LAUNCH(K_sumsq, st, launch_pdl((sumsq_kernel), grid, 256, 0, st, grad, per_sample, sumsq));
   }
-  ADVK_LAUNCH(K_update, st, update_kernel<<<grid, 256, 0, st>>>(param, grad, step, mode, per_sample, sumsq, guard));
+  ADVK_LAUNCH(K_update, st, launch_pdl((update_kernel), grid, 256, 0, st, param, grad, step, mode, per_sample, sumsq, guard));
   return check_launch("pgd_update");
 }
 
 extern "C" int advk_clamp(const float* x, float lo, float hi, float* out, size_t n, void* stream) {
   ADVK_REQUIRE(x && out, "null pointer");
   if (n == 0) return ADVK_OK;
-  ADVK_LAUNCH(K_clamp, (cudaStream_t)stream, clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, lo, hi, out, n));
+  ADVK_LAUNCH(K_clamp, (cudaStream_t)stream, launch_pdl((clamp_kernel), ew_blocks(n), 256, 0, (cudaStream_t)stream, x, lo, hi, out, n));
   return check_launch("clamp");
 }
 extern "C" int advk_clamp_bwd(const float* g_out, const float* x, float lo, float hi, float* g_x, size_t n,
                               void* stream) {
   ADVK_REQUIRE(x && g_out && g_x, "null pointer");
   if (n == 0) return ADVK_OK;
-  ADVK_LAUNCH(K_clamp_bwd, (cudaStream_t)stream, clamp_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(g_out, x, lo, hi, g_x, n));
+  ADVK_LAUNCH(K_clamp_bwd, (cudaStream_t)stream, launch_pdl((clamp_bwd_kernel), ew_blocks(n), 256, 0, (cudaStream_t)stream, g_out, x, lo, hi, g_x, n));
   return check_launch("clamp_bwd");
 }
 extern "C" int advk_nonzero_mask(float* x, size_t n, void* stream) {
   ADVK_REQUIRE(x != nullptr, "null pointer");
   if (n == 0) return ADVK_OK;
-  ADVK_LAUNCH(K_nonzero, (cudaStream_t)stream, nonzero_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, n));
+  ADVK_LAUNCH(K_nonzero, (cudaStream_t)stream, launch_pdl((nonzero_kernel), ew_blocks(n), 256, 0, (cudaStream_t)stream, x, n));
   return check_launch("nonzero_mask");
 }

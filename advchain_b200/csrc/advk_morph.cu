@@ -64,6 +64,7 @@ __device__ __forceinline__ P* opaque_ptr(P* p) {
 template <int DIM>
 __global__ void lowres_smooth_kernel(MorphCfg c, int NC, const float* __restrict__ in, float scale,
                                      float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (i64)NC * lr) return;
@@ -97,6 +98,7 @@ constexpr int LRS_MAX = 4096;
 template <int DIM>
 __global__ void __launch_bounds__(256)
 lowres_smooth_smem_kernel(MorphCfg c, const float* __restrict__ in, float scale, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float a[LRS_MAX];
   __shared__ float b[LRS_MAX];
   const int lr = c.Dl * c.Hl * c.Wl;
@@ -136,9 +138,9 @@ template <int DIM>
 static void launch_lowres_smooth(const MorphCfg& c, int NC, const float* in, float scale, float* out, cudaStream_t st) {
   i64 lr = (i64)c.Dl * c.Hl * c.Wl;
   if (lr <= LRS_MAX)
-    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_smem_kernel<DIM><<<NC, 256, 0, st>>>(c, in, scale, out));
+    ADVK_LAUNCH(K_lowres_smooth, st, launch_pdl((lowres_smooth_smem_kernel<DIM>), NC, 256, 0, st, c, in, scale, out));
   else
-    ADVK_LAUNCH(K_lowres_smooth, st, lowres_smooth_kernel<DIM><<<blocks_for(NC * lr, 128), 128, 0, st>>>(c, NC, in, scale, out));
+    ADVK_LAUNCH(K_lowres_smooth, st, launch_pdl((lowres_smooth_kernel<DIM>), blocks_for(NC * lr, 128), 128, 0, st, c, NC, in, scale, out));
 }
 
 // upsampled velocity at one voxel; u_lr planar [N][DIM][lr]
@@ -173,6 +175,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256)
 init_phi0_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n,
                  typename V<DIM>::T* __restrict__ phi0) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
@@ -188,6 +191,7 @@ init_phi0_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n
 template <int DIM>
 __global__ void __launch_bounds__(256)
 unorm2_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[32];
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,6 +217,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256)
 init_phi0_rows_kernel(MorphCfg c, Dims g, const float* __restrict__ u_lr, float inv2n,
                       typename V<DIM>::T* __restrict__ phi0, float* __restrict__ norm2) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float rowbuf[DIM][8][LRW_MAX];
   __shared__ float red[32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -267,11 +272,11 @@ static void launch_init_phi0(const MorphCfg& c, const Dims& g, const float* u_lr
   const i64 gz = (DIM == 3) ? (i64)g.N * g.D : g.N;
   if (c.Wl <= LRW_MAX && gz <= 65535) {
     dim3 grid(1, (g.H + 7) / 8, (unsigned)gz);
-    ADVK_LAUNCH(phi0 ? K_init_phi0 : K_unorm2, st, init_phi0_rows_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, (T*)phi0, norm2));
+    ADVK_LAUNCH(phi0 ? K_init_phi0 : K_unorm2, st, launch_pdl((init_phi0_rows_kernel<DIM>), grid, 256, 0, st, c, g, u_lr, inv2n, (T*)phi0, norm2));
   } else {
     dim3 grid(blocks_for(g.S, 256), g.N);
-    if (phi0) ADVK_LAUNCH(K_init_phi0, st, init_phi0_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, inv2n, (T*)phi0));
-    else ADVK_LAUNCH(K_unorm2, st, unorm2_kernel<DIM><<<grid, 256, 0, st>>>(c, g, u_lr, norm2));
+    if (phi0) ADVK_LAUNCH(K_init_phi0, st, launch_pdl((init_phi0_kernel<DIM>), grid, 256, 0, st, c, g, u_lr, inv2n, (T*)phi0));
+    else ADVK_LAUNCH(K_unorm2, st, launch_pdl((unorm2_kernel<DIM>), grid, 256, 0, st, c, g, u_lr, norm2));
   }
 }
 
@@ -290,6 +295,7 @@ __device__ __forceinline__ float compose_axis(float c, int size, float step, flo
 template <int DIM>
 __global__ void __launch_bounds__(256, 8)
 ss_step_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename V<DIM>::T T;
   const int n = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
@@ -338,6 +344,7 @@ template <int DIM, bool EMIT_R>
 __global__ void __launch_bounds__(256, 8)
 ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out,
                     const typename V<DIM>::T* __restrict__ phi0, typename V<DIM>::T* __restrict__ rout) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename V<DIM>::T T;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
   if (p >= g.S) return;
@@ -398,6 +405,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256)
 ss_step_bwd_plain_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, const typename V<DIM>::T* __restrict__ up,
                          typename V<DIM>::T* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename V<DIM>::T T;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;           // S < 2^31 (host-checked)
   if (p >= g.S) return;
@@ -452,6 +460,7 @@ template <int DIM, bool ZS>
 __global__ void __launch_bounds__(256)
 ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
                         typename V<DIM>::T* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   typedef typename V<DIM>::T T;
   constexpr int NZ = DIM == 3 ? 2 : 1;
   const unsigned FULL = 0xffffffffu;
@@ -613,9 +622,9 @@ template <int DIM>
 static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
                                typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
   dim3 grid(blocks_for(g.S, 256), g.N);
-  if (ssb_mode() & 1) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_plain_kernel<DIM><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-  else if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
-  else ADVK_LAUNCH(K_ss_step_bwd, st, (ss_step_bwd_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, phi_prev, up, out)));
+  if (ssb_mode() & 1) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_plain_kernel<DIM>), grid, 256, 0, st, g, phi_prev, up, out)));
+  else if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_lean_kernel<DIM, true>), grid, 256, 0, st, g, phi_prev, up, out)));
+  else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_lean_kernel<DIM, false>), grid, 256, 0, st, g, phi_prev, up, out)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -679,6 +688,7 @@ constexpr int S2_TX = 32, S2_TY = 16, S2_THREADS = 256;
 template <int MODE>
 __global__ void __launch_bounds__(S2_THREADS)
 smooth2d_kernel(Dims g, SmoothArgs<2> a) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float s_in[2][S2_TY + 2 * KR][S2_TX + 2 * KR];
   __shared__ float s_tmp[2][S2_TY + 2 * KR][S2_TX];
   const int n = blockIdx.z;
@@ -728,6 +738,7 @@ constexpr int SZ_CHUNK = 16;
 template <int MODE>
 __global__ void __launch_bounds__(SX_THREADS)
 smooth3d_xy_kernel(Dims g, SmoothArgs<3> a, float4* __restrict__ tmp) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ __align__(16) float s_in[3][SX_IH][SX_IW];
   __shared__ __align__(16) float s_tmp[3][SX_IH][SX_TX];
   const int z = blockIdx.z % g.D, n = blockIdx.z / g.D;
@@ -792,6 +803,7 @@ smooth3d_xy_kernel(Dims g, SmoothArgs<3> a, float4* __restrict__ tmp) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 smooth3d_z_kernel(Dims g, SmoothArgs<3> a, const float4* __restrict__ tmp, int nzc) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int n = blockIdx.z / nzc, zb = (blockIdx.z % nzc) * SZ_CHUNK;
   if (x >= g.W || y >= g.H) return;
@@ -830,14 +842,14 @@ static void launch_smooth(const Dims& g, const MorphCfg& c, const void* A, const
   for (int i = 0; i < KT; ++i) a.w[i] = c.w[i];
   if (DIM == 2) {
     dim3 grid((g.W + S2_TX - 1) / S2_TX, (g.H + S2_TY - 1) / S2_TY, g.N);
-    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth2d_kernel<MODE><<<grid, S2_THREADS, 0, st>>>(g, *reinterpret_cast<SmoothArgs<2>*>(&a)));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, launch_pdl((smooth2d_kernel<MODE>), grid, S2_THREADS, 0, st, g, *reinterpret_cast<SmoothArgs<2>*>(&a)));
   } else {
     SmoothArgs<3>& a3 = *reinterpret_cast<SmoothArgs<3>*>(&a);
     dim3 gxy((g.W + SX_TX - 1) / SX_TX, (g.H + SX_TY - 1) / SX_TY, (unsigned)(g.N * g.D));
-    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_xy_kernel<MODE><<<gxy, SX_THREADS, 0, st>>>(g, a3, (float4*)tmp));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, launch_pdl((smooth3d_xy_kernel<MODE>), gxy, SX_THREADS, 0, st, g, a3, (float4*)tmp));
     const int nzc = (g.D + SZ_CHUNK - 1) / SZ_CHUNK;
     dim3 gz((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)(g.N * nzc));
-    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, smooth3d_z_kernel<MODE><<<gz, 256, 0, st>>>(g, a3, (const float4*)tmp, nzc));
+    ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st, launch_pdl((smooth3d_z_kernel<MODE>), gz, 256, 0, st, g, a3, (const float4*)tmp, nzc));
   }
 }
 
@@ -871,6 +883,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 adjoint_axis_kernel(const T* __restrict__ a, const T* __restrict__ a2, const T* __restrict__ b, float vs,
                     T* __restrict__ out, i64 outer, int n_in, int n_out, i64 inner, float scale) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= outer * n_out * inner) return;
   i64 i = idx % inner;
@@ -913,6 +926,7 @@ __global__ void __launch_bounds__(256)
 adjoint_axis_big_kernel(const T* __restrict__ a, const T* __restrict__ b, float vs, T* __restrict__ out,
                         int n_in, int n_out, i64 inner, float scale, i64 sl_in, i64 sp_in, i64 so_in,
                         i64 sl_out, i64 sj_out, i64 so_out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   // lanes run over `inner` positions (stride sl_*), the axis has stride sp_in / sj_out, blockIdx.y strides
   // so_*: the same kernel serves [outer][axis][inner] (lanes = inner) and [outer][axis] (lanes = outer)
   extern __shared__ float4 adj_smem4[];
@@ -956,22 +970,23 @@ static void launch_adjoint_axis(const T* a, const T* a2, const T* b, float vs, T
   i64 tot = outer * n_out * inner;
   if (!a2 && inner >= 32 && n_out <= ADJ_NOUT_MAX && outer <= 65535) {
     dim3 grid((unsigned)((inner + 31) / 32), (unsigned)outer);
-    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(
+    ADVK_LAUNCH(K_adjoint_axis, st, launch_pdl((adjoint_axis_big_kernel<T>), grid, 256, sizeof(T) * 32 * n_out, st, 
         a, b, vs, out, n_in, n_out, inner, scale, 1, inner, (i64)n_in * inner, 1, inner, (i64)n_out * inner));
     return;
   }
   if (!a2 && inner == 1 && outer >= 32 && n_out <= ADJ_NOUT_MAX) {      // last axis: lanes over the rows
     dim3 grid((unsigned)((outer + 31) / 32), 1);
-    ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_big_kernel<T><<<grid, 256, sizeof(T) * 32 * n_out, st>>>(
+    ADVK_LAUNCH(K_adjoint_axis, st, launch_pdl((adjoint_axis_big_kernel<T>), grid, 256, sizeof(T) * 32 * n_out, st, 
         a, b, vs, out, n_in, n_out, outer, scale, n_in, 1, 0, n_out, 1, 0));
     return;
   }
-  ADVK_LAUNCH(K_adjoint_axis, st, adjoint_axis_kernel<T><<<blocks_for(tot, 256), 256, 0, st>>>(a, a2, b, vs, out, outer, n_in, n_out, inner, scale));
+  ADVK_LAUNCH(K_adjoint_axis, st, launch_pdl((adjoint_axis_kernel<T>), blocks_for(tot, 256), 256, 0, st, a, a2, b, vs, out, outer, n_in, n_out, inner, scale));
 }
 
 template <int DIM>
 __global__ void aos_to_planar_kernel(const typename V<DIM>::T* __restrict__ in, float* __restrict__ out,
                                      int N, i64 lr) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (i64)N * lr) return;
   i64 n = idx / lr, q = idx % lr;
@@ -1000,9 +1015,9 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   const bool fused = DIM == 3 && lean && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
   for (int k = 1; k <= nb; ++k) {
     if (lean && fused && k == nb)
-      ADVK_LAUNCH(K_ss_step, st, (ss_step_lean_kernel<DIM, true><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
-    else if (lean) ADVK_LAUNCH(K_ss_step, st, (ss_step_lean_kernel<DIM, false><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
-    else ADVK_LAUNCH(K_ss_step, st, ss_step_kernel<DIM><<<grid, 256, 0, st>>>(g, L + (k - 1) * F, L + k * F));
+      ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, true>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
+    else if (lean) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, false>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
+    else ADVK_LAUNCH(K_ss_step, st, launch_pdl((ss_step_kernel<DIM>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F));
   }
   if (!(fused && launch_smooth_tma<0>(g, c, L + (nb + 1) * F, nullptr, nullptr, nullptr, field_out, st)))
     launch_smooth<DIM, 0>(g, c, L + nb * F, L, nullptr, nullptr, field_out, L + (nb + 1) * F, st);
@@ -1089,7 +1104,7 @@ static int field_bwd(const Dims& g, const MorphCfg& c, float scale, int nb, cons
     launch_adjoint_axis<T>(s1, nullptr, nullptr, 1.f, s2, (i64)g.N * c.Dl * c.Hl, g.W, c.Wl, 1, c.sW, st);
   }
   float* planar = (float*)(s2 + (i64)g.N * lr);
-  ADVK_LAUNCH(K_aos_to_planar, st, aos_to_planar_kernel<DIM><<<blocks_for(g.N * lr, 128), 128, 0, st>>>(s2, planar, g.N, lr));
+  ADVK_LAUNCH(K_aos_to_planar, st, launch_pdl((aos_to_planar_kernel<DIM>), blocks_for(g.N * lr, 128), 128, 0, st, s2, planar, g.N, lr));
   int NC = g.N * DIM;
   launch_lowres_smooth<DIM>(c, NC, planar, scale, g_v, st);
   return check_launch("morph_field_bwd");

@@ -76,6 +76,7 @@ template <int MODE, int PPT>
 __global__ void __launch_bounds__(FT_THREADS * 2 / PPT, 2)
 smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ FtArgs q) {
+  pdl_trigger();               // programmatic dependent launch (advk_common.cuh); pdl_wait() follows the barrier set-up
   constexpr int NT = FtCfg<MODE>::NT, NS = FtCfg<MODE>::NS;
   constexpr int XO = 2 * PPT;                   // consecutive outputs of one x-pass task
   constexpr int XW = 6 * (2 / PPT);             // warps that carry x-pass tasks: 24 rows x (32 / XO) runs / 32
@@ -97,6 +98,7 @@ smooth3d_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();                  // everything above worked on kernel parameters and shared memory only
   // plane i lives in stage i % NS.  Planes outside the volume are requested like the others: the whole box is
   // out of bounds, TMA fills it with zeros without touching memory, and the stage / phase of a plane stays a
   // pure function of i (static after unrolling the plane loop by KT = 3 * NS)
@@ -330,10 +332,10 @@ static bool launch_smooth_tma(const Dims& g, const MorphCfg& c, const void* inA,
   dim3 grid(tx, ty, (unsigned)(g.N * q.nzc));
   if (ppt == 2)
     ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
-                (smooth3d_tma_kernel<MODE, 2><<<grid, FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+                (launch_pdl((smooth3d_tma_kernel<MODE, 2>), grid, FT_THREADS, FtCfg<MODE>::SMEM, st, mapA, mapB, q)));
   else
     ADVK_LAUNCH(MODE ? K_smooth_bwd : K_smooth_fwd, st,
-                (smooth3d_tma_kernel<MODE, 1><<<grid, 2 * FT_THREADS, FtCfg<MODE>::SMEM, st>>>(mapA, mapB, q)));
+                (launch_pdl((smooth3d_tma_kernel<MODE, 1>), grid, 2 * FT_THREADS, FtCfg<MODE>::SMEM, st, mapA, mapB, q)));
   return true;
 }
 

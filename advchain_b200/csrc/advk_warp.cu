@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(WARP_THREADS)
 warp_fwd_kernel(Dims g, int C, const float* __restrict__ src, const float* __restrict__ theta,
                 const void* __restrict__ field, int pad, int interp,
                 const float* __restrict__ padv, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
@@ -105,6 +106,7 @@ warp_bwd_kernel(Dims g, int C, const float* __restrict__ g_out, const float* __r
                 const float* __restrict__ theta, const void* __restrict__ field, int pad,
                 int interp, const float* __restrict__ padv, float* __restrict__ g_src,
                 float* __restrict__ g_theta, void* __restrict__ g_field) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[12 * 32];
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(WARP_THREADS)
 warp_bicubic_fwd_kernel(Dims g, int C, const float* __restrict__ src, const float* __restrict__ theta,
                         const void* __restrict__ field, int pad, const float* __restrict__ padv,
                         float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.S) return;
@@ -288,6 +291,7 @@ warp_bicubic_bwd_kernel(Dims g, int C, const float* __restrict__ g_out, const fl
                         const float* __restrict__ theta, const void* __restrict__ field, int pad,
                         const float* __restrict__ padv, float* __restrict__ g_src,
                         float* __restrict__ g_theta, void* __restrict__ g_field) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   __shared__ float red[6 * 32];
   const int n = blockIdx.y;
   const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -348,11 +352,11 @@ static int launch_fwd(const advk_geom* gg, int C, const float* src, const float*
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (interp == ADVK_INTERP_BICUBIC)
-    ADVK_LAUNCH(K_warp_fwd, st, warp_bicubic_fwd_kernel<FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, padv, out));
+    ADVK_LAUNCH(K_warp_fwd, st, launch_pdl((warp_bicubic_fwd_kernel<FIELD>), grid, WARP_THREADS, 0, st, g, C, src, theta, field, pad, padv, out));
   else if (gg->d == 2)
-    ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
+    ADVK_LAUNCH(K_warp_fwd, st, launch_pdl((warp_fwd_kernel<2, FIELD>), grid, WARP_THREADS, 0, st, g, C, src, theta, field, pad, interp, padv, out));
   else
-    ADVK_LAUNCH(K_warp_fwd, st, warp_fwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, src, theta, field, pad, interp, padv, out));
+    ADVK_LAUNCH(K_warp_fwd, st, launch_pdl((warp_fwd_kernel<3, FIELD>), grid, WARP_THREADS, 0, st, g, C, src, theta, field, pad, interp, padv, out));
   return check_launch("warp_fwd");
 }
 
@@ -369,11 +373,11 @@ static int launch_bwd(const advk_geom* gg, int C, const float* g_out, const floa
   dim3 grid(blocks_for(g.S, WARP_THREADS), g.N);
   cudaStream_t st = (cudaStream_t)stream;
   if (interp == ADVK_INTERP_BICUBIC)
-    ADVK_LAUNCH(K_warp_bwd, st, warp_bicubic_bwd_kernel<FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, padv, g_src, g_theta, g_field));
+    ADVK_LAUNCH(K_warp_bwd, st, launch_pdl((warp_bicubic_bwd_kernel<FIELD>), grid, WARP_THREADS, 0, st, g, C, g_out, src, theta, field, pad, padv, g_src, g_theta, g_field));
   else if (gg->d == 2)
-    ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<2, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
+    ADVK_LAUNCH(K_warp_bwd, st, launch_pdl((warp_bwd_kernel<2, FIELD>), grid, WARP_THREADS, 0, st, g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
   else
-    ADVK_LAUNCH(K_warp_bwd, st, warp_bwd_kernel<3, FIELD><<<grid, WARP_THREADS, 0, st>>>(g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
+    ADVK_LAUNCH(K_warp_bwd, st, launch_pdl((warp_bwd_kernel<3, FIELD>), grid, WARP_THREADS, 0, st, g, C, g_out, src, theta, field, pad, interp, padv, g_src, g_theta, g_field));
   return check_launch("warp_bwd");
 }
 

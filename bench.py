@@ -678,6 +678,13 @@ def run_b200(args):
     wD = (4 * C + 2 * d) if has_int else (2 * C + 2 * d)
     wB, wC_, wU = 2 * K + 3 * d + 1, 3 * K + 2 * d, (3 * C if "noise" in chain else 0)
     w_field = 94 * d
+    # the same two chain passes as they can be EXECUTED: a resampling needs the complete output of the stage before
+    # it, so every stage boundary is a round trip through HBM; compulsory words per stage
+    has_noise, has_bias, has_morph, has_aff = ("noise" in chain), ("bias" in chain), ("morph" in chain), ("affine" in chain)
+    wA_ps = ((2 + has_noise) * C if has_int else 0) + ((2 * C + d + 1) if has_morph else 0) + \
+            ((2 * C + 1 + has_morph) if has_aff else 0)
+    wD_ps = (3 * C if has_aff else 0) + ((3 * C + 2 * d) if has_morph else 0) + \
+            (((2 + 2 * has_noise) * C + has_bias) if has_int else 0)
     words = wA + wB + wC_ + wD + wU + w_field        # full chain: 102d + 10C + 5K + 1
     FIELD_KERNELS = ("ss_step", "ss_step_bwd", "smooth_fwd", "smooth_bwd", "init_phi0", "lowres_smooth",
                      "adjoint_axis", "aos_to_planar", "unorm2", "steps_check")
@@ -695,6 +702,7 @@ def run_b200(args):
 
     scopes = {
         "chain_apply_fwd_bwd_A+D": scope(("chain_img_fwd", "chain_img_bwd"), wA + wD),
+        "chain_apply_fwd_bwd_A+D_per_stage": scope(("chain_img_fwd", "chain_img_bwd"), wA_ps + wD_ps),
         "apply_total_A+B+C+D+U": scope(APPLY_KERNELS, wA + wB + wC_ + wD + wU),
         "field_build_fwd_bwd": scope(FIELD_KERNELS, w_field),
         "whole_step_advk_kernels": {"ms_per_step": round(sum(tot.values()), 4), "algo_bytes_per_step": words * 4.0 * nvox,
@@ -705,7 +713,10 @@ def run_b200(args):
                                            "frac": words * 4.0 * nvox / (ms / args.steps * 1e-3) / 1e9 / peak},
         "unit": "GB/s", "peak": peak,
         "note": "per-scope time = CUDA-event time of our kernels of that scope in eager steps (graph nodes cannot be "
-                "bracketed); the last scope uses the CUDA-graph step time of `value`",
+                "bracketed); the last scope uses the CUDA-graph step time of `value`; `_per_stage` divides the same time "
+                "by the compulsory bytes of the chain as executed (one HBM round trip per stage boundary: a resampling "
+                "needs the complete output of the stage before it), the scope without the suffix by the bytes of a "
+                "hypothetical single pass (SURVEY.md section 8d)",
     }
     iters = (1 if strong else world) * args.steps          # strong scaling: one iteration covers the global batch
     value = iters / (ms * 1e-3)

@@ -97,6 +97,8 @@ unsigned long long advk_launch_count(int kid, int reset);
 int advk_prof_configure(int kid, int capacity);
 int advk_prof_collect(int* kernel_ids, float* ms, int max_records);  /* host ptrs */
 int advk_prof_group_runs(int enable);
+/* programmatic dependent launch of the library's kernels (default on; ADVK_PDL=0); returns the previous setting */
+int advk_set_pdl(int enable);
 int advk_prof_collect_runs(int* kernel_ids, float* ms, int* launches, int max_records);  /* host ptrs */
 
 /* ---- AdvAffine: parameters -> matrices -------------------------------------------------

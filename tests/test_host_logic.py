@@ -234,3 +234,45 @@ def test_install_as_advchain_registers_reference_submodules():
     from advchain.augmentor.adv_morph import AdvMorph, get_base_grid      # noqa: F401
     from advchain.augmentor.adv_affine import AdvAffine                   # noqa: F401
     from advchain.augmentor.adv_noise import AdvNoise                     # noqa: F401
+
+
+def test_every_pdl_launched_kernel_waits_for_its_predecessors():
+    """A kernel launched with the programmatic-stream-serialization attribute may start before its predecessor
+    has finished: it must execute griddepcontrol.wait (pdl_wait()) before its first global-memory access
+    (advk_common.cuh).  Checked over the sources: every kernel named in a launch_pdl(...) call has pdl_wait() in
+    its body, ahead of any __ldg / pointer dereference for all but the TMA kernel (which first sets up barriers)."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "advchain_b200", "csrc")
+    srcs = {f: open(f).read() for f in glob.glob(os.path.join(root, "*.cu")) + glob.glob(os.path.join(root, "*.cuh"))}
+    launched = set()
+    for text in srcs.values():
+        for m in re.finditer(r"launch_pdl\(\((\w+)", text):
+            launched.add(m.group(1))
+    launched.discard("KERN")                     # macro parameter of the lean adjoint dispatch
+    launched |= {"lean_warp_bwd_kernel", "lean_warp_bwd_pk_kernel"}
+    assert len(launched) > 40
+    bodies = {}
+    for text in srcs.values():
+        for m in re.finditer(r"__global__\s+void\b[^;{(]*?(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", text):
+            i, d = m.end() - 1, 0
+            while True:
+                d += text[i] == "("
+                d -= text[i] == ")"
+                if d == 0:
+                    break
+                i += 1
+            j = text.index("{", i)
+            bodies[m.group(1)] = text[j:j + 3000]
+    for name in sorted(launched):
+        assert name in bodies, name
+        body = bodies[name]
+        k = body.find("pdl_wait()")
+        assert k >= 0, "%s is launched by launch_pdl but never calls pdl_wait()" % name
+        if name != "smooth3d_tma_kernel":
+            assert k < 80, "%s: pdl_wait() is not the first statement" % name
+    # ... and nothing launched with <<< >>> is left outside the cooperative / generic-stage executor
+    for f, text in srcs.items():
+        for m in re.finditer(r"(\w+)(?:<[^<>]*>)?\s*<<<", text):
+            assert m.group(1) in ("chain_fwd_stage_kernel", "chain_bwd_stage_kernel"), (f, m.group(1))
