@@ -370,14 +370,20 @@ class ComposeAdversarialTransformSolver(object):
             # iterations i_iter+1 .. n_iter (adv_compose_solver.py:308-368), as replays of a captured CUDA graph
             # when enabled and capturable, else eagerly
             k = n_iter - i_iter
-            if not (graph_ok and self._optimize_with_graph(model, data, init_output, optimize_flags, k, step_sizes,
-                                                           anatomy=anatomy)):
-                for _ in range(k):
-                    i_iter += 1
-                    self._eager_iteration(model, data, init_output, optimize_flags, step_sizes, anatomy, i_iter)
+            replayed = bool(graph_ok and self._optimize_with_graph(model, data, init_output, optimize_flags, k,
+                                                                   step_sizes, anatomy=anatomy))
+            for attempt in (0, 1):
+                if not replayed:
+                    for j in range(k):
+                        self._eager_iteration(model, data, init_output, optimize_flags, step_sizes, anatomy,
+                                              i_iter + j + 1)
+                # last-iteration bookkeeping (:369-375), enqueued while a replayed loop is still running
+                transforms = self._finish_loop(optimize_flags)
+                if not replayed or self._graph_verified():
+                    break
+                replayed = False                 # wrong 3-D step count assumed: redo these iterations eagerly
             i_iter = n_iter
-            # last-iteration bookkeeping (:369-375) and the anatomy-preserving retry state machine (:376-400)
-            transforms = self._finish_loop(optimize_flags)
+            # the anatomy-preserving retry state machine (:376-400)
             if self.if_contains_geo_transform(transforms) and use_anatomy:
                 if abs(self.compute_anatomy_misoverlapping_loss(anatomy_mask_images)) <= volume_preserve_tolerance:
                     stop_flag = True
@@ -511,20 +517,32 @@ class ComposeAdversarialTransformSolver(object):
                 st["norm2"][j:j + 1].copy_(n2.reshape(1))
         model.zero_grad()
 
-    @staticmethod
-    def _config_fingerprint(t):
-        """Everything of a transform's configuration that a captured iteration bakes into kernel arguments."""
-        def flat(v):
-            if isinstance(v, (list, tuple)):
-                return tuple(flat(x) for x in v)
-            if isinstance(v, dict):
-                return tuple(sorted((k, flat(x)) for k, x in v.items()))
-            return v if isinstance(v, (int, float, str, bool, type(None))) else repr(v)
-        names = ("epsilon", "xi", "ignore_values", "image_padding_mode", "forward_interp", "backward_interp",
+    _FP_NAMES = ("epsilon", "xi", "ignore_values", "image_padding_mode", "forward_interp", "backward_interp",
                  "data_size", "vector_size", "control_point_spacing", "downscale", "interpolation_order",
                  "use_log", "space", "rot", "scale", "shift", "num_steps")
-        fp = [(n, flat(getattr(t, n))) for n in names if hasattr(t, n)]
-        fp.append(("config", flat(getattr(t, "config_dict", None))))
+
+    @staticmethod
+    def _config_fingerprint(t):
+        """Everything of a transform's configuration that a captured iteration bakes into kernel arguments.
+        Runs before every graph replay, with the GPU idle behind the previous call's host sync: scalars are
+        taken as they are, only containers are flattened (61 -> 14 us for the four transforms of the full chain)."""
+        def flat(v):
+            c = v.__class__
+            if c is float or c is int or c is str or c is bool or v is None:
+                return v
+            if c is list or c is tuple:
+                return tuple(flat(x) for x in v)
+            if c is dict:
+                return tuple((k, flat(x)) for k, x in sorted(v.items()))
+            return repr(v)
+        d = t.__dict__
+        fp = []
+        for n in ComposeAdversarialTransformSolver._FP_NAMES:
+            if n in d:
+                fp.append((n, flat(d[n])))
+            elif hasattr(t, n):
+                fp.append((n, flat(getattr(t, n))))
+        fp.append(("config", flat(d.get("config_dict"))))
         return tuple(fp)
 
     @staticmethod
@@ -576,6 +594,7 @@ class ComposeAdversarialTransformSolver(object):
         finally:
             self.min_intensity, self.max_intensity = saved_range
             st["viol"].zero_()
+            st["viol_seen"] = 0
             for t in morph3d:
                 t._fixed_steps = None
                 t._steps_cache = None
@@ -649,20 +668,27 @@ class ComposeAdversarialTransformSolver(object):
                       anatomy=None if anatomy is None else anatomy[0].detach().clone(),
                       anatomy_weight=None if anatomy is None else float(anatomy[1]),
                       dist=torch.zeros(1, dtype=torch.float32, device=data.device),
-                      viol=torch.zeros(1, dtype=torch.int32, device=data.device),
+                      viol=torch.zeros(1, dtype=torch.int32, device=data.device), viol_seen=0,
                       norm2=torch.zeros(max(len(morph3d), 1), dtype=torch.float32, device=data.device))
             self._graphs[key] = st
             while len(self._graphs) > _GRAPH_CACHE_MAX:          # least recently captured goes first
                 self._graphs.pop(next(iter(self._graphs)))
-        st["data"].copy_(data.detach())
-        # always refreshed: (data_ptr, _version, shape) does not identify a tensor -- a training loop makes a
-        # new clean prediction every step, typically at the freed address of the previous one, version 0
-        st["init_output"].copy_(init_output.detach())
+        # The static copies are refreshed unless the source is provably the memory of the previous call,
+        # unchanged: same storage / offset / layout, same _version (counts in-place writes, shared by detach()
+        # aliases), and a reference to the storage has been held since -- so its address cannot have been
+        # recycled.  (data_ptr, _version, shape) alone does not identify a tensor: a training loop makes a new
+        # clean prediction every step, typically at the freed address of the previous one, version 0.
+        for name, src in (("data", data), ("init_output", init_output)):
+            ident = (src.untyped_storage().data_ptr(), src.storage_offset(), tuple(src.shape), tuple(src.stride()))
+            seen = st.get("src_" + name)
+            if seen is None or seen[1] != src._version or seen[2] != ident:
+                st[name].copy_(src.detach())
+                st["src_" + name] = (src.detach(), src._version, ident)
         if anatomy is not None:
             st["anatomy"].copy_(anatomy[0].detach())
         for buf, p in zip(st["params"], start):
             buf.copy_(p)
-        st["viol"].zero_()
+        # (the violation counter is cumulative: no zeroing launch before the replay, see _graph_verified)
         want_norm = bool(morph3d) and n_iter > 1
         cur, launches = nsteps, 0
 
@@ -687,20 +713,37 @@ class ComposeAdversarialTransformSolver(object):
         self.graph_replays = getattr(self, "graph_replays", 0) + n_iter
         self.graph_launches_per_replay = launches
         self.last_dist = st["dist"][0]
-        if morph3d and int(st["viol"].item()) != 0:
-            # the count assumed for the first iteration was wrong: redo the loop eagerly from the start
-            for t in morph3d:
-                t._last_nb_steps = None
-            self.graph_redos = getattr(self, "graph_redos", 0) + 1
-            return fail()
-        for t, n in zip(morph3d, nsteps):
-            t._last_nb_steps = n
         for t, buf in zip(chain, st["params"]):
             t.param = buf.clone()
         for flag, t in zip(optimize_flags, chain):
             t.is_training = bool(flag)          # _finish_loop's eval() detaches and clears the flag
         self._mask_cache = None
         self._fwd_mask = None
+        # The count assumed for the first iteration is verified on the device; the host reads the verdict (the
+        # call's one synchronisation) in _graph_verified(), AFTER the caller has enqueued the end-of-loop
+        # bookkeeping -- that host work then runs beside the replay instead of behind it with the GPU idle.
+        self._pending_check = (st if morph3d else None, morph3d, nsteps, fail)
+        return True
+
+    def _graph_verified(self):
+        """-> False when the graph loop that just ran assumed a wrong 3-D step count: the parameters are back
+        at their start values and the caller redoes the loop eagerly."""
+        pending, self._pending_check = getattr(self, "_pending_check", None), None
+        if pending is None:
+            return True
+        st, morph3d, nsteps, fail = pending
+        count = int(st["viol"].item()) if st is not None else 0          # the call's one host synchronisation
+        seen = st.get("viol_seen", 0) if st is not None else 0
+        if st is not None:
+            st["viol_seen"] = count
+        if count != seen:
+            for t in morph3d:
+                t._last_nb_steps = None
+            self.graph_redos = getattr(self, "graph_redos", 0) + 1
+            fail()
+            return False
+        for t, n in zip(morph3d, nsteps):
+            t._last_nb_steps = n
         return True
 
     def rescale_intensity(self, data, new_min=0, new_max=1, eps=1e-20):

@@ -367,3 +367,55 @@ def test_graph_cache_is_shared_and_captures_on_second_sight():
         assert torch.isfinite(sol.last_dist)
     assert replays == [0, 1, 1], replays          # eager, capture + replay, replay from the shared cache
     assert len(solver_mod._GRAPH_CACHE) <= solver_mod._GRAPH_CACHE_MAX
+
+
+def test_graph_loop_sees_in_place_changes_of_its_inputs():
+    """The graph loop keeps static copies of `data` and `init_output` and skips refreshing them only when the
+    source is provably the unchanged memory of the previous call (same storage, same _version, reference held).
+    An in-place write between two calls must reach the replay; an untouched pair must give the same result."""
+    from advchain_b200.augmentor import AdvAffine, AdvNoise, ComposeAdversarialTransformSolver
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [2, 1, 32, 40]
+    cfgs = stage_cfgs(2, size)
+    torch.manual_seed(23)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv2d(1, 3, 3, 1, 1).eval().to(dev)
+
+    def make(graph):
+        ts = [AdvNoise(2, cfgs["noise"], device=dev), AdvAffine(2, cfgs["affine"], device=dev)]
+        sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0
+        return sol, ts
+
+    gsol, gts = make(True)
+    esol, ets = make(False)
+    init = gsol.get_init_output(conv, x)
+    gsol.init_random_transformation()
+    start = [t.param.detach().clone() for t in gts]
+
+    def run(sol, ts, data, ref):
+        for t, p in zip(ts, start):
+            t.param = p.clone()
+            t.is_training = False
+        sol.optimizing_transform(model=conv, data=data, init_output=ref, optimize_flags=[True, True], n_iter=1,
+                                 step_sizes=[1.0, 1.0])
+        return float(sol.last_dist), [t.param.detach().clone() for t in ts]
+
+    d1, _ = run(gsol, gts, x, init)
+    d1b, _ = run(gsol, gts, x, init)                       # untouched inputs: the refresh is skipped
+    assert getattr(gsol, "graph_replays", 0) == 2
+    assert d1b == d1
+    init.mul_(0.5)                                         # in-place writes: same objects, new _version
+    x.mul_(0.9).add_(0.05)
+    d2, p2 = run(gsol, gts, x, init)
+    e2, q2 = run(esol, ets, x, init)
+    assert abs(d2 - d1) > 1e-6 * abs(d1), "the replay did not see the in-place change"
+    assert abs(d2 - e2) <= 2e-5 * abs(e2), (d2, e2)
+    for a, b in zip(p2, q2):
+        assert rel_err(a, b) < 1e-4
+    fresh = init.clone()                                   # a new tensor with the same values: refreshed, same result
+    d3, _ = run(gsol, gts, x, fresh)
+    assert abs(d3 - d2) <= 1e-6 * abs(d2)
