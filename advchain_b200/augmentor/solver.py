@@ -517,32 +517,34 @@ class ComposeAdversarialTransformSolver(object):
                 st["norm2"][j:j + 1].copy_(n2.reshape(1))
         model.zero_grad()
 
-    _FP_NAMES = ("epsilon", "xi", "ignore_values", "image_padding_mode", "forward_interp", "backward_interp",
-                 "data_size", "vector_size", "control_point_spacing", "downscale", "interpolation_order",
-                 "use_log", "space", "rot", "scale", "shift", "num_steps")
+    # attributes of a transform that change from call to call without changing what a captured iteration bakes in
+    # (power_iteration is a key component of its own; config_dict is only read by init_config, which copies it
+    # into the attributes fingerprinted here)
+    _FP_VOLATILE = frozenset(("param", "is_training", "affine_matrix", "shard", "device", "debug", "use_gpu",
+                              "power_iteration", "config_dict"))
+    _FP_SCALARS = frozenset((float, int, str, bool))
 
     @staticmethod
     def _config_fingerprint(t):
-        """Everything of a transform's configuration that a captured iteration bakes into kernel arguments.
-        Runs before every graph replay, with the GPU idle behind the previous call's host sync: scalars are
-        taken as they are, only containers are flattened (61 -> 14 us for the four transforms of the full chain)."""
-        def flat(v):
+        """Everything of a transform's configuration that a captured iteration bakes into kernel arguments: every
+        public instance attribute (epsilon, xi, the affine ranges, interpolation / padding modes, sizes, ...)
+        except the volatile ones, tensors and None (an attribute that is None now and a tensor later must not
+        change the key; a None that becomes a number does).  Runs before every graph replay with the GPU idle
+        behind the previous call's host sync, so it is kept cheap (21 us for the four transforms of the full
+        chain): scalars are taken as they are, lists become tuples, anything else its repr."""
+        scalars = ComposeAdversarialTransformSolver._FP_SCALARS
+        volatile = ComposeAdversarialTransformSolver._FP_VOLATILE
+        fp = [t.__class__.__name__]
+        for k, v in t.__dict__.items():
+            if v is None or k in volatile or k[0] == "_":
+                continue
             c = v.__class__
-            if c is float or c is int or c is str or c is bool or v is None:
-                return v
-            if c is list or c is tuple:
-                return tuple(flat(x) for x in v)
-            if c is dict:
-                return tuple((k, flat(x)) for k, x in sorted(v.items()))
-            return repr(v)
-        d = t.__dict__
-        fp = []
-        for n in ComposeAdversarialTransformSolver._FP_NAMES:
-            if n in d:
-                fp.append((n, flat(d[n])))
-            elif hasattr(t, n):
-                fp.append((n, flat(getattr(t, n))))
-        fp.append(("config", flat(d.get("config_dict"))))
+            if c in scalars:
+                fp.append((k, v))
+            elif c is list or c is tuple:
+                fp.append((k, tuple(v)))
+            elif not isinstance(v, torch.Tensor):
+                fp.append((k, repr(v)))
         return tuple(fp)
 
     @staticmethod
@@ -686,9 +688,13 @@ class ComposeAdversarialTransformSolver(object):
                 st["src_" + name] = (src.detach(), src._version, ident)
         if anatomy is not None:
             st["anatomy"].copy_(anatomy[0].detach())
-        for buf, p in zip(st["params"], start):
-            buf.copy_(p)
-        # (the violation counter is cumulative: no zeroing launch before the replay, see _graph_verified)
+        # start parameters -> static buffers in ONE multi-tensor launch (this runs with the GPU idle behind the
+        # previous call's synchronisation; the violation counter is cumulative: no zeroing launch either)
+        try:
+            torch._foreach_copy_(st["params"], start)
+        except (AttributeError, RuntimeError):
+            for buf, p in zip(st["params"], start):
+                buf.copy_(p)
         want_norm = bool(morph3d) and n_iter > 1
         cur, launches = nsteps, 0
 
