@@ -378,6 +378,10 @@ class ChainApply(Function):
              ptr(stash), ptr(out), ptr(mask_out), stream())
         ctx.save_for_backward(src, stash, *params)
         ctx.meta = (spec, g, int(n_scr.value))
+        # the mask and the stash never carry a gradient: without this autograd hands backward() freshly
+        # zero-filled tensors of their sizes (19 M + 2 M floats for the prediction chain at 128^3: 16 us of fills
+        # per chain adjoint, profiles/r02u_launch_list.md)
+        ctx.set_materialize_grads(False)
         if mask_out is not None:
             ctx.mark_non_differentiable(mask_out, stash)
         else:
@@ -391,6 +395,8 @@ class ChainApply(Function):
         src, stash, params = saved[0], saved[1], list(saved[2:])
         spec, g, n_scr = ctx.meta
         need = ctx.needs_input_grad
+        if g_out is None:                                   # the chain output itself was not used
+            return (None, None, None) + (None,) * len(params)
         grads = [None] * len(params)
         ups = []
         for st in spec.stages:

@@ -681,7 +681,8 @@ lean_theta_reduce_kernel(Dims g, const void* __restrict__ gc, float* __restrict_
   float acc[NG];
 #pragma unroll
   for (int i = 0; i < NG; ++i) acc[i] = 0.f;
-  for (int p = blockIdx.x * 256 + threadIdx.x; p < S; p += gridDim.x * 256) {
+#pragma unroll 4
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < S; p += gridDim.x * 256) {      // (loads of 4 trips in flight)
     int x, y, z;
     voxel_xyz(g, (unsigned)p, x, y, z);
     const float bx = base_coord_s(x, g.W, g.stW, 0.f), by = base_coord_s(y, g.H, g.stH, 0.f);
