@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadvchain_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
 INTERP_LINEAR, INTERP_NEAREST, INTERP_BICUBIC = 0, 1, 2
@@ -105,6 +105,7 @@ SIGNATURES = {
     "advk_pgd_update_guarded": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P, _P]),
     "advk_morph_tune": (_I, [_I]),
     "advk_morph_steps_check": (_I, [_P, _I, _I, _P, _P]),
+    "advk_publish_verdict": (_I, [_P, _P, _P, _P]),
     "advk_clamp": (_I, [_P, _F, _F, _P, _Z, _P]),
     "advk_clamp_bwd": (_I, [_P, _P, _F, _F, _P, _Z, _P]),
     "advk_nonzero_mask": (_I, [_P, _Z, _P]),

@@ -25,7 +25,8 @@ int check_launch(const char* what);
   X(smooth_fwd) X(smooth_bwd) X(adjoint_axis) X(lowres_smooth) X(init_phi0) X(ss_step)           \
   X(ss_step_bwd) X(aos_to_planar) X(unorm2) X(warp_fwd) X(warp_bwd) X(loss_softmax)               \
   X(loss_contour) X(loss_contour_adj) X(loss_finalize) X(loss_grad) X(chain_fwd) X(chain_fwd_stage) X(chain_bwd)         \
-  X(chain_bwd_stage) X(steps_check) X(chain_img_fwd) X(chain_pk_fwd) X(chain_img_bwd) X(chain_pk_bwd)
+  X(chain_bwd_stage) X(steps_check) X(chain_img_fwd) X(chain_pk_fwd) X(chain_img_bwd) X(chain_pk_bwd)        \
+  X(publish)
 enum KernelId {
 #define ADVK_X(n) K_##n,
   ADVK_KERNELS(ADVK_X)

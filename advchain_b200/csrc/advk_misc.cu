@@ -282,6 +282,25 @@ extern "C" int advk_morph_steps_check(const float* norm2, int nb_steps, int min_
   return check_launch("morph_steps_check");
 }
 
+// Early verdict of a graph-replayed PGD iteration: one thread bumps the replay's sequence number and stores
+// (sequence << 8 | violations & 0xff) as ONE 32-bit word into pinned, device-mapped HOST memory, so that the host
+// can poll the word while the rest of the iteration is still running instead of synchronising behind it.
+__global__ void publish_kernel(const int* __restrict__ violations, unsigned* __restrict__ seq,
+                               volatile unsigned* host_word) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  const unsigned s = *seq + 1u;
+  *seq = s;
+  *host_word = (s << 8) | ((unsigned)*violations & 0xffu);
+  __threadfence_system();
+}
+
+extern "C" int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, void* stream) {
+  ADVK_REQUIRE(violations && seq && host_word, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  ADVK_LAUNCH(K_publish, st, launch_pdl((publish_kernel), 1, 1, 0, st, violations, seq, (volatile unsigned*)host_word));
+  return check_launch("publish_verdict");
+}
+
 extern "C" int advk_pgd_update(float* param, const float* grad, float step, int mode, int N,
                                size_t per_sample, double* sumsq, void* stream) {
   return advk_pgd_update_guarded(param, grad, step, mode, N, per_sample, sumsq, nullptr, stream);

@@ -391,6 +391,77 @@ ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename 
   }
 }
 
+// A CTA of the tile kernels (advk_morph_tune bits 3 and 4) owns a 32 (x) x 8 (y) tile of one z plane, one warp
+// per row: block index -> (tile x, tile y, z) by multiply-high division.
+struct TileMap {
+  FastDiv ftx, fty;     // tiles along x, tiles along y
+  int tx, ty;
+};
+static TileMap make_tilemap(const Dims& g) {
+  TileMap tm;
+  tm.tx = (g.W + 31) / 32; tm.ty = (g.H + 7) / 8;
+  tm.ftx = make_fastdiv((unsigned)tm.tx); tm.fty = make_fastdiv((unsigned)tm.ty);
+  return tm;
+}
+
+// The lean forward step on 32 x 8 tiles (advk_morph_tune bit 4): the 8 rows of a tile share their corner rows
+// through L1 -- (8+1) rows x 2 planes of 33 voxels per 256 voxels = 1.16 sector fills per voxel against the
+// 1.5 of 256 consecutive voxels (2 rows of 128: 3 rows x 2 planes).  Same arithmetic as ss_step_lean_kernel.
+template <int DIM, bool EMIT_R>
+__global__ void __launch_bounds__(256, 8)
+ss_step_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out,
+                    const typename V<DIM>::T* __restrict__ phi0, typename V<DIM>::T* __restrict__ rout) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  typedef typename V<DIM>::T T;
+  const unsigned b = blockIdx.x;
+  const unsigned q = fast_div(b, tm.ftx);                         // b = (z * ty + tyi) * tx + txi
+  const int txi = (int)(b - q * (unsigned)tm.tx);
+  const int z = (int)fast_div(q, tm.fty);
+  const int tyi = (int)(q - (unsigned)z * (unsigned)tm.ty);
+  const int x = txi * 32 + (threadIdx.x & 31), y = tyi * 8 + (threadIdx.x >> 5);
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W;
+  const int p = (z * g.H + y) * g.W + x;
+  const i64 nb = (i64)blockIdx.y * g.S;
+  const T* src = opaque_ptr(in + nb);
+  const T f = __ldg(src + p);
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
+  Axis az;
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
+  const int dxo = ax.v1 ? 1 : 0, dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
+  const T* c000 = src + (az.i0 * HW + ay.i0 * g.W + ax.i0);
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll
+  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const T s = __ldg(c000 + (dz * dzo + dy * dyo + dx * dxo));
+        const float w = (dx ? ax.w1 : ax.w0) * (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
+        ox += s.x * w; oy += s.y * w;
+        if (DIM == 3) oz += V<DIM>::z(s) * w;
+      }
+    }
+  }
+  (out + nb)[p] = V<DIM>::make(ox, oy, oz);
+  if (EMIT_R) {
+    const T q0 = __ldg(opaque_ptr(phi0 + nb) + p);
+    float m;
+    const float bx = base_coord_s(x, g.W, g.stW), by = base_coord_s(y, g.H, g.stH);
+    const float rx = compose_axis((ox - q0.x) + bx, g.W, g.stW, m) - bx;
+    const float ry = compose_axis((oy - q0.y) + by, g.H, g.stH, m) - by;
+    float rz = 0.f;
+    if (DIM == 3) {
+      const float bz = base_coord_s(z, g.D, g.stD);
+      rz = compose_axis((oz - V<DIM>::z(q0)) + bz, g.D, g.stD, m) - bz;
+    }
+    (opaque_ptr(rout + nb))[p] = V<DIM>::make(rx, ry, rz);
+  }
+}
+
 // Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
 //     dL/dphi_{k-1}(y) = sum_x g_k(x) * w(phi_{k-1}(x), y)            scatter adjoint of the gather
 //                      + mult * < d(sample)/d(coord) at y , g_k(y) >   spatial-Jacobian term
@@ -565,15 +636,155 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
   }
 }
 
+// Tile adjoint (advk_morph_tune bit 3): the lean kernel on a 32 (x) x 8 (y) tile of one z plane, one warp per row,
+// with a second hand-off ALONG Y through shared memory.  The RED payload is what keeps the L1 -> crossbar port
+// busy in the lean kernel (6.1 M sectors = 194 MB per launch at 128^3, 70 % of the port's cycles): the corner
+// rows (y0+1, z0 | z0+1) of the voxel (x, y) are the corner rows (y0, ...) of the voxel (x, y+1) whenever that
+// voxel's corner (0,0,0) lies one row further (always, for a smooth field), so the upper rows travel to the
+// thread one row up as ONE float4 each (value xyz + the target voxel offset in w) and are added to its lower-row
+// REDs: 2 corner REDs + the Jacobian RED per voxel instead of 4 + 1 (the last row of a tile keeps its own upper
+// rows: 3.25 on average).  A receiver whose address does not match -- or that lies outside the volume -- issues
+// the sender's REDs at the sender's addresses, so the result does not depend on the field being smooth.
+template <int DIM, bool ZS>
+__global__ void __launch_bounds__(256)
+ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
+                        typename V<DIM>::T* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  typedef typename V<DIM>::T T;
+  constexpr int NZ = DIM == 3 ? 2 : 1;
+  const unsigned FULL = 0xffffffffu;
+  __shared__ float4 hand_s[NZ][8][32];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const unsigned b = blockIdx.x;
+  const unsigned q = fast_div(b, tm.ftx);                         // b = (z * ty + tyi) * tx + txi
+  const int txi = (int)(b - q * (unsigned)tm.tx);
+  const unsigned z = fast_div(q, tm.fty);
+  const int tyi = (int)(q - z * (unsigned)tm.ty);
+  const int x = txi * 32 + lane, y = tyi * 8 + row;
+  const bool live = x < g.W && y < g.H;
+  const int HW = g.H * g.W;
+  const int p = live ? ((int)z * g.H + y) * g.W + x : 0;
+  const i64 nb = (i64)blockIdx.y * g.S;
+  const T* src = opaque_ptr(phi_prev + nb);
+  T* dst = opaque_ptr(out + nb);
+  T* upn = opaque_ptr(up + nb);
+  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
+  if (live) {
+    f = __ldg(src + p);
+    go = upn[p];
+  }
+  Axis ax = make_axis_border(f.x, g.W);
+  Axis ay = make_axis_border(f.y, g.H);
+  Axis az;
+  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
+  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; az.mult = 0.f; }
+  const float gx = go.x, gy = go.y, gz = V<DIM>::z(go);
+  // outside corners are redirected to corner 0 of their axis (weight / mult exactly 0 there): see the lean kernel
+  const int dxo = ax.v1 ? 1 : 0, dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
+  const int a000 = az.i0 * HW + ay.i0 * g.W + ax.i0;
+  // x hand-off by weight (shuffles, executed by all lanes)
+  const int next = __shfl_down_sync(FULL, live ? a000 : -1, 1);
+  const bool hand = live && ax.v1 && lane < 31 && next == a000 + 1;
+  const float px = __shfl_up_sync(FULL, gx, 1), py = __shfl_up_sync(FULL, gy, 1);
+  const float pz = DIM == 3 ? __shfl_up_sync(FULL, gz, 1) : 0.f;
+  float w1[NZ][2];
+  float vx[NZ][2], vy[NZ][2], vz[NZ][2];
+#pragma unroll
+  for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const float wr = (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
+      const float a = ax.w0 * wr;
+      w1[dz][dy] = ax.w1 * wr;
+      const float got = __shfl_up_sync(FULL, hand ? w1[dz][dy] : 0.f, 1);
+      const float bw = lane ? got : 0.f;
+      vx[dz][dy] = gx * a + px * bw; vy[dz][dy] = gy * a + py * bw; vz[dz][dy] = gz * a + pz * bw;
+    }
+  }
+  // y hand-off: the upper rows go to the thread one row up (the last row of the tile keeps them)
+  const bool send = live && ay.v1 && row < 7;
+#pragma unroll
+  for (int dz = 0; dz < NZ; ++dz)
+    hand_s[dz][row][lane] = make_float4(vx[dz][1], vy[dz][1], vz[dz][1],
+                                        __int_as_float(send ? a000 + dz * dzo + dyo : -1));
+  __syncthreads();
+  T* d000 = dst + a000;
+  if (row) {
+#pragma unroll
+    for (int dz = 0; dz < NZ; ++dz) {
+      const float4 h = hand_s[dz][row - 1][lane];
+      const int ha = __float_as_int(h.w);
+      if (ha >= 0) {
+        if (live && ha == a000 + dz * dzo) { vx[dz][0] += h.x; vy[dz][0] += h.y; vz[dz][0] += h.z; }
+        else atomicAdd(dst + ha, V<DIM>::make(h.x, h.y, h.z));     // non-smooth spot / receiver outside the volume
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int dz = 0; dz < NZ; ++dz) {
+      atomicAdd(d000 + dz * dzo, V<DIM>::make(vx[dz][0], vy[dz][0], vz[dz][0]));
+      if (!send) atomicAdd(d000 + (dz * dzo + dyo), V<DIM>::make(vx[dz][1], vy[dz][1], vz[dz][1]));
+    }
+    if (ax.v1 && !hand) {                                           // row ends and non-smooth spots only
+#pragma unroll
+      for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const float c = w1[dz][dy];
+          atomicAdd(d000 + (dz * dzo + dy * dyo + 1), V<DIM>::make(gx * c, gy * c, gz * c));
+        }
+      }
+    }
+  }
+  // gathers -> d = <phi(corner), g>, Jacobian term by separable differences (as in the lean kernel)
+  const T* s000 = src + a000;
+  float d[NZ][2][2];
+#pragma unroll
+  for (int dz = 0; dz < NZ; ++dz) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const T* r = s000 + (dz * dzo + dy * dyo);
+      const T s0 = __ldg(r), s1 = __ldg(r + dxo);
+      d[dz][dy][0] = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
+      d[dz][dy][1] = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
+    }
+  }
+  float jx, jy, jz = 0.f;
+  {
+    float jxz[NZ], eyd[NZ], ey[NZ];
+#pragma unroll
+    for (int dz = 0; dz < NZ; ++dz) {
+      const float e0 = ax.w0 * d[dz][0][0] + ax.w1 * d[dz][0][1], e1 = ax.w0 * d[dz][1][0] + ax.w1 * d[dz][1][1];
+      jxz[dz] = ay.w0 * (d[dz][0][1] - d[dz][0][0]) + ay.w1 * (d[dz][1][1] - d[dz][1][0]);
+      eyd[dz] = e1 - e0;
+      ey[dz] = ay.w0 * e0 + ay.w1 * e1;
+    }
+    if (DIM == 3) {
+      jx = az.w0 * jxz[0] + az.w1 * jxz[NZ - 1];
+      jy = az.w0 * eyd[0] + az.w1 * eyd[NZ - 1];
+      jz = ey[NZ - 1] - ey[0];
+    } else {
+      jx = jxz[0]; jy = eyd[0];
+    }
+  }
+  if (live) {
+    atomicAdd(dst + p, V<DIM>::make(jx * ax.mult, jy * ay.mult, jz * az.mult));
+    if (ZS) upn[p] = V<DIM>::make(0.f, 0.f, 0.f);               // AFTER the REDs (see the lean kernel)
+  }
+}
+
 // advk_morph_tune / ADVK_SSB_MODE: bit 0 = the plain predecessors of the lean squaring-step kernels
 // (predicated forward step, one-RED-per-corner adjoint with memset nodes); bit 1 = the two-launch predecessor
 // (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh); bit 2 = the lean
-// adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd).  Default 0.
+// adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd); bit 3 = the tile
+// adjoint with the y hand-off through shared memory (ss_step_bwd_tile_kernel) instead of the lean one; bit 4 = the
+// lean forward step on 32 x 8 tiles (ss_step_tile_kernel).  Default 0.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 7) : 0;
+    g_ssb_mode = e ? (atoi(e) & 31) : 0;
   }
   return g_ssb_mode;
 }
@@ -622,6 +833,13 @@ template <int DIM>
 static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
                                typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
   dim3 grid(blocks_for(g.S, 256), g.N);
+  if ((ssb_mode() & 9) == 8) {
+    const TileMap tm = make_tilemap(g);
+    dim3 tg((unsigned)((i64)tm.tx * tm.ty * g.D), g.N);
+    if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
+    else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
+    return;
+  }
   if (ssb_mode() & 1) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_plain_kernel<DIM>), grid, 256, 0, st, g, phi_prev, up, out)));
   else if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_lean_kernel<DIM, true>), grid, 256, 0, st, g, phi_prev, up, out)));
   else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_lean_kernel<DIM, false>), grid, 256, 0, st, g, phi_prev, up, out)));
@@ -1013,8 +1231,14 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   const bool lean = (ssb_mode() & 1) == 0;
   // 3-D: the last step also writes the smoothing input r into the scratch level, for the TMA-staged Gaussian
   const bool fused = DIM == 3 && lean && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
+  const bool tiled = lean && (ssb_mode() & 16) != 0;
+  const TileMap tm = make_tilemap(g);
+  dim3 tg((unsigned)((i64)tm.tx * tm.ty * g.D), g.N);
   for (int k = 1; k <= nb; ++k) {
-    if (lean && fused && k == nb)
+    if (tiled && fused && k == nb)
+      ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_tile_kernel<DIM, true>), tg, 256, 0, st, g, tm, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
+    else if (tiled) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_tile_kernel<DIM, false>), tg, 256, 0, st, g, tm, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
+    else if (lean && fused && k == nb)
       ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, true>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
     else if (lean) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, false>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
     else ADVK_LAUNCH(K_ss_step, st, launch_pdl((ss_step_kernel<DIM>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F));
@@ -1116,7 +1340,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 7;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 31;
   return prev;
 }
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ADVK_ABI_VERSION 2
+#define ADVK_ABI_VERSION 3
 
 enum { ADVK_OK = 0, ADVK_ERR_ARG = -1, ADVK_ERR_UNSUPPORTED = -2, ADVK_ERR_CUDA = -3 };
 enum { ADVK_PAD_ZEROS = 0, ADVK_PAD_BORDER = 1, ADVK_PAD_REFLECTION = 2 };
@@ -175,6 +175,9 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  *   bit 2: the lean adjoint zeroes the scatter target it consumed itself (two targets).  Default: three targets
  *          in rotation, zeroed by memsets on a library-owned side stream beside the next launch (event fork /
  *          join: capturable, no host synchronisation).
+ *   bit 3: the adjoint on 32 x 8 tiles (one warp per row) with a second hand-off along y through shared memory:
+ *          2 corner REDs + the Jacobian RED per voxel instead of 4 + 1.
+ *   bit 4: the forward step on the same 32 x 8 tiles (fewer L1 fills per voxel).
  * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
  * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
@@ -228,6 +231,13 @@ int advk_pgd_update_guarded(float* param, const float* grad, float step, int mod
  * (from advk_morph_unorm2) gives a different count. */
 int advk_morph_steps_check(const float* norm2, int nb_steps, int min_steps, int* violations,
                            void* stream);
+/* Early verdict of a graph-captured iteration (the reference reads its NaN guard and its 3-D step count on
+ * the host in the middle of every iteration, adv_compose_solver.py:345, adv_morph.py:159-162; here the host
+ * needs ONE word per call, and needs it before the iteration has finished so that the next call can be enqueued
+ * behind the running one).  Increments *seq (device, 1 word) and stores (*seq << 8) | (*violations & 0xff) as one
+ * 32-bit word to `host_word`, which must be pinned host memory that the device can address (cudaHostAlloc /
+ * torch pin_memory under unified addressing).  The host polls that word; no stream synchronisation. */
+int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, void* stream);
 
 /* ---- fused chain apply ---------------------------------------------------------------------
  * ONE launch applies a whole chain of transforms to an N x C x S tensor, ONE launch applies its
