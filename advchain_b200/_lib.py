@@ -99,6 +99,7 @@ SIGNATURES = {
     "advk_chain_apply_fwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_chain_apply_bwd": (_I, [C.POINTER(ChainDesc), _P, _P, _P, _P, _P, _P]),
     "advk_loss_scratch_floats": (_Z, [_G, _I]),
+    "advk_loss_tune": (_I, [_I]),
     "advk_consistency_loss_fwd": (_I, [_G, _I, _P, _P, _P, _F, _F, _F, _I, _P, _P, _P]),
     "advk_consistency_loss_bwd": (_I, [_G, _I, _P, _F, _F, _F, _I, _P, _P, _P, _P]),
     "advk_pgd_update": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P]),

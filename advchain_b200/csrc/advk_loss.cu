@@ -17,6 +17,7 @@
 //   K2 loss_contour : R_k = mult_k m^2 (k * E_c)    ; contour partial sums      (c >= 1)
 //   K3 loss_contour_adj : s_c = sum_k k^T * R_k (c >= 1)
 //   K4 loss_grad    : g_pred_c = 2 A_mse m^2 E_c + 2 A_cont s_c ; softmax backward
+#include <stdlib.h>
 #include "advk_common.cuh"
 
 namespace advk {
@@ -262,6 +263,136 @@ loss_contour_adj_kernel(Dims g, int K, int nzc, const float* __restrict__ R, flo
   }
 }
 
+// 3-D, fused (the default; advk_loss_tune(0) / ADVK_LOSS_FUSED=0 selects the two kernels above): the Sobel
+// responses AND their adjoint in ONE z-marching pass.  The adjoint at a voxel needs R on its 3 x 3 x 3
+// neighbourhood, i.e. E on 5 x 5 x 5: the CTA stages E planes with a 2-voxel halo (36 x 12 cells), evaluates R
+// on the tile + 1-voxel halo (34 x 10 cells, two per thread, 3-plane register windows for the h(D) factor) into
+// shared memory, and every thread applies the adjoint stencils to that plane with a second 3-plane window.  R
+// (48 MB written and read back per loss at 1 x 4 x 128^3) never exists in global memory; the contour adjoint
+// s_c = sum_k k^T * R_k goes to the scratch slot R used to occupy, for loss_grad_kernel.  Same arithmetic per
+// cell as loss_contour_kernel / loss_contour_adj_kernel: bit-identical s, R outside the volume is 0.
+constexpr int LF_EX = LT_X + 4, LF_EY = LT_Y + 4, LF_EN = LF_EX * LF_EY;     // E plane: halo 2
+constexpr int LF_RX = LT_X + 2, LF_RY = LT_Y + 2, LF_RN = LF_RX * LF_RY;     // R plane: halo 1
+
+template <int ROW>
+__device__ __forceinline__ void sobel_plane_w(const float* __restrict__ t, int tx, int ty, float& a, float& b) {
+  const float* q0 = t + ty * ROW + tx;
+  const float* q1 = q0 + ROW;
+  const float* q2 = q1 + ROW;
+  const float r00 = q0[0], r01 = q0[1], r02 = q0[2];
+  const float r10 = q1[0], r12 = q1[2];
+  const float r20 = q2[0], r21 = q2[1], r22 = q2[2];
+  a = (r00 + 2.f * r01 + r02) - (r20 + 2.f * r21 + r22);
+  b = (r00 + 2.f * r10 + r20) - (r02 + 2.f * r12 + r22);
+}
+
+__global__ void __launch_bounds__(LT_X * LT_Y)
+loss_contour_fused_kernel(Dims g, int K, int nzc, const float* __restrict__ E, const float* __restrict__ mask,
+                          float* __restrict__ Sg, double* __restrict__ acc) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  constexpr int NT = LT_X * LT_Y;
+  __shared__ float et[2][LF_EN];
+  __shared__ float rt[2][2][LF_RN];
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int tx = tid % LT_X, ty = tid / LT_X;
+  const int zc = blockIdx.z % nzc;
+  const int nc = blockIdx.z / nzc;
+  const int n = nc / (K - 1), c = 1 + nc % (K - 1);
+  const int x0 = blockIdx.x * LT_X, y0 = blockIdx.y * LT_Y;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool inxy = x < g.W && y < g.H;
+  const int HW = g.H * g.W;
+  const float* e = E + ((i64)n * K + c) * g.S;
+  const float* mk = mask ? mask + (i64)n * g.S : nullptr;
+  float* so = Sg + ((i64)n * (K - 1) + (c - 1)) * g.S;
+  const int zb = zc * LT_Z, ze = min(g.D, zb + LT_Z);
+  // this thread's two E cells (staging) and two R cells (evaluation); in-plane voxel offset, -1 = outside
+  int eoff[2], roff[2], rlx[2], rly[2];
+  bool rown[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ie = tid + j * NT;
+    const int ely = ie / LF_EX, elx = ie - ely * LF_EX;
+    const int egy = y0 + ely - 2, egx = x0 + elx - 2;
+    eoff[j] = (ie < LF_EN && egy >= 0 && egy < g.H && egx >= 0 && egx < g.W) ? egy * g.W + egx : -1;
+    const int ir = tid + j * NT;
+    rly[j] = ir / LF_RX; rlx[j] = ir - rly[j] * LF_RX;
+    const int rgy = y0 + rly[j] - 1, rgx = x0 + rlx[j] - 1;
+    roff[j] = (ir < LF_RN && rgy >= 0 && rgy < g.H && rgx >= 0 && rgx < g.W) ? rgy * g.W + rgx : -1;
+    rown[j] = roff[j] >= 0 && rly[j] >= 1 && rly[j] <= LT_Y && rlx[j] >= 1 && rlx[j] <= LT_X;
+  }
+  const bool has_r1 = tid + NT < LF_RN;
+  const float mult0 = 2.f;                                   // quirk Q10: gx is used for x and y
+  float wa[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, wb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float ua[3] = {0.f, 0.f, 0.f}, ub[3] = {0.f, 0.f, 0.f};
+  float pe[2], mnext[2] = {1.f, 1.f};
+  float v[1] = {0.f};
+  {
+    const int pz = zb - 2;
+    const bool zin = pz >= 0 && pz < g.D;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) pe[j] = (zin && eoff[j] >= 0) ? __ldg(e + (i64)pz * HW + eoff[j]) : 0.f;
+  }
+  for (int pz = zb - 2; pz <= ze + 1; ++pz) {
+    const int it = pz - (zb - 2);
+    float* et_ = et[it & 1];
+    et_[tid] = pe[0];
+    if (tid + NT < LF_EN) et_[tid + NT] = pe[1];
+    __syncthreads();
+    const float m0 = mnext[0], m1 = mnext[1];                // mask of plane zr = pz - 1 (loaded one iteration ago)
+    if (pz <= ze) {                                          // next E plane, and the mask of this plane for the next round
+      const int qz = pz + 1;
+      const bool zin = qz >= 0 && qz < g.D;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) pe[j] = (zin && eoff[j] >= 0) ? __ldg(e + (i64)qz * HW + eoff[j]) : 0.f;
+      const bool pin = pz >= 0 && pz < g.D;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) mnext[j] = (mk && pin && roff[j] >= 0) ? __ldg(mk + (i64)pz * HW + roff[j]) : 1.f;
+    }
+    wa[0][0] = wa[0][1]; wa[0][1] = wa[0][2]; wb[0][0] = wb[0][1]; wb[0][1] = wb[0][2];
+    sobel_plane_w<LF_EX>(et_, rlx[0], rly[0], wa[0][2], wb[0][2]);
+    if (has_r1) {
+      wa[1][0] = wa[1][1]; wa[1][1] = wa[1][2]; wb[1][0] = wb[1][1]; wb[1][1] = wb[1][2];
+      sobel_plane_w<LF_EX>(et_, rlx[1], rly[1], wa[1][2], wb[1][2]);
+    }
+    if (it < 2) continue;                                    // (block-uniform)
+    // E planes pz-2 .. pz are in the windows: R of plane zr = pz - 1 on the tile + halo 1
+    const int zr = pz - 1;
+    const bool zrin = zr >= 0 && zr < g.D;
+    const bool zown = zr >= zb && zr < ze;
+    float* r0_ = rt[it & 1][0];
+    float* r1_ = rt[it & 1][1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j == 1 && !has_r1) break;
+      float R0 = 0.f, R1 = 0.f;
+      if (zrin && roff[j] >= 0) {
+        const float g0 = wa[j][0] + 2.f * wa[j][1] + wa[j][2];        // gx = h(D) hp(H) h(W)
+        const float g1 = wb[j][0] + 2.f * wb[j][1] + wb[j][2];        // gz = h(D) h(H) hp(W)
+        const float m = j ? m1 : m0;
+        const float a0 = m * g0, a1 = m * g1;
+        if (zown && rown[j]) v[0] += mult0 * a0 * a0 + a1 * a1;
+        R0 = mult0 * m * a0;
+        R1 = m * a1;
+      }
+      r0_[tid + j * NT] = R0;
+      r1_[tid + j * NT] = R1;
+    }
+    __syncthreads();
+    ua[0] = ua[1]; ua[1] = ua[2]; ub[0] = ub[1]; ub[1] = ub[2];
+    float dummy;
+    sobel_plane_w<LF_RX>(r0_, tx, ty, ua[2], dummy);         // hp(H) h(W) R0
+    sobel_plane_w<LF_RX>(r1_, tx, ty, dummy, ub[2]);         // h(H) hp(W) R1
+    if (it >= 4 && inxy) {                                   // R planes zr-2 .. zr: the adjoint at plane zo = zr - 1
+      const int zo = zr - 1;
+      so[((i64)zo * g.H + y) * g.W + x] = -((ua[0] + 2.f * ua[1] + ua[2]) + (ub[0] + 2.f * ub[1] + ub[2]));
+    }
+  }
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(acc + 1, (double)v[0]);
+}
+
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont, float a_kl,
                                      float* __restrict__ loss) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
@@ -274,8 +405,10 @@ template <int KC>
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __restrict__ pred,
                  const float* __restrict__ mask, float a_mse, float a_cont, float a_kl, int is_gt,
-                 const float* __restrict__ upstream, float* __restrict__ g_out) {
+                 const float* __restrict__ upstream, const float* sc, int sc_K, int sc_off, float* g_out) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  // sc: the contour adjoint s_c, plane (n * sc_K + c - sc_off): the scratch slot of the fused 3-D kernel
+  // (sc_K = K-1, sc_off = 1) or g_out itself (sc_K = K, sc_off = 0: loss_contour_adj_kernel wrote it there)
   const int K = KC > 0 ? KC : Krt;
   constexpr int KA = KC > 0 ? KC : 1;
   const int n = blockIdx.y;
@@ -294,7 +427,7 @@ loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __res
       const i64 q = q0 + (i64)c * S;
       e[c] = E[q]; pr[c] = pred[q];
       gp[c] = cm * e[c];
-      if (c >= 1 && a_cont != 0.f) gp[c] += cc * g_out[q];
+      if (c >= 1 && a_cont != 0.f) gp[c] += cc * sc[((i64)n * sc_K + (c - sc_off)) * S + p];
       dot += gp[c] * pr[c];
       const float t = pr[c] - e[c];
       psum += is_gt ? ((t == 0.f) ? 1e-8f : 1.f - 1e-8f) : t;
@@ -315,7 +448,7 @@ loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __res
   i64 q = q0;
   for (int c = 0; c < K; ++c, q += S) {
     float gp = cm * E[q];
-    if (c >= 1 && a_cont != 0.f) gp += cc * g_out[q];
+    if (c >= 1 && a_cont != 0.f) gp += cc * sc[((i64)n * sc_K + (c - sc_off)) * S + p];
     g_out[q] = gp;
     dot += gp * pred[q];
   }
@@ -343,6 +476,22 @@ loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __res
 }  // namespace advk
 
 using namespace advk;
+
+// 1 (default; environment ADVK_LOSS_FUSED): 3-D contour term by loss_contour_fused_kernel; 0: the two-kernel
+// predecessor.  Must not change between a forward call and the backward call that consumes its scratch.
+static int g_loss_fused = -1;
+static int loss_fused() {
+  if (g_loss_fused < 0) {
+    const char* e = getenv("ADVK_LOSS_FUSED");
+    g_loss_fused = e ? (atoi(e) != 0) : 1;
+  }
+  return g_loss_fused;
+}
+extern "C" int advk_loss_tune(int fused) {
+  int prev = loss_fused();
+  if (fused >= 0) g_loss_fused = fused != 0;
+  return prev;
+}
 
 static void loss_scales(const Dims& g, int K, int d, float w_mse, float w_contour, float w_kl, float& a_mse,
                         float& a_cont, float& a_kl) {
@@ -392,6 +541,7 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
     if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
+    else if (loss_fused()) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_fused_kernel), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
     else ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<3>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
   }
   ADVK_LAUNCH(K_loss_finalize, st, launch_pdl((loss_finalize_kernel), 1, 1, 0, st, acc, a_mse, a_cont, a_kl, loss));
@@ -413,14 +563,15 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   float a_mse, a_cont, a_kl;
   loss_scales(g, K, gg->d, w_mse, w_contour, w_kl, a_mse, a_cont, a_kl);
   if (K <= 1) a_cont = 0.f;
-  if (a_cont != 0.f) {
+  const bool fused = gg->d == 3 && loss_fused();            // the forward left s_c where R would have been
+  if (a_cont != 0.f && !fused) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
     if (gg->d == 2) ADVK_LAUNCH(K_loss_contour_adj, st, launch_pdl((loss_contour_adj_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, R, g_output));
     else ADVK_LAUNCH(K_loss_contour_adj, st, launch_pdl((loss_contour_adj_kernel<3>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, R, g_output));
   }
   dim3 grid(blocks_for(g.S, 256), g.N);
-#define ADVK_LGRAD(KC) ADVK_LAUNCH(K_loss_grad, st, launch_pdl((loss_grad_kernel<KC>), grid, 256, 0, st, g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, g_output))
+#define ADVK_LGRAD(KC) ADVK_LAUNCH(K_loss_grad, st, launch_pdl((loss_grad_kernel<KC>), grid, 256, 0, st, g.S, K, E, pred, mask, a_mse, a_cont, a_kl, is_gt, upstream, fused ? R : g_output, fused ? K - 1 : K, fused ? 1 : 0, g_output))
   switch (K) {
     case 2: ADVK_LGRAD(2); break;
     case 3: ADVK_LGRAD(3); break;

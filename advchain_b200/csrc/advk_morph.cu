@@ -636,7 +636,8 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
   }
 }
 
-// Tile adjoint (advk_morph_tune bit 3): the lean kernel on a 32 (x) x 8 (y) tile of one z plane, one warp per row,
+// Tile adjoint (the default where the tiles are full; advk_morph_tune bits 3 / 5 force it on / off): the lean
+// kernel on a 32 (x) x 8 (y) tile of one z plane, one warp per row,
 // with a second hand-off ALONG Y through shared memory.  The RED payload is what keeps the L1 -> crossbar port
 // busy in the lean kernel (6.1 M sectors = 194 MB per launch at 128^3, 70 % of the port's cycles): the corner
 // rows (y0+1, z0 | z0+1) of the voxel (x, y) are the corner rows (y0, ...) of the voxel (x, y+1) whenever that
@@ -645,6 +646,9 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
 // REDs: 2 corner REDs + the Jacobian RED per voxel instead of 4 + 1 (the last row of a tile keeps its own upper
 // rows: 3.25 on average).  A receiver whose address does not match -- or that lies outside the volume -- issues
 // the sender's REDs at the sender's addresses, so the result does not depend on the field being smooth.
+// Measured at 128^3 (gpurun_out/r02w): 715 against 733 us per 16 launches, 441.3 against 438.3 it/s -- the RED
+// sectors drop by a third, the launch by 2.4 %: with the REDs thinned the kernel sits on its two dependent
+// round trips (phi(p), g(p) -> corners) at 50 % occupancy.
 template <int DIM, bool ZS>
 __global__ void __launch_bounds__(256)
 ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
@@ -778,13 +782,14 @@ ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict
 // (predicated forward step, one-RED-per-corner adjoint with memset nodes); bit 1 = the two-launch predecessor
 // (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh); bit 2 = the lean
 // adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd); bit 3 = the tile
-// adjoint with the y hand-off through shared memory (ss_step_bwd_tile_kernel) instead of the lean one; bit 4 = the
-// lean forward step on 32 x 8 tiles (ss_step_tile_kernel).  Default 0.
+// adjoint with the y hand-off through shared memory (ss_step_bwd_tile_kernel) whatever the geometry (default: where
+// the 32 x 8 tiles are at least 97 % full); bit 4 = the lean forward step on 32 x 8 tiles (ss_step_tile_kernel,
+// measured equal to the linear mapping); bit 5 = the lean linear adjoint whatever the geometry.  Default 0.
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 31) : 0;
+    g_ssb_mode = e ? (atoi(e) & 63) : 0;
   }
   return g_ssb_mode;
 }
@@ -833,8 +838,11 @@ template <int DIM>
 static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev, typename V<DIM>::T* up,
                                typename V<DIM>::T* out, bool may_zero_up, cudaStream_t st) {
   dim3 grid(blocks_for(g.S, 256), g.N);
-  if ((ssb_mode() & 9) == 8) {
-    const TileMap tm = make_tilemap(g);
+  // Tile adjoint by default where the tiles are (almost) full -- it buys 2.4 % per launch at 128^3, less than a
+  // partly filled tile column costs; bit 3 forces it, bit 5 forces the lean linear kernel.
+  const TileMap tm = make_tilemap(g);
+  const bool tile_fits = (i64)g.W * g.H * 100 >= (i64)97 * (tm.tx * 32) * (tm.ty * 8);
+  if ((ssb_mode() & 1) == 0 && ((ssb_mode() & 8) || (tile_fits && !(ssb_mode() & 32)))) {
     dim3 tg((unsigned)((i64)tm.tx * tm.ty * g.D), g.N);
     if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
     else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
@@ -1340,7 +1348,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 31;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 63;
   return prev;
 }
 

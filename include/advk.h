@@ -175,9 +175,11 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  *   bit 2: the lean adjoint zeroes the scatter target it consumed itself (two targets).  Default: three targets
  *          in rotation, zeroed by memsets on a library-owned side stream beside the next launch (event fork /
  *          join: capturable, no host synchronisation).
- *   bit 3: the adjoint on 32 x 8 tiles (one warp per row) with a second hand-off along y through shared memory:
- *          2 corner REDs + the Jacobian RED per voxel instead of 4 + 1.
- *   bit 4: the forward step on the same 32 x 8 tiles (fewer L1 fills per voxel).
+ *   bit 3: force the adjoint on 32 x 8 tiles (one warp per row) with a second hand-off along y through shared
+ *          memory: 2 corner REDs + the Jacobian RED per voxel instead of 4 + 1.  Default: used where the tiles are
+ *          at least 97 % full (W, H multiples of 32, 8 or large), the lean linear kernel elsewhere.
+ *   bit 4: the forward step on the same 32 x 8 tiles (fewer L1 fills per voxel; measured equal).
+ *   bit 5: force the lean linear adjoint.
  * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
  * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
@@ -335,6 +337,12 @@ int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out, const flo
  * floats, 8-byte aligned; it carries the softmax / edge maps from fwd to bwd.  loss: 1 float
  * (device).  bwd: upstream = device pointer to dL/dloss (NULL = 1); g_output N x K x S, written. */
 size_t advk_loss_scratch_floats(const advk_geom* g, int K);
+/* 1 (default; environment ADVK_LOSS_FUSED): the 3-D contour term and its adjoint run as ONE z-marching kernel in
+ * the forward call (the Sobel responses stay in shared memory, the adjoint s_c is left in `scratch` for the
+ * backward call); 0: the two-kernel predecessor (responses written by fwd, adjoint applied by bwd).  Same
+ * results.  A negative value only queries; returns the previous setting.  Must not change between a forward
+ * call and the backward call that consumes its scratch. */
+int advk_loss_tune(int fused);
 int advk_consistency_loss_fwd(const advk_geom* g, int K, const float* output, const float* reference,
                               const float* mask, float w_mse, float w_contour, float w_kl, int is_gt,
                               float* scratch, float* loss, void* stream);

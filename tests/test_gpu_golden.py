@@ -303,6 +303,49 @@ def test_graph_loop_follows_the_3d_step_count():
     assert float((res[1] - res[0]).norm() / res[0].norm()) < 2e-3
 
 
+def test_graph_loop_early_verdict_sequence():
+    """The graph loop's one wait per call ends when the replay PUBLISHES its step-count verdict (one word in
+    pinned host memory, advk_publish_verdict), not when the replay ends.  Every replay bumps a device-side
+    sequence number; the word the host accepted must carry exactly the number of replays launched so far, the
+    device counter must agree once the stream has drained, and the parameters must equal the eager loop's."""
+    from advchain_b200.augmentor import AdvMorph, AdvNoise, ComposeAdversarialTransformSolver
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [1, 1, 24, 32, 40]
+    cfgs = stage_cfgs(3, size, vector=[3, 4, 5])
+    torch.manual_seed(11)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv3d(1, 3, 3, 1, 1).eval().to(dev)
+    start, res = None, []
+    for graph in (False, True):
+        ts = [AdvNoise(3, cfgs["noise"], device=dev), AdvMorph(3, cfgs["morph"], device=dev)]
+        sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0
+        init = sol.get_init_output(conv, x)
+        for t in ts:
+            t.init_parameters()
+        if start is None:
+            start = [t.param.detach().clone() for t in ts]
+        for call in range(4):
+            for t, p in zip(ts, start):
+                t.param = p.clone()
+            sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True, True], n_iter=1,
+                                     step_sizes=[1.0, 1.0])
+            if graph:
+                st = [v for v in sol._graphs.values() if isinstance(v, dict) and v["refs"][1]() is ts[0]][-1]
+                assert st["publish"] and st["seq_host"] >= call + 1
+                word = int(st["tok_np"][0]) & 0xffffffff          # accepted by the call that just returned
+                assert (word >> 8) == st["seq_host"] & 0xffffff
+        res.append([t.param.detach().clone() for t in ts])
+    torch.cuda.synchronize()
+    assert int(st["seq"].item()) == st["seq_host"]
+    assert getattr(sol, "graph_replays", 0) == 4 and getattr(sol, "graph_redos", 0) == 0
+    for a, b in zip(res[0], res[1]):
+        assert float((a - b).norm() / a.norm()) < 2e-3
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_nan_loss_skips_the_update(graph):
     """adv_compose_solver.py:345-346: a NaN / Inf consistency loss skips backward and the parameter

@@ -207,15 +207,16 @@ MORPH_TIE_TOL = 1e-2
 @pytest.mark.parametrize("d,size,vsize,scale", MORPH)
 @pytest.mark.parametrize("vnorm", [1.0, 6.0])
 @pytest.mark.parametrize("support", ["interior", "full"])
-@pytest.mark.parametrize("tile", [0, 1, 2, 4, 8, 16, 28])
+@pytest.mark.parametrize("tile", [0, 1, 2, 4, 8, 16, 28, 32])
 def test_morph_field(d, size, vsize, scale, vnorm, support, tile):
     """vnorm=6 mimics late PGD steps where ||v|| has grown and parts of the field hit the clamp.
     `tile` is the advk_morph_tune mask: 0 the defaults (lean squaring-step kernels; 3-D: TMA-staged one-launch
     Gaussian fed by the last squaring step), bit 0 the plain squaring-step predecessors (predicated forward
     step, one RED per corner + memset nodes), bit 1 the two-launch predecessor of the 3-D Gaussian, bit 2 the
     adjoint that zeroes its consumed buffer itself (default: three targets zeroed by side-stream memsets), bit 3
-    the adjoint on 32 x 8 tiles with the y hand-off through shared memory, bit 4 the forward step on the same
-    tiles (28 = both tile kernels + the self-zeroing adjoint)."""
+    forces the adjoint on 32 x 8 tiles with the y hand-off through shared memory (default only where the tiles
+    are full), bit 4 the forward step on the same tiles (28 = both tile kernels + the self-zeroing adjoint),
+    bit 5 forces the lean linear adjoint."""
     from advchain_b200 import _lib
     from advchain_b200.augmentor import AdvMorph
     ops = _ops()
@@ -352,7 +353,8 @@ def test_clamp_and_mask():
 
 
 LOSS = [(2, [2, 4, 37, 53]), (3, [2, 4, 11, 19, 23]), (3, [1, 3, 16, 16, 16]), (2, [3, 2, 32, 48]),
-        (2, [1, 6, 20, 24]), (3, [1, 8, 8, 12, 16])]      # K = 6: run-time class count, K = 8: register path
+        (2, [1, 6, 20, 24]), (3, [1, 8, 8, 12, 16]),      # K = 6: run-time class count, K = 8: register path
+        (3, [1, 4, 37, 21, 45])]                          # three z chunks, partial tiles in x and y
 
 
 @pytest.mark.parametrize("d,size", LOSS)
@@ -386,6 +388,36 @@ def test_consistency_loss(d, size, types, weights, masked, is_gt):
     assert _lib.launch_count("loss_grad") == 1, "the fused loss kernel did not run"
     assert abs(l1.item() - l0.item()) <= 1e-5 * abs(l0.item())
     assert rel_err(o1.grad, 3.0 * o0.grad) < 2e-5
+
+
+@pytest.mark.parametrize("size", [[2, 4, 37, 21, 45], [1, 3, 16, 40, 64], [1, 2, 5, 9, 33]])
+@pytest.mark.parametrize("masked", [False, True])
+def test_consistency_loss_fused_contour_is_the_two_kernel_result(size, masked):
+    """3-D contour term: the one-pass kernel (Sobel responses + their adjoint on a z-marching tile with a 2-voxel
+    halo, the default) against its two-kernel predecessor (advk_loss_tune(0)): the same arithmetic per cell, so the
+    gradient is bit-identical and the loss differs by the order of its double-precision partial sums only."""
+    from advchain_b200 import _lib
+    from advchain_b200.common.loss import calc_segmentation_consistency
+    torch.manual_seed(12)
+    out = (torch.randn(*size) * 2).to(_dev())
+    ref = (torch.randn(*size) * 2).to(_dev())
+    mask = (torch.rand(size[0], 1, *size[2:]) > 0.3).float().to(_dev()).expand(*size) if masked else None
+    res = []
+    prev = _lib.load().advk_loss_tune(-1)
+    try:
+        for fused in (0, 1):
+            _lib.load().advk_loss_tune(fused)
+            o = out.clone().requires_grad_(True)
+            _lib.launch_count("loss_contour_adj", reset=True)
+            loss = calc_segmentation_consistency(o, ref, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                 scales=[0], mask=mask)
+            loss.backward()
+            assert _lib.launch_count("loss_contour_adj") == (0 if fused else 1)
+            res.append((loss.item(), o.grad.clone()))
+    finally:
+        _lib.load().advk_loss_tune(prev)
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+    assert torch.equal(res[0][1], res[1][1])
 
 
 def test_consistency_loss_fallbacks():
