@@ -404,76 +404,6 @@ static TileMap make_tilemap(const Dims& g) {
   return tm;
 }
 
-// The lean forward step with the x1 corners taken from the NEIGHBOUR LANE (advk_morph_tune bit 4).  The lean
-// kernel is bound by L1 wavefronts (67 % of the data pipe: 8 gathers of 512 B per warp, r02u): lane i's corner-1
-// column is lane i+1's corner-0 column whenever that lane's corner (0,0,0) is one voxel further, so only the 4
-// corner-0 gathers are issued and their values travel one lane down by shuffle; the lanes without such a
-// neighbour (lane 31, non-smooth spots) load their corner-1 column themselves.  Bit-identical result.
-template <int DIM, bool EMIT_R>
-__global__ void __launch_bounds__(256, 8)
-ss_step_xs_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename V<DIM>::T* __restrict__ out,
-                  const typename V<DIM>::T* __restrict__ phi0, typename V<DIM>::T* __restrict__ rout) {
-  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
-  typedef typename V<DIM>::T T;
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int pp = blockIdx.x * blockDim.x + threadIdx.x;          // S < 2^31 (host-checked)
-  const bool live = pp < g.S;
-  const int p = live ? pp : (int)g.S - 1;                         // (every shuffle is executed by all lanes)
-  const i64 nb = (i64)blockIdx.y * g.S;
-  const T* src = opaque_ptr(in + nb);
-  const T f = __ldg(src + p);
-  Axis ax = make_axis_border(f.x, g.W);
-  Axis ay = make_axis_border(f.y, g.H);
-  Axis az;
-  if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
-  else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
-  const int HW = g.H * g.W;
-  const int dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
-  const int a000 = az.i0 * HW + ay.i0 * g.W + ax.i0;
-  const int nxt = __shfl_down_sync(FULL, a000, 1);
-  const bool share = ax.v1 && lane < 31 && nxt == a000 + 1;
-  const T* c000 = src + a000;
-  float ox = 0.f, oy = 0.f, oz = 0.f;
-#pragma unroll
-  for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const T* r = c000 + (dz * dzo + dy * dyo);
-      const T s0 = __ldg(r);
-      float tx = __shfl_down_sync(FULL, s0.x, 1), ty = __shfl_down_sync(FULL, s0.y, 1);
-      float tz = DIM == 3 ? __shfl_down_sync(FULL, V<DIM>::z(s0), 1) : 0.f;
-      if (!share) {
-        if (ax.v1) { const T s1 = __ldg(r + 1); tx = s1.x; ty = s1.y; tz = V<DIM>::z(s1); }
-        else { tx = s0.x; ty = s0.y; tz = V<DIM>::z(s0); }       // outside corner: weight exactly 0
-      }
-      const float wr = (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
-      const float w0 = ax.w0 * wr, w1 = ax.w1 * wr;
-      ox += s0.x * w0; oy += s0.y * w0;
-      if (DIM == 3) oz += V<DIM>::z(s0) * w0;
-      ox += tx * w1; oy += ty * w1;
-      if (DIM == 3) oz += tz * w1;
-    }
-  }
-  if (!live) return;
-  (out + nb)[p] = V<DIM>::make(ox, oy, oz);
-  if (EMIT_R) {
-    const T q = __ldg(opaque_ptr(phi0 + nb) + p);
-    int x, y, z;
-    voxel_xyz(g, (unsigned)p, x, y, z);
-    float m;
-    const float bx = base_coord_s(x, g.W, g.stW), by = base_coord_s(y, g.H, g.stH);
-    const float rx = compose_axis((ox - q.x) + bx, g.W, g.stW, m) - bx;
-    const float ry = compose_axis((oy - q.y) + by, g.H, g.stH, m) - by;
-    float rz = 0.f;
-    if (DIM == 3) {
-      const float bz = base_coord_s(z, g.D, g.stD);
-      rz = compose_axis((oz - V<DIM>::z(q)) + bz, g.D, g.stD, m) - bz;
-    }
-    (opaque_ptr(rout + nb))[p] = V<DIM>::make(rx, ry, rz);
-  }
-}
-
 // Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
 //     dL/dphi_{k-1}(y) = sum_x g_k(x) * w(phi_{k-1}(x), y)            scatter adjoint of the gather
 //                      + mult * < d(sample)/d(coord) at y , g_k(y) >   spatial-Jacobian term
@@ -661,8 +591,8 @@ ss_step_bwd_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ phi_prev,
 // Measured at 128^3 (gpurun_out/r02w): 715 against 733 us per 16 launches, 441.3 against 438.3 it/s -- the RED
 // sectors drop by a third, the launch by 2.4 %: with the REDs thinned the kernel sits on its two dependent
 // round trips (phi(p), g(p) -> corners) at 50 % occupancy.
-template <int DIM, bool ZS, bool XS>
-__global__ void __launch_bounds__(256, XS ? 5 : 1)
+template <int DIM, bool ZS>
+__global__ void __launch_bounds__(256)
 ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict__ phi_prev, typename V<DIM>::T* up,
                         typename V<DIM>::T* __restrict__ out) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
@@ -761,21 +691,9 @@ ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
       const T* r = s000 + (dz * dzo + dy * dyo);
-      const T s0 = __ldg(r);
+      const T s0 = __ldg(r), s1 = __ldg(r + dxo);
       d[dz][dy][0] = s0.x * gx + s0.y * gy + V<DIM>::z(s0) * gz;
-      if (XS) {
-        // bit 6: the x1 corner is the neighbour lane's x0 corner whenever the scatter is handed over (`hand`)
-        float tx = __shfl_down_sync(FULL, s0.x, 1), ty = __shfl_down_sync(FULL, s0.y, 1);
-        float tz = DIM == 3 ? __shfl_down_sync(FULL, V<DIM>::z(s0), 1) : 0.f;
-        if (!hand) {
-          if (dxo) { const T s1 = __ldg(r + 1); tx = s1.x; ty = s1.y; tz = V<DIM>::z(s1); }
-          else { tx = s0.x; ty = s0.y; tz = V<DIM>::z(s0); }
-        }
-        d[dz][dy][1] = tx * gx + ty * gy + tz * gz;
-      } else {
-        const T s1 = __ldg(r + dxo);
-        d[dz][dy][1] = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
-      }
+      d[dz][dy][1] = s1.x * gx + s1.y * gy + V<DIM>::z(s1) * gz;
     }
   }
   float jx, jy, jz = 0.f;
@@ -807,16 +725,16 @@ ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict
 // (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh); bit 2 = the lean
 // adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd); bit 3 = the tile
 // adjoint with the y hand-off through shared memory (ss_step_bwd_tile_kernel) whatever the geometry (default: where
-// the 32 x 8 tiles are at least 97 % full); bit 4 = the lean forward step with the x1 corners shuffled in from the
-// neighbour lane (ss_step_xs_kernel); bit 5 = the lean linear adjoint whatever the geometry; bit 6 = the tile
-// adjoint takes its x1 corners from the neighbour lane as well.  Default 0.
-// (The forward step on 32 x 8 tiles -- 1.16 instead of 1.5 L1 fills per voxel -- measured 2 % SLOWER than the
-// linear mapping, gpurun_out/r02w: removed.)
+// the 32 x 8 tiles are at least 97 % full); bit 5 = the lean linear adjoint whatever the geometry.  Default 0.
+// Measured and removed (gpurun_out/r02w, r02y): the forward step on 32 x 8 tiles (1.16
+// instead of 1.5 L1 fills per voxel: 2 % slower), and the x1 corners of either step taken from the neighbour lane
+// by shuffle (4 gathers instead of 8: forward +1.1 %, adjoint +1.8 % of the whole iteration, and not bit-identical
+// because the weight products associate differently).
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 127) : 0;
+    g_ssb_mode = e ? (atoi(e) & 63) : 0;
   }
   return g_ssb_mode;
 }
@@ -871,11 +789,8 @@ static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev
   const bool tile_fits = (i64)g.W * g.H * 100 >= (i64)97 * (tm.tx * 32) * (tm.ty * 8);
   if ((ssb_mode() & 1) == 0 && ((ssb_mode() & 8) || (tile_fits && !(ssb_mode() & 32)))) {
     dim3 tg((unsigned)((i64)tm.tx * tm.ty * g.D), g.N);
-    const bool xs = (ssb_mode() & 64) != 0;
-    if (may_zero_up && xs) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
-    else if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
-    else if (xs) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
-    else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
+    if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
+    else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
     return;
   }
   if (ssb_mode() & 1) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_plain_kernel<DIM>), grid, 256, 0, st, g, phi_prev, up, out)));
@@ -1269,12 +1184,8 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   const bool lean = (ssb_mode() & 1) == 0;
   // 3-D: the last step also writes the smoothing input r into the scratch level, for the TMA-staged Gaussian
   const bool fused = DIM == 3 && lean && (ssb_mode() & 2) == 0 && ft_encoder() != nullptr;
-  const bool xs = lean && (ssb_mode() & 16) != 0;
   for (int k = 1; k <= nb; ++k) {
-    if (xs && fused && k == nb)
-      ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_xs_kernel<DIM, true>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
-    else if (xs) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_xs_kernel<DIM, false>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
-    else if (lean && fused && k == nb)
+    if (lean && fused && k == nb)
       ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, true>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
     else if (lean) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, false>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
     else ADVK_LAUNCH(K_ss_step, st, launch_pdl((ss_step_kernel<DIM>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F));
@@ -1376,7 +1287,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 127;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 63;
   return prev;
 }
 

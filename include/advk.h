@@ -178,9 +178,7 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  *   bit 3: force the adjoint on 32 x 8 tiles (one warp per row) with a second hand-off along y through shared
  *          memory: 2 corner REDs + the Jacobian RED per voxel instead of 4 + 1.  Default: used where the tiles are
  *          at least 97 % full (W, H multiples of 32, 8 or large), the lean linear kernel elsewhere.
- *   bit 4: the forward step takes its x1 corners from the neighbour lane by shuffle (4 gathers instead of 8).
  *   bit 5: force the lean linear adjoint.
- *   bit 6: the tile adjoint takes its x1 corners from the neighbour lane by shuffle as well.
  * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
  * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
