@@ -106,7 +106,7 @@ SIGNATURES = {
     "advk_pgd_update_guarded": (_I, [_P, _P, _F, _I, _I, _Z, _P, _P, _P]),
     "advk_morph_tune": (_I, [_I]),
     "advk_morph_steps_check": (_I, [_P, _I, _I, _P, _P]),
-    "advk_publish_verdict": (_I, [_P, _P, _P, _P]),
+    "advk_publish_verdict": (_I, [_P, _P, _P, _P, _P, _P]),
     "advk_clamp": (_I, [_P, _F, _F, _P, _Z, _P]),
     "advk_clamp_bwd": (_I, [_P, _P, _F, _F, _P, _Z, _P]),
     "advk_nonzero_mask": (_I, [_P, _Z, _P]),

@@ -64,6 +64,7 @@ class AdvMorph(AdvTransformBase):
         self._cfg = None
         self._fixed_steps = None    # (n, int32 device counter): graph mode, rule verified on the device
         self._last_nb_steps = None  # count the last graph-mode loop ran with (and verified)
+        self._norm_seen = None      # device scalar: |u|^2 the last device-side step-rule check looked at
         self.shard = None           # sharding.ShardContext: whole-batch norm for the 3-D step rule (quirk Q2)
 
     def init_config(self, config_dict):
@@ -169,6 +170,7 @@ class AdvMorph(AdvTransformBase):
                 self.shard.all_reduce_sum_(n2)          # quirk Q2: whole-batch norm, no host round trip
             _ops.call("advk_morph_steps_check", _ops.ptr(n2), int(n), int(self.num_steps), viol.data_ptr(),
                       _ops.stream())
+            self._norm_seen = n2
             self._steps_cache = (weakref.ref(self.param), self.param._version, self._scale(), n)
             return n
         if self.shard is not None:
@@ -202,6 +204,7 @@ class AdvMorph(AdvTransformBase):
                 self.shard.all_reduce_sum_(norm_out)
             _ops.call("advk_morph_steps_check", _ops.ptr(norm_out), int(nb), int(self.num_steps), viol.data_ptr(),
                       _ops.stream())
+            self._norm_seen = norm_out          # the graph loop publishes it to the host with the verdict
             self._steps_cache = (weakref.ref(p), p._version, self._scale(), nb)
         self._cache[sign] = (weakref.ref(p), p._version, self._scale(),
                              torch.is_grad_enabled() and p.requires_grad, field)

@@ -75,6 +75,7 @@ class ComposeAdversarialTransformSolver(object):
         self._graphs = _GRAPH_CACHE      # shared by all solvers: training loops build a solver per step
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
         self.graph_capture_after = 1      # eager runs of a configuration before it is captured
+        self.spec_first_ratio = 1.6       # assumed growth of |u| over the FIRST PGD step (later ones: measured)
         self.overlap_field_builds = os.environ.get("ADVK_OVERLAP_FIELDS", "1") != "0"   # graph loop only
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
@@ -460,9 +461,15 @@ class ComposeAdversarialTransformSolver(object):
         read from and written back to static buffers, the NaN/Inf guard runs on the device."""
         chain = self.chain_of_transforms
         model.zero_grad()
+        if st.get("mode") == "spec":
+            # speculative multi-iteration loop: the parameters this iteration starts from, so that an iteration
+            # that ran with a mispredicted 3-D step count can be taken back (one multi-tensor copy)
+            torch._foreach_copy_(st["backup"], st["params"])
         for t, buf in zip(chain, st["params"]):
             t.param = buf
             t.is_training = False
+            if isinstance(t, AdvMorph):
+                t._norm_seen = None
         self.make_learnable_transformation(optimize_flags=st["flags"], chain_of_transforms=chain)
         side = None
         if self.overlap_field_builds:
@@ -488,7 +495,10 @@ class ComposeAdversarialTransformSolver(object):
         if st.get("publish"):
             # every field of this iteration is built and its 3-D step count checked: the verdict goes to the
             # host NOW (one word into pinned memory), four fifths of the iteration before it ends
+            seen = [t._norm_seen for t in chain if isinstance(t, AdvMorph) and t.spatial_dims == 3]
+            n2 = seen[0] if len(seen) == 1 and seen[0] is not None else None
             _ops.call("advk_publish_verdict", st["viol"].data_ptr(), st["seq"].data_ptr(), st["tok"].data_ptr(),
+                      None if n2 is None else _ops.ptr(n2), None if n2 is None else st["normh"].data_ptr(),
                       _ops.stream())
         if self.if_contains_geo_transform(chain):
             warped = self.predict_backward(out)
@@ -511,7 +521,7 @@ class ComposeAdversarialTransformSolver(object):
                 finally:
                     t._guard = None
                 buf.copy_(t.param.detach())
-        if st.get("want_norm"):
+        if st.get("mode") == "norm":
             # norm of the velocity field the NEXT iteration will integrate (3-D step rule, adv_morph.py:
             # 159-162): the host reads it between replays and picks the graph captured for that count
             for j, t in enumerate(t_ for t_ in chain if isinstance(t_, AdvMorph) and t_.spatial_dims == 3):
@@ -554,15 +564,16 @@ class ComposeAdversarialTransformSolver(object):
 
     @staticmethod
     def _steps_from_norm2(norm2, min_steps):
-        """adv_morph.py:159-162: smallest n >= min_steps with ||u|| / 2^n <= 0.5."""
-        import math
-        nrm = math.sqrt(max(float(norm2), 0.0))
+        """adv_morph.py:159-162: smallest n >= min_steps with ||u|| / 2^n <= 0.5 -- in fp32 like the device-side
+        check (steps_check_kernel: sqrtf, exact division by a power of two)."""
+        import numpy as np
+        nrm = float(np.sqrt(np.float32(max(float(norm2), 0.0))))
         n = int(min_steps)
-        while nrm / (2.0 ** n) > 0.5:
+        while nrm / (2.0 ** n) > 0.5 and n < 64:
             n += 1
         return n
 
-    def _capture_iteration(self, model, st, morph3d, nsteps, want_norm, start):
+    def _capture_iteration(self, model, st, morph3d, nsteps, mode, start):
         """Captures one PGD iteration for the given 3-D step counts into st["graphs"]; returns the entry or
         None when the model / driver refuses capture."""
         saved_range = (self.min_intensity, self.max_intensity)
@@ -570,7 +581,7 @@ class ComposeAdversarialTransformSolver(object):
             self.min_intensity, self.max_intensity = st["range"]  # bake the bounds, no aminmax in the graph
         for t, n in zip(morph3d, nsteps):
             t._fixed_steps = (n, st["viol"])
-        st["want_norm"] = want_norm
+        st["mode"] = mode
         keep = [b.clone() for b in st["params"]]
         entry = None
         try:
@@ -594,7 +605,7 @@ class ComposeAdversarialTransformSolver(object):
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.shard is not None else "global"):
                 self._graph_iteration(model, st)
             entry = (graph, _lib.launch_count() - before)
-            st["graphs"][(nsteps, want_norm)] = entry
+            st["graphs"][(nsteps, mode)] = entry
         except Exception as exc:                                 # model or driver refuses capture
             logging.warning("advchain_b200: CUDA-graph capture failed (%s); running eagerly", exc)
             torch.cuda.synchronize()
@@ -615,11 +626,14 @@ class ComposeAdversarialTransformSolver(object):
         different from the one assumed).
 
         3-D step count (adv_morph.py:159-162): a graph is captured per count.  The first iteration of a
-        call assumes the count the previous call started with (verified on the device by
-        advk_morph_steps_check: one scalar read after the loop; mismatch -> eager redo); every further
-        iteration reads the norm the previous replay left behind (one scalar read per iteration) and
-        replays the graph captured for exactly that count, so a count that grows during a 5- or 10-step
-        loop costs a capture the first time, not a redo."""
+        call assumes the count the previous call started with; every replay checks its count on the device
+        (advk_morph_steps_check) and publishes the verdict, with the norm it was checked against, into pinned
+        host memory as soon as its fields are built (advk_publish_verdict).  The host never waits for a replay
+        to END: it waits for that word, extrapolates the norm by one iteration, picks the graph captured for the
+        predicted count and enqueues it behind the running replay.  A replay that ran with the wrong count is
+        taken back (in-graph backup of the parameters) and repeated with the right one; a prediction within 10 %
+        of a threshold waits for the exact norm instead.  The verdict of the LAST replay is collected by
+        _graph_verified() after the end-of-loop bookkeeping (mismatch -> the loop is redone eagerly)."""
         chain = self.chain_of_transforms
         if anatomy is not None and not self.if_contains_geo_transform(chain):
             anatomy = None               # the score is only evaluated for chains with a geometric transform
@@ -670,7 +684,7 @@ class ComposeAdversarialTransformSolver(object):
                 return False
         start = [t.param.detach() for t in chain]      # the incoming tensors themselves: never written here
         if st is None:
-            st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, want_norm=False,
+            st = dict(flags=list(optimize_flags), step=step, range=rng, graphs={}, mode="single",
                       refs=[weakref.ref(model)] + [weakref.ref(t) for t in chain],
                       data=data.detach().clone(), init_output=init_output.detach().clone(),
                       params=[p.clone() for p in start],
@@ -680,8 +694,11 @@ class ComposeAdversarialTransformSolver(object):
                       viol=torch.zeros(1, dtype=torch.int32, device=data.device), viol_seen=0,
                       publish=bool(morph3d) and os.environ.get("ADVK_EARLY_VERDICT", "1") != "0", seq=torch.zeros(1, dtype=torch.int32, device=data.device), seq_host=0,
                       tok=torch.zeros(1, dtype=torch.int32).pin_memory(),
+                      normh=torch.zeros(1, dtype=torch.float32).pin_memory(),
+                      backup=[torch.empty_like(p) for p in start],
                       norm2=torch.zeros(max(len(morph3d), 1), dtype=torch.float32, device=data.device))
             st["tok_np"] = st["tok"].numpy()         # the host polls this word (same memory, no API call)
+            st["normh_np"] = st["normh"].numpy()
             self._graphs[key] = st
             while len(self._graphs) > _GRAPH_CACHE_MAX:          # least recently captured goes first
                 self._graphs.pop(next(iter(self._graphs)))
@@ -705,8 +722,19 @@ class ComposeAdversarialTransformSolver(object):
         except (AttributeError, RuntimeError):
             for buf, p in zip(st["params"], start):
                 buf.copy_(p)
-        want_norm = bool(morph3d) and n_iter > 1
-        cur, launches = nsteps, 0
+        # how the count of iterations 2.. is found (3-D, n_iter > 1): "spec" -- every replay publishes, early, the
+        # norm its step rule was checked against; the host extrapolates it by one iteration and launches the next
+        # replay behind the running one, an iteration that turns out to have run with the wrong count is taken back
+        # (in-graph backup of the parameters) and repeated, a prediction too close to a threshold waits for the
+        # exact norm instead; "norm" -- the predecessor: every replay ends with the norm of the updated velocity
+        # and the host reads it behind the replay (one full synchronisation per iteration).
+        if not morph3d or n_iter == 1:
+            mode = "single"
+        elif len(morph3d) == 1 and st["publish"] and os.environ.get("ADVK_SPECULATE", "1") != "0":
+            mode = "spec"
+        else:
+            mode = "norm"
+        cur, launches, replays = nsteps, 0, 0
 
         def fail():
             for t, p in zip(chain, start):
@@ -714,20 +742,59 @@ class ComposeAdversarialTransformSolver(object):
                 t.is_training = False
             return False
 
-        for i in range(n_iter):
-            entry = st["graphs"].get((cur, want_norm))
+        def exact_counts():
+            # the rule applied to the static parameters as they are now (waits for the stream): rare paths only
+            out = []
+            for t in morph3d:
+                n2 = _ops.morph_unorm2(st["params"][chain.index(t)], t.data_size, t._morph_cfg(), t._scale())
+                if self.shard is not None:
+                    n2 = self.shard.global_norm2(n2)
+                out.append(self._steps_from_norm2(float(n2), t.num_steps))
+            return tuple(out)
+
+        i, hist, first = 0, [], nsteps
+        while i < n_iter:
+            entry = st["graphs"].get((cur, mode))
             if entry is None:
-                entry = self._capture_iteration(model, st, morph3d, cur, want_norm, start)
+                entry = self._capture_iteration(model, st, morph3d, cur, mode, start)
                 if entry is None:
                     self._graphs[key] = False
                     return fail()
             entry[0].replay()
             st["seq_host"] += 1
+            replays += 1
             launches = entry[1]
-            if want_norm and i + 1 < n_iter:
+            if i == 0:
+                first = cur
+            if i + 1 == n_iter:
+                break                                # the last verdict is picked up by _graph_verified()
+            if mode == "norm":
                 vals = st["norm2"].tolist()                      # one scalar read: waits for the replay
                 cur = tuple(self._steps_from_norm2(v, t.num_steps) for v, t in zip(vals, morph3d))
-        self.graph_replays = getattr(self, "graph_replays", 0) + n_iter
+            elif mode == "spec":
+                count = self._await_verdict(st)                  # early in the replay that was just launched
+                if count != st["viol_seen"]:
+                    # iteration i integrated its field with the wrong count: back to its start parameters, the
+                    # count from the very norm it was checked against, and once more
+                    st["viol_seen"] = count
+                    torch._foreach_copy_(st["params"], st["backup"])
+                    again = (self._steps_from_norm2(float(st["normh_np"][0]), morph3d[0].num_steps),)
+                    self.graph_iter_redos = getattr(self, "graph_iter_redos", 0) + 1
+                    if again == cur:                 # host and device disagree about the rule: do not spin on it
+                        self._pending_check = None
+                        return fail()
+                    cur = again
+                    continue
+                hist.append(max(float(st["normh_np"][0]), 0.0) ** 0.5)
+                # the norm grows by a similar factor from one PGD step to the next: extrapolate, and only trust
+                # the extrapolation when +-10 % of it give the same count
+                ratio = (min(max(hist[-1] / hist[-2], 1.0), 2.0) if len(hist) > 1 and hist[-2] > 0.0
+                         else self.spec_first_ratio)
+                pred = hist[-1] * ratio
+                lo, mid, hi = (self._steps_from_norm2((f * pred) ** 2, morph3d[0].num_steps) for f in (0.9, 1.0, 1.1))
+                cur = (mid,) if lo == hi else exact_counts()
+            i += 1
+        self.graph_replays = getattr(self, "graph_replays", 0) + replays
         self.graph_launches_per_replay = launches
         self.last_dist = st["dist"][0]
         for t, buf in zip(chain, st["params"]):
@@ -741,7 +808,7 @@ class ComposeAdversarialTransformSolver(object):
         # the replay to finish: the iteration publishes it into pinned host memory as soon as its fields are
         # built (advk_publish_verdict), so the call returns while the last replay is still running and the next
         # call's replay is enqueued behind it -- no idle GPU between calls.
-        self._pending_check = (st if morph3d else None, morph3d, nsteps, fail)
+        self._pending_check = (st if morph3d else None, morph3d, first, fail)
         return True
 
     @staticmethod

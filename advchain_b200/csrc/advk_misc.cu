@@ -286,18 +286,25 @@ extern "C" int advk_morph_steps_check(const float* norm2, int nb_steps, int min_
 // (sequence << 8 | violations & 0xff) as ONE 32-bit word into pinned, device-mapped HOST memory, so that the host
 // can poll the word while the rest of the iteration is still running instead of synchronising behind it.
 __global__ void publish_kernel(const int* __restrict__ violations, unsigned* __restrict__ seq,
-                               volatile unsigned* host_word) {
+                               volatile unsigned* host_word, const float* __restrict__ norm2,
+                               volatile float* host_norm2) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
   const unsigned s = *seq + 1u;
   *seq = s;
+  if (norm2 && host_norm2) {                // the norm the step rule was checked against, visible BEFORE the word
+    *host_norm2 = *norm2;
+    __threadfence_system();
+  }
   *host_word = (s << 8) | ((unsigned)*violations & 0xffu);
   __threadfence_system();
 }
 
-extern "C" int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, void* stream) {
+extern "C" int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, const float* norm2,
+                                    float* host_norm2, void* stream) {
   ADVK_REQUIRE(violations && seq && host_word, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  ADVK_LAUNCH(K_publish, st, launch_pdl((publish_kernel), 1, 1, 0, st, violations, seq, (volatile unsigned*)host_word));
+  ADVK_LAUNCH(K_publish, st, launch_pdl((publish_kernel), 1, 1, 0, st, violations, seq, (volatile unsigned*)host_word,
+                                        norm2, (volatile float*)host_norm2));
   return check_launch("publish_verdict");
 }
 

@@ -237,8 +237,12 @@ int advk_morph_steps_check(const float* norm2, int nb_steps, int min_steps, int*
  * needs ONE word per call, and needs it before the iteration has finished so that the next call can be enqueued
  * behind the running one).  Increments *seq (device, 1 word) and stores (*seq << 8) | (*violations & 0xff) as one
  * 32-bit word to `host_word`, which must be pinned host memory that the device can address (cudaHostAlloc /
- * torch pin_memory under unified addressing).  The host polls that word; no stream synchronisation. */
-int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, void* stream);
+ * torch pin_memory under unified addressing).  The host polls that word; no stream synchronisation.
+ * norm2 / host_norm2 (both nullable): *norm2 (device; the sum advk_morph_field_fwd left in norm2_out, i.e. what the
+ * step rule was checked against) is stored to the pinned float host_norm2 before the word, so a host that sees the
+ * word also sees the norm: a multi-iteration loop predicts the next iteration's count from it. */
+int advk_publish_verdict(const int* violations, unsigned* seq, unsigned* host_word, const float* norm2,
+                         float* host_norm2, void* stream);
 
 /* ---- fused chain apply ---------------------------------------------------------------------
  * ONE launch applies a whole chain of transforms to an N x C x S tensor, ONE launch applies its

@@ -247,15 +247,18 @@ def test_anatomy_branch_runs_as_graph_replays():
     assert all(torch.isfinite(t.param).all() for t in chain)
 
 
-def test_graph_loop_follows_the_3d_step_count():
+@pytest.mark.parametrize("speculate", ["1", "0"])
+def test_graph_loop_follows_the_3d_step_count(speculate, monkeypatch):
     """adv_morph.py:159-162: in 3-D the number of squaring steps follows the norm of the velocity field,
-    which grows during the PGD loop.  The graph loop reads that norm between replays and replays the graph
-    captured for exactly that count (no redo); the count ASSUMED for the first iteration of a later call
-    is verified on the device, and a stale one makes the loop redo itself eagerly.  Either way the result
-    is the eager loop's."""
+    which grows during the PGD loop.  The graph loop predicts the count of the next iteration from the norms the
+    replays publish, every replay verifies its own count on the device, an iteration that ran with the wrong one
+    is taken back and repeated (graph_iter_redos), and the count ASSUMED for the first iteration of a later
+    call, if stale in a one-iteration call, makes the loop redo itself eagerly.  Either way the result is the
+    eager loop's.  ADVK_SPECULATE=0 selects the predecessor (exact norm read behind every replay)."""
     from advchain_b200.augmentor import AdvMorph, ComposeAdversarialTransformSolver
     from advchain_b200.augmentor import _ops
     from tests.golden.cases import stage_cfgs
+    monkeypatch.setenv("ADVK_SPECULATE", speculate)
     dev = torch.device("cuda:0")
     size = [1, 1, 24, 24, 24]
     cfg = stage_cfgs(3, size, vector=[3, 3, 3])["morph"]
@@ -288,7 +291,8 @@ def test_graph_loop_follows_the_3d_step_count():
         ts.append(t)
     gsol = sols[1][0]
     assert getattr(gsol, "graph_redos", 0) == 0
-    assert getattr(gsol, "graph_replays", 0) == 3
+    assert getattr(gsol, "graph_replays", 0) == 3 + getattr(gsol, "graph_iter_redos", 0)
+    assert getattr(gsol, "graph_iter_redos", 0) <= 1
     counts = set(k[0] for v in gsol._graphs.values() if isinstance(v, dict) for k in v["graphs"])
     assert len(counts) >= 2, counts                       # the count grew inside the loop: two graphs
     assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
@@ -301,6 +305,49 @@ def test_graph_loop_follows_the_3d_step_count():
         res.append(t.param.detach().clone())
     assert getattr(gsol, "graph_redos", 0) == 1
     assert float((res[1] - res[0]).norm() / res[0].norm()) < 2e-3
+
+
+def test_graph_loop_takes_back_a_mispredicted_iteration():
+    """Speculative multi-iteration loop: the host predicts that the second iteration keeps the count of the first
+    (spec_first_ratio = 1: no growth), the velocity grows across the 0.5 threshold, the replay finds its count
+    wrong on the device, and the loop restores the parameters that iteration started from (in-graph backup) and
+    repeats it with the count of the norm the replay published.  The result is the eager loop's."""
+    from advchain_b200.augmentor import AdvMorph, ComposeAdversarialTransformSolver
+    from advchain_b200.augmentor import _ops
+    from tests.golden.cases import stage_cfgs
+    dev = torch.device("cuda:0")
+    size = [1, 1, 24, 24, 24]
+    cfg = stage_cfgs(3, size, vector=[3, 3, 3])["morph"]
+    torch.manual_seed(5)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv3d(1, 3, 3, 1, 1).eval().to(dev)
+    probe = AdvMorph(3, dict(cfg), device=dev)
+    probe.init_parameters()
+    v0 = probe.param.detach().clone()
+    n2 = float(_ops.morph_unorm2(v0, size, probe._morph_cfg(), 1.0).item()) ** 0.5
+    eps = 0.40 * 256.0 / n2                   # +-10 % of 0.40 stay below 0.5: the host is sure of 8 steps
+    outs, gsol = [], None
+    for graph in (False, True):
+        c = dict(cfg)
+        c["epsilon"] = eps
+        t = AdvMorph(3, c, device=dev)
+        sol = ComposeAdversarialTransformSolver([t], divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0
+        sol.spec_first_ratio = 1.0
+        init = sol.get_init_output(conv, x)
+        t.init_parameters()
+        t.param = v0.clone()
+        assert t._nb_steps() == 8
+        sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True], n_iter=3,
+                                 step_sizes=[1.0])
+        outs.append(t.param.detach().clone())
+        gsol = sol
+    assert getattr(gsol, "graph_iter_redos", 0) >= 1, "the velocity did not cross the threshold: adjust eps"
+    assert getattr(gsol, "graph_redos", 0) == 0
+    assert getattr(gsol, "graph_replays", 0) == 3 + gsol.graph_iter_redos
+    assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
 
 
 def test_graph_loop_early_verdict_sequence():
