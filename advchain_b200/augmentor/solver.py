@@ -75,7 +75,7 @@ class ComposeAdversarialTransformSolver(object):
         self._graphs = _GRAPH_CACHE      # shared by all solvers: training loops build a solver per step
         self._fwd_mask = None             # (chain key, forward valid-region mask N x 1 x spatial)
         self.graph_capture_after = 1      # eager runs of a configuration before it is captured
-        self.spec_first_ratio = 1.6       # assumed growth of |u| over the FIRST PGD step (later ones: measured)
+        self.spec_first_ratio = 4.0       # headroom asked of |u| before the FIRST PGD step's count is predicted
         self.overlap_field_builds = os.environ.get("ADVK_OVERLAP_FIELDS", "1") != "0"   # graph loop only
         self._mask_cache = None           # (chain key, binarised mask after the warp-back)
 
@@ -753,6 +753,7 @@ class ComposeAdversarialTransformSolver(object):
             return tuple(out)
 
         i, hist, first = 0, [], nsteps
+        trace = self.spec_trace = []     # (iteration, |u| seen, band low, band high, count chosen, predicted?) of this call
         while i < n_iter:
             entry = st["graphs"].get((cur, mode))
             if entry is None:
@@ -766,7 +767,7 @@ class ComposeAdversarialTransformSolver(object):
             launches = entry[1]
             if i == 0:
                 first = cur
-            if i + 1 == n_iter:
+            if i + 1 == n_iter and mode != "spec":
                 break                                # the last verdict is picked up by _graph_verified()
             if mode == "norm":
                 vals = st["norm2"].tolist()                      # one scalar read: waits for the replay
@@ -785,14 +786,21 @@ class ComposeAdversarialTransformSolver(object):
                         return fail()
                     cur = again
                     continue
+                if i + 1 == n_iter:
+                    break                            # (the last replay is verified, early, like the others)
                 hist.append(max(float(st["normh_np"][0]), 0.0) ** 0.5)
-                # the norm grows by a similar factor from one PGD step to the next: extrapolate, and only trust
-                # the extrapolation when +-10 % of it give the same count
-                ratio = (min(max(hist[-1] / hist[-2], 1.0), 2.0) if len(hist) > 1 and hist[-2] > 0.0
-                         else self.spec_first_ratio)
-                pred = hist[-1] * ratio
-                lo, mid, hi = (self._steps_from_norm2((f * pred) ** 2, morph3d[0].num_steps) for f in (0.9, 1.0, 1.1))
-                cur = (mid,) if lo == hi else exact_counts()
+                # |u| grows by a similar AMOUNT from one PGD step to the next (v <- v + unit(g)): extrapolate
+                # linearly and only trust the prediction when half and one-and-a-half of that increment give the
+                # same count; the first step (no increment known yet; the update can be much smoother than the
+                # random start, i.e. survive the Gaussian much better) needs spec_first_ratio of headroom
+                if len(hist) > 1:
+                    d = max(hist[-1] - hist[-2], 0.0)
+                    lo_n, hi_n = hist[-1] + 0.5 * d, 1.02 * hist[-1] + 1.5 * d
+                else:
+                    lo_n, hi_n = hist[-1], hist[-1] * self.spec_first_ratio
+                lo, hi = (self._steps_from_norm2(v * v, morph3d[0].num_steps) for v in (lo_n, hi_n))
+                cur = (lo,) if lo == hi else exact_counts()
+                trace.append((i + 1, round(hist[-1], 3), round(lo_n, 3), round(hi_n, 3), cur[0], lo == hi))
             i += 1
         self.graph_replays = getattr(self, "graph_replays", 0) + replays
         self.graph_launches_per_replay = launches
@@ -808,7 +816,12 @@ class ComposeAdversarialTransformSolver(object):
         # the replay to finish: the iteration publishes it into pinned host memory as soon as its fields are
         # built (advk_publish_verdict), so the call returns while the last replay is still running and the next
         # call's replay is enqueued behind it -- no idle GPU between calls.
-        self._pending_check = (st if morph3d else None, morph3d, first, fail)
+        if mode == "spec":
+            self._pending_check = None               # every replay of the loop has been verified already
+            for t, n in zip(morph3d, first):
+                t._last_nb_steps = n
+        else:
+            self._pending_check = (st if morph3d else None, morph3d, first, fail)
         return True
 
     @staticmethod

@@ -52,3 +52,4 @@ print("%s n_iter %d ADVK_SPECULATE=%s: %.4f ms per inner iteration (%.1f it/s), 
           wl, n_iter, os.environ.get("ADVK_SPECULATE", "1"), ms / (calls * n_iter), 1e3 * calls * n_iter / ms,
           getattr(sol, "graph_replays", 0) - r0, calls * n_iter, getattr(sol, "graph_iter_redos", 0),
           getattr(sol, "graph_redos", 0)))
+print("   last call (iteration, |u| of the previous one, band, count, predicted): %s" % (getattr(sol, "spec_trace", None),))
