@@ -1078,9 +1078,9 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
 #undef ADVK_LB
 #undef ADVK_LB1
   if (split) {
-    // ~16 CTAs per SM over the whole batch (4 per SM ran at 1.7 TB/s: 18.9 us for 32 MB, gpurun_out/r02u);
-    // every CTA ends in d(d+1) atomics on its sample's gradient
-    unsigned gx = (unsigned)((lean_sms() * 16 + P.g.N - 1) / P.g.N);
+    // ~4 CTAs per SM over the whole batch, 4 loads in flight per thread (lean_theta_reduce_kernel); every CTA ends
+    // in d(d+1) atomics on its sample's gradient
+    unsigned gx = (unsigned)((lean_sms() * 4 + P.g.N - 1) / P.g.N);
     if (gx > (unsigned)P.tps) gx = (unsigned)P.tps;
     if (gx < 1) gx = 1;
     const KernelId kid = P.pack ? K_chain_pk_bwd : K_chain_img_bwd;

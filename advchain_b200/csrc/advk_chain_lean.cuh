@@ -681,17 +681,35 @@ lean_theta_reduce_kernel(Dims g, const void* __restrict__ gc, float* __restrict_
   float acc[NG];
 #pragma unroll
   for (int i = 0; i < NG; ++i) acc[i] = 0.f;
-#pragma unroll 4
-  for (int p = blockIdx.x * 256 + threadIdx.x; p < S; p += gridDim.x * 256) {      // (loads of 4 trips in flight)
-    int x, y, z;
-    voxel_xyz(g, (unsigned)p, x, y, z);
-    const float bx = base_coord_s(x, g.W, g.stW, 0.f), by = base_coord_s(y, g.H, g.stH, 0.f);
-    if (DIM == 2) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(gc) + nS + p);
-      lean_theta_acc<DIM>(acc, v.x, v.y, 0.f, bx, by, 0.f);
-    } else {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(gc) + nS + p);
-      lean_theta_acc<DIM>(acc, v.x, v.y, v.z, bx, by, base_coord_s(z, g.D, g.stD, 0.f));
+  // 4 CTAs per SM; every thread keeps the loads of FOUR grid-strided voxels in flight before it touches any of
+  // them (one load per trip ran at 1.7 TB/s: 18.9 us for 32 MB at 128^3, gpurun_out/r02u; more, smaller CTAs
+  // instead -- 16 per SM, 3.5 trips each, a block reduction and d(d+1) atomics behind every one -- ran at 0.8
+  // TB/s: 40.4 us, profiles/r02A_launch_list.md).  A voxel past the end loads nothing and adds zeros.
+  const int stride = gridDim.x * 256;
+  for (int p0 = blockIdx.x * 256 + threadIdx.x; p0 < S; p0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const i64 p = (i64)p0 + (i64)k * stride;               // (S can sit just below 2^31)
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < (i64)S) {
+        if (DIM == 2) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(gc) + nS + p);
+          v[k].x = t.x; v[k].y = t.y;
+        } else {
+          v[k] = __ldg(reinterpret_cast<const float4*>(gc) + nS + p);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const i64 pl = (i64)p0 + (i64)k * stride;
+      const int p = pl < (i64)S ? (int)pl : S - 1;
+      int x, y, z;
+      voxel_xyz(g, (unsigned)p, x, y, z);
+      const float bx = base_coord_s(x, g.W, g.stW, 0.f), by = base_coord_s(y, g.H, g.stH, 0.f);
+      const float bz = DIM == 3 ? base_coord_s(z, g.D, g.stD, 0.f) : 0.f;
+      lean_theta_acc<DIM>(acc, v[k].x, v[k].y, DIM == 3 ? v[k].z : 0.f, bx, by, bz);
     }
   }
   lean_theta_flush<DIM>(acc, red, g_theta, n);
