@@ -276,3 +276,23 @@ def test_every_pdl_launched_kernel_waits_for_its_predecessors():
     for f, text in srcs.items():
         for m in re.finditer(r"(\w+)(?:<[^<>]*>)?\s*<<<", text):
             assert m.group(1) in ("chain_fwd_stage_kernel", "chain_bwd_stage_kernel"), (f, m.group(1))
+
+
+def test_step_count_rule_on_the_host_is_the_device_rule():
+    """adv_morph.py:159-162 as the graph loop applies it on the host to a published |u|^2 (speculative
+    multi-iteration loop, take-back of a mispredicted iteration): smallest n >= 8 with |u| / 2^n <= 0.5, evaluated
+    in fp32 like steps_check_kernel (sqrtf, exact division by a power of two) and agreeing with the oracle's loop."""
+    import numpy as np
+    from advchain_b200.augmentor.solver import ComposeAdversarialTransformSolver as S
+    from oracle import advchain_oracle as orc
+    assert S._steps_from_norm2(0.0, 8) == 8
+    assert S._steps_from_norm2(128.0 ** 2, 8) == 8            # exactly 0.5 is not above the threshold
+    assert S._steps_from_norm2(np.nextafter(np.float32(128.0 ** 2), np.float32(np.inf)), 8) in (8, 9)
+    assert S._steps_from_norm2(128.5 ** 2, 8) == 9
+    assert S._steps_from_norm2(256.0 ** 2, 8) == 9
+    assert S._steps_from_norm2(257.0 ** 2, 8) == 10
+    assert S._steps_from_norm2(float("nan"), 8) == 8           # a NaN norm never loops (the NaN guard handles the step)
+    torch.manual_seed(2)
+    for scale in (1.0, 40.0, 400.0):
+        u = torch.randn(1, 3, 8, 8, 8) * scale
+        assert S._steps_from_norm2(float((u ** 2).sum()), 8) == orc.ss_steps_for(u)
