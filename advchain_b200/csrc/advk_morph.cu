@@ -391,16 +391,6 @@ ss_step_lean_kernel(Dims g, const typename V<DIM>::T* __restrict__ in, typename 
   }
 }
 
-static int morph_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaDeviceProp pr;
-    sms = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess) ? pr.multiProcessorCount : 148;
-  }
-  return sms;
-}
-
 // A CTA of the tile adjoint owns a 32 (x) x 8 (y) tile of one z plane, one warp per row: block index ->
 // (tile x, tile y, z) by multiply-high division.
 struct TileMap {
@@ -412,57 +402,6 @@ static TileMap make_tilemap(const Dims& g) {
   tm.tx = (g.W + 31) / 32; tm.ty = (g.H + 7) / 8;
   tm.ftx = make_fastdiv((unsigned)tm.tx); tm.fty = make_fastdiv((unsigned)tm.ty);
   return tm;
-}
-
-// Persistent form of the lean forward step (advk_morph_tune bit 6): 6 CTAs per SM walk the 256-voxel blocks and
-// every thread loads phi(p) of its NEXT block before it gathers for the current one (the first of the voxel's two
-// dependent round trips hidden; 4 more registers).  Same arithmetic as ss_step_lean_kernel<DIM, false>.
-template <int DIM>
-__global__ void __launch_bounds__(256, 6)
-ss_step_pf_kernel(Dims g, unsigned n_blocks, const typename V<DIM>::T* __restrict__ in,
-                  typename V<DIM>::T* __restrict__ out) {
-  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
-  typedef typename V<DIM>::T T;
-  const i64 nb = (i64)blockIdx.y * g.S;
-  const T* src = opaque_ptr(in + nb);
-  T* dstp = opaque_ptr(out + nb);
-  const int HW = g.H * g.W;
-  const int S = (int)g.S;
-  unsigned b = blockIdx.x;
-  int p = (int)(b * 256u + threadIdx.x);
-  T f = V<DIM>::make(0.f, 0.f, 0.f);
-  if (b < n_blocks && p < S) f = __ldg(src + p);
-  for (; b < n_blocks; b += gridDim.x) {
-    const unsigned bn = b + gridDim.x;
-    const int pn = (int)(bn * 256u + threadIdx.x);
-    T fn = V<DIM>::make(0.f, 0.f, 0.f);
-    if (bn < n_blocks && pn < S) fn = __ldg(src + pn);
-    if (p < S) {
-      Axis ax = make_axis_border(f.x, g.W);
-      Axis ay = make_axis_border(f.y, g.H);
-      Axis az;
-      if (DIM == 3) az = make_axis_border(V<DIM>::z(f), g.D);
-      else { az.i0 = 0; az.w0 = 1.f; az.w1 = 0.f; az.v0 = true; az.v1 = false; }
-      const int dxo = ax.v1 ? 1 : 0, dyo = ay.v1 ? g.W : 0, dzo = (DIM == 3 && az.v1) ? HW : 0;
-      const T* c000 = src + (az.i0 * HW + ay.i0 * g.W + ax.i0);
-      float ox = 0.f, oy = 0.f, oz = 0.f;
-#pragma unroll
-      for (int dz = 0; dz < (DIM == 3 ? 2 : 1); ++dz) {
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const T s = __ldg(c000 + (dz * dzo + dy * dyo + dx * dxo));
-            const float w = (dx ? ax.w1 : ax.w0) * (dy ? ay.w1 : ay.w0) * (dz ? az.w1 : az.w0);
-            ox += s.x * w; oy += s.y * w;
-            if (DIM == 3) oz += V<DIM>::z(s) * w;
-          }
-        }
-      }
-      dstp[p] = V<DIM>::make(ox, oy, oz);
-    }
-    f = fn; p = pn;
-  }
 }
 
 // Backward of one squaring step phi_k = phi_{k-1} o phi_{k-1}:
@@ -793,74 +732,23 @@ ss_step_bwd_tile_kernel(Dims g, TileMap tm, const typename V<DIM>::T* __restrict
   ssb_tile_voxel<DIM, ZS>(g, src, dst, upn, f, go, live, p, lane, row, hand_s);
 }
 
-// Persistent form of the tile adjoint (advk_morph_tune bit 4): 4 CTAs per SM walk the tiles, and every thread
-// issues the loads of phi(p), g(p) of its NEXT tile before it works on the current one -- the first of the
-// voxel's two dependent round trips is then hidden behind the previous voxel's work (8 more registers, a
-// double-buffered hand-off so that one barrier per tile is still enough).
-template <int DIM, bool ZS>
-__global__ void __launch_bounds__(256, 4)
-ss_step_bwd_ptile_kernel(Dims g, TileMap tm, unsigned n_tiles, const typename V<DIM>::T* __restrict__ phi_prev,
-                         typename V<DIM>::T* up, typename V<DIM>::T* __restrict__ out) {
-  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
-  typedef typename V<DIM>::T T;
-  constexpr int NZ = DIM == 3 ? 2 : 1;
-  __shared__ float4 hand_s[2][NZ][8][32];
-  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  const i64 nb = (i64)blockIdx.y * g.S;
-  const T* src = opaque_ptr(phi_prev + nb);
-  T* dst = opaque_ptr(out + nb);
-  T* upn = opaque_ptr(up + nb);
-  unsigned b = blockIdx.x;
-  bool live = false;
-  int p = 0;
-  T f = V<DIM>::make(0.f, 0.f, 0.f), go = V<DIM>::make(0.f, 0.f, 0.f);
-  if (b < n_tiles) {
-    const unsigned q = fast_div(b, tm.ftx);
-    const int txi = (int)(b - q * (unsigned)tm.tx);
-    const unsigned z = fast_div(q, tm.fty);
-    const int tyi = (int)(q - z * (unsigned)tm.ty);
-    const int x = txi * 32 + lane, y = tyi * 8 + row;
-    live = x < g.W && y < g.H;
-    p = live ? ((int)z * g.H + y) * g.W + x : 0;
-    if (live) { f = __ldg(src + p); go = upn[p]; }
-  }
-  for (int it = 0; b < n_tiles; b += gridDim.x, ++it) {
-    const unsigned bn = b + gridDim.x;
-    bool liven = false;
-    int pn = 0;
-    T fn = V<DIM>::make(0.f, 0.f, 0.f), gon = V<DIM>::make(0.f, 0.f, 0.f);
-    if (bn < n_tiles) {
-      const unsigned q = fast_div(bn, tm.ftx);
-      const int txi = (int)(bn - q * (unsigned)tm.tx);
-      const unsigned z = fast_div(q, tm.fty);
-      const int tyi = (int)(q - z * (unsigned)tm.ty);
-      const int x = txi * 32 + lane, y = tyi * 8 + row;
-      liven = x < g.W && y < g.H;
-      pn = liven ? ((int)z * g.H + y) * g.W + x : 0;
-      if (liven) { fn = __ldg(src + pn); gon = upn[pn]; }
-    }
-    ssb_tile_voxel<DIM, ZS>(g, src, dst, upn, f, go, live, p, lane, row, hand_s[it & 1]);
-    f = fn; go = gon; live = liven; p = pn;
-  }
-}
-
 // advk_morph_tune / ADVK_SSB_MODE: bit 0 = the plain predecessors of the lean squaring-step kernels
 // (predicated forward step, one-RED-per-corner adjoint with memset nodes); bit 1 = the two-launch predecessor
 // (smooth3d_xy + smooth3d_z) of the TMA-staged 3-D smoothing kernel (advk_smooth_tma.cuh); bit 2 = the lean
 // adjoint zeroes its consumed buffer itself (predecessor of the side-stream memsets, field_bwd); bit 3 = the tile
 // adjoint with the y hand-off through shared memory (ss_step_bwd_tile_kernel) whatever the geometry (default: where
-// the 32 x 8 tiles are at least 97 % full); bit 4 = the tile adjoint as a persistent kernel that prefetches the next
-// tile's phi(p), g(p) (ss_step_bwd_ptile_kernel); bit 5 = the lean linear adjoint whatever the geometry; bit 6 = the
-// forward step as a persistent kernel that prefetches the next block's phi(p) (ss_step_pf_kernel).  Default 0.
+// the 32 x 8 tiles are at least 97 % full); bit 5 = the lean linear adjoint whatever the geometry.  Default 0.
 // Measured and removed (gpurun_out/r02w, r02y): the forward step on 32 x 8 tiles (1.16
 // instead of 1.5 L1 fills per voxel: 2 % slower), and the x1 corners of either step taken from the neighbour lane
 // by shuffle (4 gathers instead of 8: forward +1.1 %, adjoint +1.8 % of the whole iteration, and not bit-identical
-// because the weight products associate differently).
+// because the weight products associate differently); persistent forms that load phi(p), g(p) of their NEXT tile
+// before they work on the current one (the adjoint at 64 registers / 4 CTAs per SM: 745 against 713 us per 16
+// launches; the forward step at 40 registers / 6 CTAs: no change -- gpurun_out/r02D).
 static int g_ssb_mode = -1;
 static int ssb_mode() {
   if (g_ssb_mode < 0) {
     const char* e = getenv("ADVK_SSB_MODE");
-    g_ssb_mode = e ? (atoi(e) & 127) : 0;
+    g_ssb_mode = e ? (atoi(e) & 63) : 0;
   }
   return g_ssb_mode;
 }
@@ -915,15 +803,6 @@ static void launch_ss_step_bwd(const Dims& g, const typename V<DIM>::T* phi_prev
   const bool tile_fits = (i64)g.W * g.H * 100 >= (i64)97 * (tm.tx * 32) * (tm.ty * 8);
   if ((ssb_mode() & 1) == 0 && ((ssb_mode() & 8) || (tile_fits && !(ssb_mode() & 32)))) {
     dim3 tg((unsigned)((i64)tm.tx * tm.ty * g.D), g.N);
-    if (ssb_mode() & 16) {                              // persistent, next tile's loads in flight
-      const unsigned n_tiles = tg.x;
-      unsigned gx = (unsigned)((morph_sms() * 4 + g.N - 1) / g.N);
-      if (gx > n_tiles) gx = n_tiles;
-      dim3 pg(gx, g.N);
-      if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_ptile_kernel<DIM, true>), pg, 256, 0, st, g, tm, n_tiles, phi_prev, up, out)));
-      else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_ptile_kernel<DIM, false>), pg, 256, 0, st, g, tm, n_tiles, phi_prev, up, out)));
-      return;
-    }
     if (may_zero_up) ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, true>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
     else ADVK_LAUNCH(K_ss_step_bwd, st, (launch_pdl((ss_step_bwd_tile_kernel<DIM, false>), tg, 256, 0, st, g, tm, phi_prev, up, out)));
     return;
@@ -1322,12 +1201,6 @@ static int field_fwd(const Dims& g, const MorphCfg& c, const float* v, float sca
   for (int k = 1; k <= nb; ++k) {
     if (lean && fused && k == nb)
       ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, true>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, L, L + (nb + 1) * F)));
-    else if (lean && (ssb_mode() & 64)) {
-      const unsigned n_blocks = grid.x;
-      unsigned gx = (unsigned)((morph_sms() * 6 + g.N - 1) / g.N);
-      if (gx > n_blocks) gx = n_blocks;
-      ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_pf_kernel<DIM>), dim3(gx, g.N), 256, 0, st, g, n_blocks, L + (k - 1) * F, L + k * F)));
-    }
     else if (lean) ADVK_LAUNCH(K_ss_step, st, (launch_pdl((ss_step_lean_kernel<DIM, false>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F, nullptr, nullptr)));
     else ADVK_LAUNCH(K_ss_step, st, launch_pdl((ss_step_kernel<DIM>), grid, 256, 0, st, g, L + (k - 1) * F, L + k * F));
   }
@@ -1428,7 +1301,7 @@ using namespace advk;
 
 extern "C" int advk_morph_tune(int ssb_mode_mask) {
   int prev = ssb_mode();
-  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 127;
+  if (ssb_mode_mask >= 0) g_ssb_mode = ssb_mode_mask & 63;
   return prev;
 }
 

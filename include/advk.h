@@ -178,10 +178,7 @@ int advk_morph_field_bwd(const advk_geom* g, const advk_morph_cfg* cfg, float sc
  *   bit 3: force the adjoint on 32 x 8 tiles (one warp per row) with a second hand-off along y through shared
  *          memory: 2 corner REDs + the Jacobian RED per voxel instead of 4 + 1.  Default: used where the tiles are
  *          at least 97 % full (W, H multiples of 32, 8 or large), the lean linear kernel elsewhere.
- *   bit 4: the tile adjoint as a persistent kernel (4 CTAs per SM) whose threads load phi(p), g(p) of their next
- *          tile before they work on the current one.
  *   bit 5: force the lean linear adjoint.
- *   bit 6: the forward step as a persistent kernel (6 CTAs per SM) that loads phi(p) of its next block early.
  * Environment ADVK_SSB_MODE.  Results agree up to fp32 summation order.  A negative mask only queries;
  * returns the previous mask. */
 int advk_morph_tune(int ssb_mode_mask);
