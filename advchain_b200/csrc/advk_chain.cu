@@ -1030,6 +1030,15 @@ static bool lean_theta_split(bool pack) {
   }
   return g_lean_theta >= 2 || (g_lean_theta == 1 && pack);
 }
+// Sheared traversal of the affine adjoints (lean_shear, advk_chain_lean.cuh).  ADVK_LEAN_SHEAR: 0 / 1.
+static int g_lean_shear = -1;
+static bool lean_shear_on() {
+  if (g_lean_shear < 0) {
+    const char* e = getenv("ADVK_LEAN_SHEAR");
+    g_lean_shear = e ? (atoi(e) != 0) : 0;
+  }
+  return g_lean_shear != 0;
+}
 static int g_lean_minb_aff = -2;
 static int lean_minb_affine(bool pack) {      // register budget of the split affine adjoints (ADVK_LEAN_MINB_AFFINE)
   if (g_lean_minb_aff == -2) {
@@ -1048,6 +1057,7 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
   a.src = s.src; a.g_dst = s.g_dst; a.g_src = s.g_src; a.phi = s.phi; a.theta = s.theta;
   a.g_phi = s.g_phi; a.g_theta = s.g_theta;
   a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
+  a.shear = (!FIELD && lean_shear_on()) ? 1 : 0;
   unsigned grid = (unsigned)P.n_tiles;
   const bool split = !FIELD && s.g_theta && P.g_coord && lean_theta_split(P.pack != 0);
   if (split) { a.g_phi = P.g_coord; a.g_theta = nullptr; }
