@@ -1022,6 +1022,10 @@ static int lean_minb(bool field, bool pack) {
 // 214.9 -> 177.3 us with the split, C = 1 image chain adjoint 128.9 -> 135.4 us (its affine stage is bound by the
 // sectors a rotated line of scalar REDs touches, 6.5 M against 1.9 M for the field stage, not by registers).
 // ADVK_LEAN_THETA: 0 = never split, 1 = packed chains only (default), 2 = always.
+// (Measured and removed, gpurun_out/r02F / r02G: a SHEARED traversal of the affine adjoints -- the volume walked along
+// the direction the affine map sends to the source x axis, so that a warp's gathers and REDs fall on an axis-aligned
+// source line -- parity green, but 4-8 us slower per kernel, with exact or approximate divisions alike: the upstream
+// reads and coordinate-gradient writes along slanted output rows cost more than the aligned source rows return.)
 static int g_lean_theta = -1;
 static bool lean_theta_split(bool pack) {
   if (g_lean_theta < 0) {
@@ -1029,15 +1033,6 @@ static bool lean_theta_split(bool pack) {
     g_lean_theta = e ? atoi(e) : 1;
   }
   return g_lean_theta >= 2 || (g_lean_theta == 1 && pack);
-}
-// Sheared traversal of the affine adjoints (lean_shear, advk_chain_lean.cuh).  ADVK_LEAN_SHEAR: 0 / 1.
-static int g_lean_shear = -1;
-static bool lean_shear_on() {
-  if (g_lean_shear < 0) {
-    const char* e = getenv("ADVK_LEAN_SHEAR");
-    g_lean_shear = e ? (atoi(e) != 0) : 0;
-  }
-  return g_lean_shear != 0;
 }
 static int g_lean_minb_aff = -2;
 static int lean_minb_affine(bool pack) {      // register budget of the split affine adjoints (ADVK_LEAN_MINB_AFFINE)
@@ -1057,7 +1052,6 @@ static void lean_launch_warp_bwd(const Program& P, const Stage& s, int k, cudaSt
   a.src = s.src; a.g_dst = s.g_dst; a.g_src = s.g_src; a.phi = s.phi; a.theta = s.theta;
   a.g_phi = s.g_phi; a.g_theta = s.g_theta;
   a.clamp = (last && P.do_clamp) ? 1 : 0; a.lo = P.lo; a.hi = P.hi;
-  a.shear = (!FIELD && lean_shear_on()) ? 1 : 0;
   unsigned grid = (unsigned)P.n_tiles;
   const bool split = !FIELD && s.g_theta && P.g_coord && lean_theta_split(P.pack != 0);
   if (split) { a.g_phi = P.g_coord; a.g_theta = nullptr; }

@@ -370,50 +370,6 @@ lean_intensity_rows_kernel(const __grid_constant__ LeanInt a) {
   }
 }
 
-// Sheared traversal of an affine stage (LeanBwd::shear).  A warp owns 32 consecutive x of one output row; under a
-// rotation the positions it samples lie on a slanted line, so every gather and every RED of the warp touches 10-12
-// sectors where an axis-aligned line touches 4 (6.5 M RED sectors against 1.9 M for the field stage of the same
-// stencil, profiles/r02C_ncu_full.md).  The output volume is therefore walked along the direction that the affine
-// map sends to the SOURCE x axis: the thread of linear voxel (x, yv, zv) works on (x, yv + round(a x), zv + round(b x))
-// (indices modulo H, D: a bijection of the volume, every voxel is still processed exactly once), with (1, a, b)
-// solving P[y].(1,a,b) = P[z].(1,a,b) = 0 for the pixel-space linear part P of theta.  |a|, |b| > 1 (more than
-// 45 degrees) or a singular system: no shear.
-template <int DIM>
-__device__ __forceinline__ int lean_shear(const Dims& g, const float* __restrict__ th, int p) {
-  int x, y, z;
-  voxel_xyz(g, (unsigned)p, x, y, z);
-  if (g.W < 2) return p;
-  const float nx = (float)(g.W - 1), ny = (float)(g.H - 1), nz = (float)(g.D - 1);
-  float sa = 0.f, sb = 0.f;
-  if (DIM == 2) {
-    const float P10 = __ldg(th + 3) * ny / nx, P11 = __ldg(th + 4);
-    sa = -P10 / P11;
-    if (!(fabsf(sa) <= 1.f)) sa = 0.f;
-  } else {
-    const float P10 = __ldg(th + 4) * ny / nx, P11 = __ldg(th + 5), P12 = nz > 0.f ? __ldg(th + 6) * ny / nz : 0.f;
-    const float P20 = __ldg(th + 8) * nz / nx, P21 = ny > 0.f ? __ldg(th + 9) * nz / ny : 0.f, P22 = __ldg(th + 10);
-    const float det = P11 * P22 - P12 * P21;
-    sa = (P12 * P20 - P10 * P22) / det;
-    sb = (P21 * P10 - P11 * P20) / det;
-    if (!(fabsf(sa) <= 1.f) || !(fabsf(sb) <= 1.f)) { sa = 0.f; sb = 0.f; }
-  }
-  {
-    const float yf = (float)y + rintf(sa * (float)x), h = (float)g.H;
-    int yy = (int)(yf - h * floorf(yf / h));
-    if (yy < 0) yy += g.H;
-    if (yy >= g.H) yy -= g.H;
-    y = yy;
-  }
-  if (DIM == 3) {
-    const float zf = (float)z + rintf(sb * (float)x), dd = (float)g.D;
-    int zz = (int)(zf - dd * floorf(zf / dd));
-    if (zz < 0) zz += g.D;
-    if (zz >= g.D) zz -= g.D;
-    z = zz;
-  }
-  return (z * g.H + y) * g.W + x;
-}
-
 // ------------------------------------------------------------------------------------------- adjoint
 
 struct LeanBwd {
@@ -421,7 +377,6 @@ struct LeanBwd {
   const float* src; const float* g_dst; float* g_src;
   const void* phi; const float* theta; void* g_phi; float* g_theta;
   int clamp; float lo, hi;
-  int shear;                                     // affine stages: sheared traversal (lean_shear)
 };
 
 // separable Jacobian of the interpolated value from the 2^d corner values v (already multiplied by the
@@ -513,9 +468,8 @@ lean_warp_bwd_kernel(const __grid_constant__ LeanBwd a) {
   int cur_n = -1;
   for (unsigned t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int n = (int)fast_div(t, a.ftps);
-    int p = (int)(t - (unsigned)n * (unsigned)a.tps) * 256 + threadIdx.x;
+    const int p = (int)(t - (unsigned)n * (unsigned)a.tps) * 256 + threadIdx.x;
     const bool ok = p < S;
-    if (!FIELD && a.shear && ok) p = lean_shear<DIM>(a.g, a.theta + n * NG, p);
     if (want_theta && n != cur_n) {              // block-uniform
       if (cur_n >= 0) lean_theta_flush<DIM>(acc, red, a.g_theta, cur_n);
       cur_n = n;
@@ -614,9 +568,8 @@ lean_warp_bwd_pk_kernel(const __grid_constant__ LeanBwd a) {
   int cur_n = -1;
   for (unsigned t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int n = (int)fast_div(t, a.ftps);
-    int p = (int)(t - (unsigned)n * (unsigned)a.tps) * 256 + threadIdx.x;
+    const int p = (int)(t - (unsigned)n * (unsigned)a.tps) * 256 + threadIdx.x;
     const bool ok = p < S;
-    if (!FIELD && a.shear && ok) p = lean_shear<DIM>(a.g, a.theta + n * NG, p);
     if (want_theta && n != cur_n) {
       if (cur_n >= 0) lean_theta_flush<DIM>(acc, red, a.g_theta, cur_n);
       cur_n = n;
