@@ -355,6 +355,46 @@ def test_graph_loop_takes_back_a_mispredicted_iteration():
     assert float((outs[1] - outs[0]).norm() / outs[0].norm()) < 2e-3
 
 
+def test_graph_loop_without_early_verdict(monkeypatch):
+    """ADVK_EARLY_VERDICT=0: the predecessor of the published verdict -- the call synchronises behind its last replay
+    and reads the violation counter, a multi-iteration 3-D loop reads the exact norm behind every replay ("norm"
+    graphs).  Same result as the eager loop; kept as the A/B of DESIGN.md section 4 and as the fallback."""
+    from advchain_b200.augmentor import AdvMorph, AdvNoise, ComposeAdversarialTransformSolver
+    from tests.golden.cases import stage_cfgs
+    monkeypatch.setenv("ADVK_EARLY_VERDICT", "0")
+    dev = torch.device("cuda:0")
+    size = [1, 1, 24, 32, 40]
+    cfgs = stage_cfgs(3, size, vector=[3, 4, 5])
+    torch.manual_seed(13)
+    x = torch.rand(*size, device=dev)
+    conv = torch.nn.Conv3d(1, 3, 3, 1, 1).eval().to(dev)
+    start, res, st = None, [], None
+    for graph in (False, True):
+        ts = [AdvNoise(3, cfgs["noise"], device=dev), AdvMorph(3, cfgs["morph"], device=dev)]
+        sol = ComposeAdversarialTransformSolver(ts, divergence_types=["mse", "contour"], divergence_weights=[1.0, 0.5],
+                                                if_norm_image=True, min_intensity=0.0, max_intensity=1.0)
+        sol.use_cuda_graph = graph
+        sol.graph_capture_after = 0
+        init = sol.get_init_output(conv, x)
+        for t in ts:
+            t.init_parameters()
+        if start is None:
+            start = [t.param.detach().clone() for t in ts]
+        for n_iter in (1, 2):
+            for t, p in zip(ts, start):
+                t.param = p.clone()
+            sol.optimizing_transform(model=conv, data=x, init_output=init, optimize_flags=[True, True], n_iter=n_iter,
+                                     step_sizes=[1.0, 1.0])
+        if graph:
+            st = [v for v in sol._graphs.values() if isinstance(v, dict) and v["refs"][1]() is ts[0]][-1]
+        res.append([t.param.detach().clone() for t in ts])
+    assert st is not None and not st["publish"]
+    assert sorted(k[1] for k in st["graphs"]) == ["norm", "single"]
+    assert getattr(sol, "graph_replays", 0) == 3 and getattr(sol, "graph_redos", 0) == 0
+    for a, b in zip(res[0], res[1]):
+        assert float((a - b).norm() / a.norm()) < 2e-3
+
+
 def test_graph_loop_early_verdict_sequence():
     """The graph loop's one wait per call ends when the replay PUBLISHES its step-count verdict (one word in
     pinned host memory, advk_publish_verdict), not when the replay ends.  Every replay bumps a device-side
