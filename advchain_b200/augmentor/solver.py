@@ -716,8 +716,8 @@ class ComposeAdversarialTransformSolver(object):
                 st["src_" + name] = (src.detach(), src._version, ident)
         if anatomy is not None:
             st["anatomy"].copy_(anatomy[0].detach())
-        # start parameters -> static buffers in ONE multi-tensor launch (this runs with the GPU idle behind the
-        # previous call's synchronisation; the violation counter is cumulative: no zeroing launch either)
+        # start parameters -> static buffers in ONE multi-tensor launch, enqueued behind the previous call's replay
+        # (which is usually still running); the violation counter is cumulative: no zeroing launch either
         try:
             torch._foreach_copy_(st["params"], start)
         except (AttributeError, RuntimeError):
