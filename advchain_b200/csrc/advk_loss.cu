@@ -393,6 +393,66 @@ loss_contour_fused_kernel(Dims g, int K, int nzc, const float* __restrict__ E, c
   if (threadIdx.x == 0) atomicAdd(acc + 1, (double)v[0]);
 }
 
+// 2-D form of the one-pass contour kernel: one plane, so no register windows -- E on tile + 2-voxel halo, R on
+// tile + 1-voxel halo in shared memory, the adjoint stencils at the tile's own voxels.  Same arithmetic per cell as
+// loss_contour_kernel<2> / loss_contour_adj_kernel<2> (kx = h(H) hp(W), ky = hp(H) h(W)).
+__global__ void __launch_bounds__(LT_X * LT_Y)
+loss_contour_fused2d_kernel(Dims g, int K, const float* __restrict__ E, const float* __restrict__ mask,
+                            float* __restrict__ Sg, double* __restrict__ acc) {
+  pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
+  constexpr int NT = LT_X * LT_Y;
+  __shared__ float et[LF_EN];
+  __shared__ float rt[2][LF_RN];
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int tx = tid % LT_X, ty = tid / LT_X;
+  const int nc = blockIdx.z;
+  const int n = nc / (K - 1), c = 1 + nc % (K - 1);
+  const int x0 = blockIdx.x * LT_X, y0 = blockIdx.y * LT_Y;
+  const int x = x0 + tx, y = y0 + ty;
+  const float* e = E + ((i64)n * K + c) * g.S;
+  const float* mk = mask ? mask + (i64)n * g.S : nullptr;
+  float* so = Sg + ((i64)n * (K - 1) + (c - 1)) * g.S;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ie = tid + j * NT;
+    if (ie < LF_EN) {
+      const int ely = ie / LF_EX, elx = ie - ely * LF_EX;
+      const int gy = y0 + ely - 2, gx = x0 + elx - 2;
+      et[ie] = (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) ? __ldg(e + gy * g.W + gx) : 0.f;
+    }
+  }
+  __syncthreads();
+  float v[1] = {0.f};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ir = tid + j * NT;
+    if (ir < LF_RN) {
+      const int rly = ir / LF_RX, rlx = ir - rly * LF_RX;
+      const int gy = y0 + rly - 1, gx = x0 + rlx - 1;
+      float R0 = 0.f, R1 = 0.f;
+      if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
+        float a, b;
+        sobel_plane_w<LF_EX>(et, rlx, rly, a, b);
+        const float m = mk ? __ldg(mk + gy * g.W + gx) : 1.f;
+        const float a0 = m * b, a1 = m * a;                  // kx = h(H) hp(W) = b,  ky = hp(H) h(W) = a
+        if (rly >= 1 && rly <= LT_Y && rlx >= 1 && rlx <= LT_X) v[0] += a0 * a0 + a1 * a1;
+        R0 = m * a0;
+        R1 = m * a1;
+      }
+      rt[0][ir] = R0;
+      rt[1][ir] = R1;
+    }
+  }
+  __syncthreads();
+  float a0, b0, a1, b1;
+  sobel_plane_w<LF_RX>(rt[0], tx, ty, a0, b0);
+  sobel_plane_w<LF_RX>(rt[1], tx, ty, a1, b1);
+  if (x < g.W && y < g.H) so[(i64)y * g.W + x] = -(b0 + a1);   // kx-stencil(R0) + ky-stencil(R1)
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(acc + 1, (double)v[0]);
+}
+
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, float a_mse, float a_cont, float a_kl,
                                      float* __restrict__ loss) {
   pdl_wait(); pdl_trigger();   // programmatic dependent launch: see launch_pdl (advk_common.cuh)
@@ -477,8 +537,8 @@ loss_grad_kernel(i64 S, int Krt, const float* __restrict__ E, const float* __res
 
 using namespace advk;
 
-// 1 (default; environment ADVK_LOSS_FUSED): 3-D contour term by loss_contour_fused_kernel; 0: the two-kernel
-// predecessor.  Must not change between a forward call and the backward call that consumes its scratch.
+// 1 (default; environment ADVK_LOSS_FUSED): contour term by loss_contour_fused_kernel / loss_contour_fused2d_kernel;
+// 0: the two-kernel predecessor.  Must not change between a forward call and the backward call that consumes its scratch.
 static int g_loss_fused = -1;
 static int loss_fused() {
   if (g_loss_fused < 0) {
@@ -540,7 +600,8 @@ extern "C" int advk_consistency_loss_fwd(const advk_geom* gg, int K, const float
   if (K > 1 && w_contour != 0.f) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));
-    if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
+    if (gg->d == 2 && loss_fused()) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_fused2d_kernel), grid2, LT_X * LT_Y, 0, st, g, K, E, mask, R, acc));
+    else if (gg->d == 2) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<2>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
     else if (loss_fused()) ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_fused_kernel), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
     else ADVK_LAUNCH(K_loss_contour, st, launch_pdl((loss_contour_kernel<3>), grid2, LT_X * LT_Y, 0, st, g, K, nzc, E, mask, R, acc));
   }
@@ -563,7 +624,7 @@ extern "C" int advk_consistency_loss_bwd(const advk_geom* gg, int K, const float
   float a_mse, a_cont, a_kl;
   loss_scales(g, K, gg->d, w_mse, w_contour, w_kl, a_mse, a_cont, a_kl);
   if (K <= 1) a_cont = 0.f;
-  const bool fused = gg->d == 3 && loss_fused();            // the forward left s_c where R would have been
+  const bool fused = loss_fused() != 0;                     // the forward left s_c where R would have been
   if (a_cont != 0.f && !fused) {
     const int nzc = (gg->d == 3) ? (g.D + LT_Z - 1) / LT_Z : 1;
     dim3 grid2((g.W + LT_X - 1) / LT_X, (g.H + LT_Y - 1) / LT_Y, (unsigned)(g.N * (K - 1) * nzc));

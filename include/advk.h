@@ -340,7 +340,7 @@ int advk_chain_apply_bwd(const advk_chain_desc* d, const float* g_out, const flo
  * floats, 8-byte aligned; it carries the softmax / edge maps from fwd to bwd.  loss: 1 float
  * (device).  bwd: upstream = device pointer to dL/dloss (NULL = 1); g_output N x K x S, written. */
 size_t advk_loss_scratch_floats(const advk_geom* g, int K);
-/* 1 (default; environment ADVK_LOSS_FUSED): the 3-D contour term and its adjoint run as ONE z-marching kernel in
+/* 1 (default; environment ADVK_LOSS_FUSED): the contour term and its adjoint run as ONE kernel (3-D: z-marching) in
  * the forward call (the Sobel responses stay in shared memory, the adjoint s_c is left in `scratch` for the
  * backward call); 0: the two-kernel predecessor (responses written by fwd, adjoint applied by bwd).  Same
  * results.  A negative value only queries; returns the previous setting.  Must not change between a forward

@@ -389,11 +389,12 @@ def test_consistency_loss(d, size, types, weights, masked, is_gt):
     assert rel_err(o1.grad, 3.0 * o0.grad) < 2e-5
 
 
-@pytest.mark.parametrize("size", [[2, 4, 37, 21, 45], [1, 3, 16, 40, 64], [1, 2, 5, 9, 33]])
+@pytest.mark.parametrize("size", [[2, 4, 37, 21, 45], [1, 3, 16, 40, 64], [1, 2, 5, 9, 33], [2, 4, 37, 53], [1, 3, 64, 96],
+                                  [3, 2, 7, 5]])
 @pytest.mark.parametrize("masked", [False, True])
 def test_consistency_loss_fused_contour_is_the_two_kernel_result(size, masked):
-    """3-D contour term: the one-pass kernel (Sobel responses + their adjoint on a z-marching tile with a 2-voxel
-    halo, the default) against its two-kernel predecessor (advk_loss_tune(0)): the same arithmetic per cell, so the
+    """Contour term: the one-pass kernel (Sobel responses + their adjoint on a tile with a 2-voxel halo, marching
+    in z in 3-D; the default) against its two-kernel predecessor (advk_loss_tune(0)): the same arithmetic per cell, so the
     gradient is bit-identical and the loss differs by the order of its double-precision partial sums only."""
     from advchain_b200 import _lib
     from advchain_b200.common.loss import calc_segmentation_consistency
